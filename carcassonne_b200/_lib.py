@@ -1,0 +1,86 @@
+"""ctypes binding of libcarc_b200.so (include/carc_b200.h).
+
+There is no CPU fallback: if the shared library has not been built (``python -c "import __graft_entry__ as g;
+g.build()"`` or ``make -C carcassonne_b200/csrc``) importing this module fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcarc_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "carcassonne_b200: %s is missing -- build the CUDA library first (make -C carcassonne_b200/csrc); "
+        "there is no CPU fallback." % LIB_PATH
+    )
+
+lib = C.CDLL(LIB_PATH)
+
+c_i64 = C.c_int64
+c_int = C.c_int
+c_vp = C.c_void_p
+c_dp = C.POINTER(C.c_double)
+c_i64p = C.POINTER(C.c_int64)
+c_i32p = C.POINTER(C.c_int32)
+
+#: every symbol include/carc_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "carc_version": (c_int, []),
+    "carc_last_error": (C.c_char_p, []),
+    "carc_dmma_peak": (c_int, [c_int, c_dp, c_vp]),
+    "carc_malloc": (c_int, [C.POINTER(c_vp), C.c_size_t]),
+    "carc_free": (c_int, [c_vp]),
+    "carc_malloc_host": (c_int, [C.POINTER(c_vp), C.c_size_t]),
+    "carc_free_host": (c_int, [c_vp]),
+    "carc_memcpy_h2d": (c_int, [c_vp, c_vp, C.c_size_t, c_vp]),
+    "carc_memcpy_d2h": (c_int, [c_vp, c_vp, C.c_size_t, c_vp]),
+    "carc_stream_synchronize": (c_int, [c_vp]),
+    "carc_permute": (c_int, [c_vp, c_vp, c_int, c_i64p, c_i32p, c_int, c_int, c_vp]),
+    "carc_axpby": (c_int, [c_i64, c_dp, c_vp, c_dp, c_vp, c_int, c_vp]),
+    "carc_mul": (c_int, [c_i64, c_vp, c_vp, c_vp]),
+    "carc_dotc": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "carc_sumsq": (c_int, [c_i64, c_vp, c_vp, c_vp]),
+    "carc_count_nonfinite": (c_int, [c_i64, c_vp, c_vp, c_vp]),
+    "carc_zgemm": (c_int, [c_int, c_int, c_i64, c_i64, c_i64, c_dp, c_vp, c_i64, c_vp, c_i64, c_dp, c_vp,
+                           c_i64p, c_i64p, c_i64, c_i64, c_i64, c_i64, c_vp]),
+    "carc_operator_create": (c_int, [C.POINTER(c_vp), c_int, c_int, c_int, c_int, c_int]),
+    "carc_operator_add_term": (c_int, [c_vp, c_vp, c_vp, c_i64, c_dp]),
+    "carc_operator_finalize": (c_int, [c_vp]),
+    "carc_operator_apply": (c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "carc_operator_set_path": (c_int, [c_vp, c_int]),
+    "carc_operator_num_terms": (c_int, [c_vp]),
+    "carc_operator_cost_of_multiply": (c_i64, [c_vp]),
+    "carc_operator_destroy": (c_int, [c_vp]),
+    "carc_stage3_matvec_host": (c_int, [c_int, C.POINTER(c_vp), C.POINTER(c_vp), c_i64p, C.POINTER(c_dp),
+                                        c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _f = getattr(lib, _name)
+    _f.restype = _res
+    _f.argtypes = _args
+
+# error codes (include/carc_b200.h)
+OK, ERR_CUDA, ERR_DIMENSION_MISMATCH, ERR_RANK, ERR_VALUE, ERR_RELAX_FAILED, ERR_INVARIANT, ERR_NO_CONVERGENCE, \
+    ERR_UNSUPPORTED = range(9)
+OP_N, OP_T, OP_C, OP_J = range(4)
+
+
+class CarcError(RuntimeError):
+    def __init__(self, code, message):
+        RuntimeError.__init__(self, "libcarc_b200 error {}: {}".format(code, message))
+        self.code = code
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib.carc_last_error().decode("utf-8", "replace")
+        if rc == ERR_VALUE:
+            raise ValueError(msg)
+        raise CarcError(rc, msg)
+
+
+def cplx2(z):
+    z = complex(z)
+    return (C.c_double * 2)(z.real, z.imag)

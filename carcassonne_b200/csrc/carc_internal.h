@@ -1,0 +1,51 @@
+// Internal C++ interface between the translation units of libcarc_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define CARC_MAX_RANK 12
+
+namespace carc {
+typedef double2 cplx;
+
+const char* get_error();
+
+// tensor_ops.cu
+int permute(const cplx* src, cplx* dst, int ndim, const int64_t* shape, const int32_t* perm, int conj, int accumulate,
+            cudaStream_t stream);
+int axpby(int64_t n, cplx alpha, const cplx* x, cplx beta, cplx* y, int conj_x, cudaStream_t stream);
+int mul_inplace(int64_t n, const cplx* x, cplx* y, cudaStream_t stream);
+int reduce(int mode, int64_t n, const cplx* x, const cplx* y, double2* out_dev, cudaStream_t stream);
+
+// zgemm.cu
+enum Op { OP_N = 0, OP_T = 1, OP_C = 2, OP_J = 3 };
+// C[M,N] = alpha * op(A) * op(B) + beta * C, row-major storage.
+//   opA: N  A stored [M,K] (lda >= K);  T  stored [K,M] (lda >= M);  C  stored [K,M], conjugated;  J  [M,K] conjugated
+//   opB: N  B stored [K,N] (ldb >= N);  T  stored [N,K] (ldb >= K);  C  stored [N,K], conjugated;  J  [K,N] conjugated
+// The output element (m, n) is written at C + (m / m_div) * m_s1 + (m % m_div) * m_s0 + (n / n_div) * n_s1 +
+// (n % n_div) * n_s0, so a GEMM can write straight into a permuted ("joined") layout.
+struct GemmOut {
+  int64_t m_div, m_s1, m_s0, n_div, n_s1, n_s0;
+};
+struct GemmKMap {
+  int64_t a_kdiv, a_ks1, b_kdiv, b_ks1;
+};
+int zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, cplx alpha, const cplx* A, int64_t lda, const cplx* B,
+          int64_t ldb, cplx beta, cplx* C, const GemmOut* out, const GemmKMap* kmap, int64_t batch, int64_t strideA,
+          int64_t strideB, int64_t strideC, cudaStream_t stream);
+int dmma_peak(int iters, double* tflops_out, cudaStream_t stream);
+
+// stage3.cu
+struct Stage3Term {
+  const cplx* A;   // [X, P, Q]   (pre-joined stage-2 half 0: [(x y), D0*, D1*, D0, D1])
+  const cplx* B;   // [X, R, S]   (pre-joined stage-2 half 1: [(y' x'), D2*, D3*, D2, D3])
+  int64_t X;
+  int has_op;      // 0: identity on the physical leg
+  cplx op[16];     // row-major d x d site operator O[s', s]
+};
+int stage3_apply(const Stage3Term* terms_host, const Stage3Term* terms_dev, int nterms, int P, int Q, int R, int S,
+                 int d, const cplx* v, cplx* out, cplx* workspace, int64_t workspace_elems, int force_path,
+                 cudaStream_t stream);
+int64_t stage3_workspace_elems(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax);
+
+}  // namespace carc

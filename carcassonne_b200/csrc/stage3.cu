@@ -1,0 +1,460 @@
+// Fused center-site matvec ("stage 3") for sm_100a.
+//
+//   out[P,R,s] = sum_t sum_x sum_S B_t[x,R,S] * ( sum_s' O_t[s,s'] * ( sum_Q A_t[x,P,Q] * v[Q,S,s'] ) )
+//
+// with A_t = [(x y), D0*, D1*, D0, D1] and B_t = [(y' x'), D2*, D3*, D2, D3] the pre-joined stage-2 halves,
+// P = Q = D0*D1, R = S = D2*D3 (reference tensors/_2d/dense.py:115-160: t = A.(3,4)*v.(0,1);
+// out = B.(3,4,0)*t.(3,4,0); join [2][3][0][1][4]; the operator variant applies O to v's physical leg first;
+// tensors/_2d/sparse.py:129-133 sums the terms).
+//
+// The reference runs this as two ZGEMMs per term with the X*P*S*d intermediate spilled to memory plus two full
+// transposing copies.  Here the intermediate never leaves registers: for every environment index x a warp that
+// owns 8 rows of P computes a 8 x 8 tile of A_x v with DMMA, folds the site operator in on the accumulator
+// fragments (coefficients that are exactly zero -- Pauli structure -- are skipped), and immediately uses the
+// result as the A operand of the second DMMA chain against B_x: the C-fragment of m8n8k4 maps onto its A-fragment
+// when the K index of the second product is taken in the order {2c+e}, so no shuffle is needed.
+//
+// A_x (contiguous P*Q block) and the S-block of B_x (R rows) are brought in by TMA bulk copies
+// (cp.async.bulk -> UBLKCP) into a multi-stage ring guarded by mbarriers.  There is no dedicated producer warp:
+// the register file is split per SM sub-partition (16K registers each), so a 9th warp would cap every thread at
+// 170 registers; instead warp 0 of each consumer group runs a second cursor one item ahead and issues the copies.
+// Work decomposition: CTA = (S block of 16 columns, slab of x); inside a CTA, G independent consumer groups of
+// ceil(P/8) warps take interleaved x.  Every (CTA, group) writes one partial result; a second kernel sums the
+// partials in a fixed order, so the result is deterministic.
+#include <algorithm>
+
+#include "carc_internal.h"
+#include "common.cuh"
+
+namespace carc {
+
+namespace {
+
+constexpr int SBW = 16;        // S-block width (two 8-wide chunks)
+constexpr int BSTR = SBW + 1;  // row stride of the staged B block (odd -> conflict-free paired loads)
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+struct S3Params {
+  const Stage3Term* terms;  // device copy
+  int nterms;
+  int P, Q, R, S;
+  int Q8, NPT, G, NSB, NSL, nstA, nstB;
+  uint32_t slotA_bytes, slotB_bytes, ops_off, vt_off, ring_off, smem_total;
+  const cplx* v;
+  cplx* partial;
+};
+
+// threads per CTA are a multiple of 128 (one warp per sub-partition): 2 / 3 / 4 warps per sub-partition leave
+// 255 / 170 / 128 registers per thread
+__host__ __device__ constexpr int s3_max_threads(int nrt) {
+  return nrt >= 5 ? 256 : (nrt >= 3 ? 384 : 512);
+}
+
+template <int NRT, int DP>
+__global__ void __launch_bounds__(s3_max_threads(NRT), 1) stage3_kernel(const S3Params p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = lane >> 2, c = lane & 3;
+  const int ncw = p.G * p.NPT;
+  const int nbar_g = 2 * (p.nstA + p.nstB);
+  const uint32_t bars = smem_u32(smem);
+  cplx* ops = reinterpret_cast<cplx*>(smem + p.ops_off);
+  cplx* Vt = reinterpret_cast<cplx*>(smem + p.vt_off);
+  const int QS = p.Q8 * 8 + 1;
+  const uint32_t group_bytes = p.nstA * p.slotA_bytes + p.nstB * p.slotB_bytes;
+
+  // zero everything behind the barriers: padding rows / columns must read as finite zeros forever
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem + p.ops_off);
+    const uint32_t n16 = (p.smem_total - p.ops_off) / 16;
+    for (uint32_t i = tid; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (tid == 0) {
+    for (int g = 0; g < p.G; ++g) {
+      const uint32_t b = bars + g * nbar_g * 8;
+      for (int i = 0; i < p.nstA; ++i) {
+        mbar_init(b + (2 * i) * 8, 1);           // full A
+        mbar_init(b + (2 * i + 1) * 8, p.NPT);   // empty A
+      }
+      for (int i = 0; i < p.nstB; ++i) {
+        mbar_init(b + (2 * p.nstA + 2 * i) * 8, 1);
+        mbar_init(b + (2 * p.nstA + 2 * i + 1) * 8, p.NPT);
+      }
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  const int sb = blockIdx.x % p.NSB, sl = blockIdx.x / p.NSB;
+  const int S0 = sb * SBW;
+  const int SBv = min(SBW, p.S - S0);
+  for (int i = tid; i < p.nterms * DP * DP; i += blockDim.x) ops[i] = p.terms[i / (DP * DP)].op[i % (DP * DP)];
+  for (int i = tid; i < p.Q * SBv * DP; i += blockDim.x) {
+    const int sp = i % DP, sc = (i / DP) % SBv, q = i / (DP * SBv);
+    Vt[(sp * SBW + sc) * QS + q] = p.v[((int64_t)q * p.S + S0 + sc) * DP + sp];
+  }
+  fence_proxy_async();
+  __syncthreads();
+
+  if (warp >= ncw) return;
+  {
+    const int g = warp / p.NPT, wg = warp % p.NPT;
+    const uint32_t b = bars + g * nbar_g * 8;
+    const uint32_t ring = smem_u32(smem + p.ring_off) + g * group_bytes;
+    CTile acc[NRT][DP];
+#pragma unroll
+    for (int i = 0; i < NRT; ++i)
+#pragma unroll
+      for (int s = 0; s < DP; ++s) acc[i][s].zero();
+
+    const bool eswap = ((p.Q & 1) == 0) && (r & 1);
+    const uint32_t a_lane_off = (uint32_t)(((wg * 8 + r) * p.Q + 2 * c) * 16);
+    const uint32_t a_first = eswap ? 16u : 0u, a_second = 16u - a_first;
+    const uint32_t v_base = smem_u32(Vt) + (uint32_t)((r * QS + 2 * c) * 16);
+    const uint32_t b_lane_off = (uint32_t)((r * BSTR + 2 * c) * 16);
+
+    // item cursors: (term, x) pairs of this (CTA slab, group); the producer cursor runs ahead of the consumer
+    struct Cursor {
+      int t;
+      int64_t x, x_hi;
+    };
+    auto next = [&](Cursor& cu) -> bool {
+      cu.x += p.G;
+      while (cu.x >= cu.x_hi) {
+        if (++cu.t >= p.nterms) return false;
+        const int64_t X = p.terms[cu.t].X;
+        cu.x = X * sl / p.NSL + g;
+        cu.x_hi = X * (sl + 1) / p.NSL;
+      }
+      return true;
+    };
+    const uint32_t a_bytes = (uint32_t)(p.P * p.Q * 16);
+    const uint32_t b_row_bytes = (uint32_t)(SBv * 16);
+    auto issue = [&](const Cursor& cu, uint32_t it) {
+      const cplx* A = p.terms[cu.t].A;
+      const cplx* B = p.terms[cu.t].B;
+      const int sa = it % p.nstA, sbq = it % p.nstB;
+      const uint32_t fullA = b + (2 * sa) * 8, fullB = b + (2 * p.nstA + 2 * sbq) * 8;
+      if (lane == 0) {
+        mbar_wait(fullA + 8, ((it / p.nstA) & 1) ^ 1);
+        mbar_arrive_expect_tx(fullA, a_bytes);
+        bulk_g2s(ring + sa * p.slotA_bytes, A + cu.x * (int64_t)p.P * p.Q, a_bytes, fullA);
+        mbar_wait(fullB + 8, ((it / p.nstB) & 1) ^ 1);
+        mbar_arrive_expect_tx(fullB, b_row_bytes * p.R);
+      }
+      __syncwarp();
+      const uint32_t dst = ring + p.nstA * p.slotA_bytes + sbq * p.slotB_bytes;
+      const cplx* src = B + (cu.x * p.R) * (int64_t)p.S + S0;
+      for (int rr = lane; rr < p.R; rr += 32) bulk_g2s(dst + rr * BSTR * 16, src + (int64_t)rr * p.S, b_row_bytes, fullB);
+    };
+
+    Cursor cc = {-1, 0, 0}, pc = {-1, 0, 0};
+    uint32_t issued = 0;
+    bool more = true;
+    if (wg == 0) {
+      for (int k = 0; k < p.nstA - 1 && more; ++k) {
+        more = next(pc);
+        if (more) issue(pc, issued++);
+      }
+    }
+    uint32_t it = 0;
+    int cur_t = -1;
+    bool has_op = false;
+
+    while (next(cc)) {
+      if (wg == 0 && more) {
+        more = next(pc);
+        if (more) issue(pc, issued++);
+      }
+      if (cc.t != cur_t) {
+        cur_t = cc.t;
+        has_op = p.terms[cur_t].has_op != 0;
+      }
+      CTile T[2][DP];
+      // ---- first product: U = A_x v  (8 rows of P, this S block), then T = O U
+      {
+        const int slot = it % p.nstA;
+        mbar_wait(b + (2 * slot) * 8, (it / p.nstA) & 1);
+        const uint32_t a_base = ring + slot * p.slotA_bytes + a_lane_off;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          CTile U[DP];
+#pragma unroll
+          for (int s = 0; s < DP; ++s) U[s].zero();
+#pragma unroll 2
+          for (int kp = 0; kp < p.Q8; ++kp) {
+            const cplx x0 = lds_c(a_base + kp * 128 + a_first);
+            const cplx x1 = lds_c(a_base + kp * 128 + a_second);
+            const cplx a0 = eswap ? x1 : x0;
+            const cplx a1 = eswap ? x0 : x1;
+#pragma unroll
+            for (int s = 0; s < DP; ++s) {
+              const uint32_t va = v_base + (uint32_t)((((s * SBW + ch * 8) * QS) + kp * 8) * 16);
+              const cplx b0 = lds_c(va);
+              const cplx b1 = lds_c(va + 16);
+              cmma(U[s], a0.x, a0.y, -a0.y, b0.x, b0.y);
+              cmma(U[s], a1.x, a1.y, -a1.y, b1.x, b1.y);
+            }
+          }
+          if (!has_op) {
+#pragma unroll
+            for (int s = 0; s < DP; ++s) T[ch][s] = U[s];
+          } else {
+#pragma unroll
+            for (int s = 0; s < DP; ++s) {
+              T[ch][s].zero();
+#pragma unroll
+              for (int s2 = 0; s2 < DP; ++s2) {
+                const cplx w = ops[cur_t * DP * DP + s * DP + s2];
+                if (w.x != 0.0 || w.y != 0.0) {
+                  T[ch][s].re0 += w.x * U[s2].re0 - w.y * U[s2].im0;
+                  T[ch][s].im0 += w.x * U[s2].im0 + w.y * U[s2].re0;
+                  T[ch][s].re1 += w.x * U[s2].re1 - w.y * U[s2].im1;
+                  T[ch][s].im1 += w.x * U[s2].im1 + w.y * U[s2].re1;
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b + (2 * slot + 1) * 8);
+      }
+      // ---- second product: acc += T * B_x^T ; T's C fragments are the A fragments
+      {
+        const int slot = it % p.nstB;
+        mbar_wait(b + (2 * p.nstA + 2 * slot) * 8, (it / p.nstB) & 1);
+        const uint32_t b_base = ring + p.nstA * p.slotA_bytes + slot * p.slotB_bytes + b_lane_off;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+          for (int rt = 0; rt < NRT; ++rt) {
+            const uint32_t ba = b_base + (uint32_t)(((rt * 8) * BSTR + ch * 8) * 16);
+            const cplx b0 = lds_c(ba);
+            const cplx b1 = lds_c(ba + 16);
+#pragma unroll
+            for (int s = 0; s < DP; ++s) {
+              cmma(acc[rt][s], T[ch][s].re0, T[ch][s].im0, -T[ch][s].im0, b0.x, b0.y);
+              cmma(acc[rt][s], T[ch][s].re1, T[ch][s].im1, -T[ch][s].im1, b1.x, b1.y);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b + (2 * p.nstA + 2 * slot + 1) * 8);
+      }
+      ++it;
+    }
+    // ---- partial result of this (CTA, group)
+    cplx* part = p.partial + ((int64_t)blockIdx.x * p.G + g) * ((int64_t)p.P * p.R * DP);
+    const int row = wg * 8 + r;
+    if (row < p.P) {
+#pragma unroll
+      for (int rt = 0; rt < NRT; ++rt) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int col = rt * 8 + 2 * c + h;
+          if (col < p.R) {
+#pragma unroll
+            for (int s = 0; s < DP; ++s) {
+              cplx val;
+              val.x = h ? acc[rt][s].re1 : acc[rt][s].re0;
+              val.y = h ? acc[rt][s].im1 : acc[rt][s].im0;
+              part[((int64_t)row * p.R + col) * DP + s] = val;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// out[i] = sum_slots partial[slot][i]  (fixed order -> deterministic)
+__global__ void __launch_bounds__(256) s3_reduce_kernel(const cplx* __restrict__ partial, cplx* __restrict__ out,
+                                                        int64_t n, int slots, int accumulate) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double re = 0.0, im = 0.0;
+  for (int s = 0; s < slots; ++s) {
+    const cplx v = partial[(int64_t)s * n + i];
+    re += v.x;
+    im += v.y;
+  }
+  if (accumulate) {
+    re += out[i].x;
+    im += out[i].y;
+  }
+  out[i] = make_double2(re, im);
+}
+
+struct S3Config {
+  int NPT, NRT, Q8, NSB, NSL, G, nstA, nstB;
+  uint32_t slotA, slotB, ops_off, vt_off, ring_off, total;
+  int threads, slots;
+};
+
+bool s3_configure(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, S3Config* cfg) {
+  if (d != 2) return false;
+  if (P > 64 || R > 64 || P < 1 || R < 1) return false;
+  S3Config k;
+  k.NPT = (P + 7) / 8;
+  k.NRT = (R + 7) / 8;
+  k.Q8 = (Q + 7) / 8;
+  k.NSB = (S + SBW - 1) / SBW;
+  const int maxwarps = s3_max_threads(k.NRT) / 32;
+  if (k.NPT > maxwarps) return false;
+  k.slotA = (uint32_t)((k.NPT * 8 * Q + 8) * 16);
+  k.slotB = (uint32_t)(k.NRT * 8 * BSTR * 16);
+  const int QS = k.Q8 * 8 + 1;
+  const uint32_t vbytes = (uint32_t)(d * SBW * QS * 16);
+  const uint32_t obytes = (uint32_t)(nterms * d * d * 16);
+  int G = std::min(8, maxwarps / k.NPT);
+  if (Xmax < G) G = (int)std::max<int64_t>(1, Xmax);
+  for (; G >= 1; --G) {
+    for (int nstA = 3; nstA >= 2; --nstA) {
+      for (int nstB = 4; nstB >= nstA; --nstB) {
+        const uint32_t bar_bytes = (uint32_t)(((G * 2 * (nstA + nstB) * 8) + 127) / 128 * 128);
+        const uint32_t ops_off = bar_bytes;
+        const uint32_t vt_off = (ops_off + obytes + 127) / 128 * 128;
+        const uint32_t ring_off = (vt_off + vbytes + 127) / 128 * 128;
+        const uint64_t total = (uint64_t)ring_off + (uint64_t)G * ((uint64_t)nstA * k.slotA + (uint64_t)nstB * k.slotB);
+        if (total <= SMEM_LIMIT) {
+          k.G = G;
+          k.nstA = nstA;
+          k.nstB = nstB;
+          k.ops_off = ops_off;
+          k.vt_off = vt_off;
+          k.ring_off = ring_off;
+          k.total = (uint32_t)total;
+          k.threads = G * k.NPT * 32;
+          int64_t nsl = std::max<int64_t>(1, 148 / k.NSB);
+          nsl = std::min<int64_t>(nsl, std::max<int64_t>(1, Xmax / G));
+          k.NSL = (int)nsl;
+          k.slots = k.NSB * k.NSL * G;
+          *cfg = k;
+          return true;
+        }
+      }
+    }
+  }
+  return false;
+}
+
+template <int NRT>
+int s3_launch(const S3Params& p, const S3Config& k, cudaStream_t stream) {
+  static bool configured[16] = {false};
+  int dev = 0;
+  CARC_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 16 && !configured[dev]) {
+    CARC_CHECK_CUDA(
+        cudaFuncSetAttribute(stage3_kernel<NRT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    configured[dev] = true;
+  }
+  stage3_kernel<NRT, 2><<<k.NSB * k.NSL, k.threads, k.total, stream>>>(p);
+  CARC_CHECK_CUDA(cudaGetLastError());
+  return CARC_OK;
+}
+
+// Unfused device path (any P, R, d): three DMMA GEMMs per term and x chunk, the intermediate written directly in
+// the layout the second GEMM wants through the generalised output map -- no transposing copies.
+int s3_unfused(const Stage3Term* terms, int nterms, int P, int Q, int R, int S, int d, const cplx* v, cplx* out,
+               cplx* ws, int64_t ws_elems, cudaStream_t stream) {
+  const cplx one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0);
+  const int64_t n = (int64_t)P * R * d;
+  const int64_t wsize = (int64_t)Q * S * d;
+  CARC_REQUIRE(ws_elems >= wsize + (int64_t)P * S * d, CARC_ERR_VALUE, "stage3: workspace too small");
+  cplx* W = ws;
+  cplx* T = ws + wsize;
+  const int64_t tcap = ws_elems - wsize;
+  CARC_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(cplx) * n, stream));
+  for (int t = 0; t < nterms; ++t) {
+    const cplx* w = v;
+    if (terms[t].has_op) {
+      // W[(Q S), s'] = sum_s v[(Q S), s] * O[s', s]
+      cplx* opdev = T;  // borrow the head of T for the d x d operator
+      CARC_CHECK_CUDA(cudaMemcpyAsync(opdev, terms[t].op, sizeof(cplx) * d * d, cudaMemcpyHostToDevice, stream));
+      int rc = zgemm(OP_N, OP_T, (int64_t)Q * S, d, d, one, v, d, opdev, d, zero, W, nullptr, nullptr, 1, 0, 0, 0, stream);
+      if (rc) return rc;
+      w = W;
+    }
+    const int64_t X = terms[t].X;
+    int64_t xc = std::max<int64_t>(1, tcap / ((int64_t)P * S * d));
+    for (int64_t x0 = 0; x0 < X; x0 += xc) {
+      const int64_t nx = std::min(xc, X - x0);
+      // T'[p, s, x, S] = sum_q A[(x p), q] * w[q, (S s)]
+      GemmOut o1;
+      o1.m_div = P; o1.m_s1 = S; o1.m_s0 = (int64_t)d * nx * S;
+      o1.n_div = d; o1.n_s1 = 1; o1.n_s0 = nx * S;
+      int rc = zgemm(OP_N, OP_N, nx * P, (int64_t)S * d, Q, one, terms[t].A + x0 * P * Q, Q, w, (int64_t)S * d, zero, T,
+                     &o1, nullptr, 1, 0, 0, 0, stream);
+      if (rc) return rc;
+      // out[p, r, s] += sum_{(x S)} T'[(p s), (x S)] * B[x, r, S]
+      GemmOut o2;
+      o2.m_div = d; o2.m_s1 = (int64_t)R * d; o2.m_s0 = 1;
+      o2.n_div = R; o2.n_s1 = 0; o2.n_s0 = d;
+      GemmKMap km;
+      km.a_kdiv = 0; km.a_ks1 = 0; km.b_kdiv = S; km.b_ks1 = (int64_t)R * S;
+      rc = zgemm(OP_N, OP_T, (int64_t)P * d, R, nx * S, one, T, nx * S, terms[t].B + x0 * R * S, S, one, out, &o2, &km, 1,
+                 0, 0, 0, stream);
+      if (rc) return rc;
+    }
+  }
+  return CARC_OK;
+}
+
+}  // namespace
+
+int64_t stage3_workspace_elems(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax) {
+  S3Config k;
+  int64_t fused = 0;
+  if (s3_configure(nterms, P, Q, R, S, d, Xmax, &k)) fused = (int64_t)k.slots * P * R * d;
+  // unfused path: W + at least 64 MiB worth of intermediate (or the whole thing if smaller)
+  int64_t per_x = (int64_t)P * S * d;
+  int64_t t = std::min<int64_t>(Xmax * per_x, std::max<int64_t>(per_x, (64ll << 20) / 16));
+  int64_t unfused = (int64_t)Q * S * d + t;
+  return std::max(fused, unfused);
+}
+
+int stage3_apply(const Stage3Term* terms_host, const Stage3Term* terms_dev, int nterms, int P, int Q, int R, int S,
+                 int d, const cplx* v, cplx* out, cplx* workspace, int64_t workspace_elems, int force_path,
+                 cudaStream_t stream) {
+  CARC_REQUIRE(nterms >= 0 && P > 0 && Q > 0 && R > 0 && S > 0 && d > 0 && d <= 4, CARC_ERR_VALUE,
+               "stage3: invalid dimensions");
+  const int64_t n = (int64_t)P * R * d;
+  if (nterms == 0) {
+    CARC_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(cplx) * n, stream));
+    return CARC_OK;
+  }
+  int64_t Xmax = 0;
+  for (int t = 0; t < nterms; ++t) Xmax = std::max(Xmax, terms_host[t].X);
+  S3Config k;
+  const bool can_fuse = force_path != 2 && Xmax > 0 && s3_configure(nterms, P, Q, R, S, d, Xmax, &k);
+  CARC_REQUIRE(!(force_path == 1 && !can_fuse), CARC_ERR_UNSUPPORTED, "stage3: fused path unavailable for this shape");
+  if (!can_fuse) return s3_unfused(terms_host, nterms, P, Q, R, S, d, v, out, workspace, workspace_elems, stream);
+
+  CARC_REQUIRE(workspace_elems >= (int64_t)k.slots * n, CARC_ERR_VALUE, "stage3: workspace too small");
+  S3Params p;
+  p.terms = terms_dev;
+  p.nterms = nterms;
+  p.P = P; p.Q = Q; p.R = R; p.S = S;
+  p.Q8 = k.Q8; p.NPT = k.NPT; p.G = k.G; p.NSB = k.NSB; p.NSL = k.NSL; p.nstA = k.nstA; p.nstB = k.nstB;
+  p.slotA_bytes = k.slotA; p.slotB_bytes = k.slotB;
+  p.ops_off = k.ops_off; p.vt_off = k.vt_off; p.ring_off = k.ring_off; p.smem_total = k.total;
+  p.v = v;
+  p.partial = workspace;
+  int rc;
+  switch (k.NRT) {
+    case 1: rc = s3_launch<1>(p, k, stream); break;
+    case 2: rc = s3_launch<2>(p, k, stream); break;
+    case 3: rc = s3_launch<3>(p, k, stream); break;
+    case 4: rc = s3_launch<4>(p, k, stream); break;
+    case 5: rc = s3_launch<5>(p, k, stream); break;
+    case 6: rc = s3_launch<6>(p, k, stream); break;
+    case 7: rc = s3_launch<7>(p, k, stream); break;
+    default: rc = s3_launch<8>(p, k, stream); break;
+  }
+  if (rc) return rc;
+  s3_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(workspace, out, n, k.slots, 0);
+  CARC_CHECK_CUDA(cudaGetLastError());
+  return CARC_OK;
+}
+
+}  // namespace carc

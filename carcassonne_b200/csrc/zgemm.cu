@@ -1,0 +1,259 @@
+// Complex128 GEMM on the FP64 tensor pipe (DMMA.8x8x4) for sm_100a.
+//
+// This is the engine behind every pairwise contraction of the path that is not the fused stage-3 matvec:
+// NDArrayData.contractWith == numpy.tensordot -> OpenBLAS zgemm in the reference (data/__init__.py:157-159);
+// here: stage-1 / stage-2 environment builds, side->corner and center->side absorption, formMatrix, the
+// compression normal equations, absorbMatrixAt.
+//
+// Layout: CTA tile 128 x 64 x 16 (complex), 8 warps as 4 (M) x 2 (N), warp tile 32 x 32 = 4 x 4 DMMA tiles with
+// separate real / imaginary accumulators (128 registers).  Operands are staged by a 3-stage cp.async pipeline
+// into K-contiguous shared tiles with an odd row stride (17 complex) so that the paired fragment loads below
+// are bank-conflict free.  A complex MMA is four real DMMAs; the sign of the imaginary operand is flipped once
+// per fragment load (integer XOR on the sign bit), which is also how conjugated operands are handled.
+//
+// Fragment mapping: one 8-wide K chunk feeds two DMMA k-steps.  k-step e in {0,1} uses the K indices
+// {2c + e : c = lane % 4}, i.e. every lane reads two adjacent complex numbers (32 contiguous bytes) per
+// operand row.  Any permutation of K is legal as long as A and B use the same one.
+#include "carc_internal.h"
+#include "common.cuh"
+
+namespace carc {
+
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 16, STAGES = 3, LDK = BK + 1;
+constexpr int NTHREADS = 256;
+constexpr int SMEM_BYTES = STAGES * (BM + BN) * LDK * (int)sizeof(cplx);
+
+struct GemmParams {
+  const cplx* A;
+  const cplx* B;
+  cplx* C;
+  int64_t M, N, K, lda, ldb;
+  int64_t strideA, strideB, strideC;
+  int a_kcontig, b_kcontig;   // 1: K is the unit-stride axis of the stored operand
+  int64_t a_kdiv, a_ks1, b_kdiv, b_ks1;  // optional two-level K for K-contiguous operands (kdiv == 0: off):
+                                         // element k lives at (k / kdiv) * ks1 + (k % kdiv) within its row
+  uint32_t a_sign, b_sign;    // 0x80000000 to conjugate
+  cplx alpha, beta;
+  GemmOut out;
+};
+
+__device__ __forceinline__ double flip(double x, uint32_t mask) {
+  return __hiloint2double(__double2hiint(x) ^ (int)mask, __double2loint(x));
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) zgemm_kernel(GemmParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* As = reinterpret_cast<cplx*>(smem_raw);
+  cplx* Bs = As + STAGES * BM * LDK;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1;       // 4 x 2 warps
+  const int r = lane >> 2, c = lane & 3;
+  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+  const cplx* A = p.A + (int64_t)blockIdx.z * p.strideA;
+  const cplx* B = p.B + (int64_t)blockIdx.z * p.strideB;
+  cplx* C = p.C + (int64_t)blockIdx.z * p.strideC;
+
+  CTile acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j].zero();
+
+  const int64_t KT = (p.K + BK - 1) / BK;
+
+  auto load_tile = [&](int64_t kt, int stage) {
+    const int64_t k0 = kt * BK;
+    cplx* as = As + stage * BM * LDK;
+    cplx* bs = Bs + stage * BN * LDK;
+#pragma unroll
+    for (int it = 0; it < BM * BK / NTHREADS; ++it) {
+      int e = it * NTHREADS + tid;
+      int m, k;
+      if (p.a_kcontig) { m = e / BK; k = e % BK; } else { k = e / BM; m = e % BM; }
+      int64_t gm = m0 + m, gk = k0 + k;
+      bool ok = gm < p.M && gk < p.K;
+      if (p.a_kdiv) gk = (gk / p.a_kdiv) * p.a_ks1 + (gk % p.a_kdiv);
+      const cplx* src = ok ? (p.a_kcontig ? A + gm * p.lda + gk : A + gk * p.lda + gm) : A;
+      cp_async16(smem_u32(as + m * LDK + k), src, ok);
+    }
+#pragma unroll
+    for (int it = 0; it < BN * BK / NTHREADS; ++it) {
+      int e = it * NTHREADS + tid;
+      int n, k;
+      if (p.b_kcontig) { n = e / BK; k = e % BK; } else { k = e / BN; n = e % BN; }
+      int64_t gn = n0 + n, gk = k0 + k;
+      bool ok = gn < p.N && gk < p.K;
+      if (p.b_kdiv) gk = (gk / p.b_kdiv) * p.b_ks1 + (gk % p.b_kdiv);
+      const cplx* src = ok ? (p.b_kcontig ? B + gn * p.ldb + gk : B + gk * p.ldb + gn) : B;
+      cp_async16(smem_u32(bs + n * LDK + k), src, ok);
+    }
+  };
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < KT) load_tile(s, s);
+    cp_async_commit();
+  }
+
+  for (int64_t kt = 0; kt < KT; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      int64_t nk = kt + STAGES - 1;
+      if (nk < KT) load_tile(nk, (int)(nk % STAGES));
+      cp_async_commit();
+    }
+    const int stage = (int)(kt % STAGES);
+    const uint32_t as = smem_u32(As + stage * BM * LDK + (wm * 32 + r) * LDK + 2 * c);
+    const uint32_t bs = smem_u32(Bs + stage * BN * LDK + (wn * 32 + r) * LDK + 2 * c);
+#pragma unroll
+    for (int k8 = 0; k8 < BK / 8; ++k8) {
+      cplx b[4][2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        b[j][0] = lds_c(bs + (j * 8 * LDK + k8 * 8) * 16);
+        b[j][1] = lds_c(bs + (j * 8 * LDK + k8 * 8 + 1) * 16);
+        b[j][0].y = flip(b[j][0].y, p.b_sign);
+        b[j][1].y = flip(b[j][1].y, p.b_sign);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        cplx a0 = lds_c(as + (i * 8 * LDK + k8 * 8) * 16);
+        cplx a1 = lds_c(as + (i * 8 * LDK + k8 * 8 + 1) * 16);
+        a0.y = flip(a0.y, p.a_sign);
+        a1.y = flip(a1.y, p.a_sign);
+        const double na0 = -a0.y, na1 = -a1.y;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          cmma(acc[i][j], a0.x, a0.y, na0, b[j][0].x, b[j][0].y);
+          cmma(acc[i][j], a1.x, a1.y, na1, b[j][1].x, b[j][1].y);
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: C = alpha * acc + beta * C at the generalised address
+  const bool use_beta = !(p.beta.x == 0.0 && p.beta.y == 0.0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + wm * 32 + i * 8 + r;
+    if (m >= p.M) continue;
+    const int64_t moff = (m / p.out.m_div) * p.out.m_s1 + (m % p.out.m_div) * p.out.m_s0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int64_t n = n0 + wn * 32 + j * 8 + 2 * c + h;
+        if (n >= p.N) continue;
+        const int64_t off = moff + (n / p.out.n_div) * p.out.n_s1 + (n % p.out.n_div) * p.out.n_s0;
+        const double re = h ? acc[i][j].re1 : acc[i][j].re0;
+        const double im = h ? acc[i][j].im1 : acc[i][j].im0;
+        cplx v;
+        v.x = p.alpha.x * re - p.alpha.y * im;
+        v.y = p.alpha.x * im + p.alpha.y * re;
+        if (use_beta) {
+          cplx o = C[off];
+          v.x += p.beta.x * o.x - p.beta.y * o.y;
+          v.y += p.beta.x * o.y + p.beta.y * o.x;
+        }
+        C[off] = v;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// DMMA issue-rate microbenchmark: every warp keeps 16 independent accumulator tiles in flight.
+__global__ void __launch_bounds__(256, 1) dmma_peak_kernel(double* out, int iters) {
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  double c0[16], c1[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) c0[j] = c1[j] = 0.0;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dmma(c0[j], c1[j], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s += c0[j] + c1[j];
+  if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace
+
+int zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, cplx alpha, const cplx* A, int64_t lda, const cplx* B,
+          int64_t ldb, cplx beta, cplx* C, const GemmOut* out, const GemmKMap* kmap, int64_t batch, int64_t strideA,
+          int64_t strideB, int64_t strideC, cudaStream_t stream) {
+  CARC_REQUIRE(opA >= 0 && opA <= 3 && opB >= 0 && opB <= 3, CARC_ERR_VALUE, "zgemm: invalid op");
+  CARC_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 0, CARC_ERR_VALUE, "zgemm: negative dimension");
+  if (M == 0 || N == 0 || batch == 0) return CARC_OK;
+  static bool configured[16] = {false};
+  int dev = 0;
+  CARC_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 16 && !configured[dev]) {
+    CARC_CHECK_CUDA(cudaFuncSetAttribute(zgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured[dev] = true;
+  }
+  GemmParams p;
+  p.A = A; p.B = B; p.C = C;
+  p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb;
+  p.strideA = strideA; p.strideB = strideB; p.strideC = strideC;
+  p.a_kcontig = (opA == OP_N || opA == OP_J);
+  p.b_kcontig = (opB == OP_T || opB == OP_C);
+  p.a_sign = (opA == OP_C || opA == OP_J) ? 0x80000000u : 0u;
+  p.b_sign = (opB == OP_C || opB == OP_J) ? 0x80000000u : 0u;
+  p.alpha = alpha; p.beta = beta;
+  p.a_kdiv = p.a_ks1 = p.b_kdiv = p.b_ks1 = 0;
+  if (kmap) {
+    CARC_REQUIRE((!kmap->a_kdiv || p.a_kcontig) && (!kmap->b_kdiv || p.b_kcontig), CARC_ERR_VALUE,
+                 "zgemm: a two-level K map needs a K-contiguous operand");
+    p.a_kdiv = kmap->a_kdiv; p.a_ks1 = kmap->a_ks1; p.b_kdiv = kmap->b_kdiv; p.b_ks1 = kmap->b_ks1;
+  }
+  if (out) {
+    p.out = *out;
+  } else {
+    p.out.m_div = M > 0 ? M : 1; p.out.m_s1 = 0; p.out.m_s0 = N;
+    p.out.n_div = N > 0 ? N : 1; p.out.n_s1 = 0; p.out.n_s0 = 1;
+  }
+  CARC_REQUIRE(p.out.m_div > 0 && p.out.n_div > 0, CARC_ERR_VALUE, "zgemm: invalid output map");
+  int64_t gx = (N + BN - 1) / BN, gy = (M + BM - 1) / BM;
+  CARC_REQUIRE(gy < 65536 && batch < 65536, CARC_ERR_VALUE, "zgemm: grid too large (M tiles %lld, batch %lld)",
+               (long long)gy, (long long)batch);
+  dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)batch);
+  zgemm_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(p);
+  CARC_CHECK_CUDA(cudaGetLastError());
+  return CARC_OK;
+}
+
+int dmma_peak(int iters, double* tflops_out, cudaStream_t stream) {
+  double* buf = nullptr;
+  const int blocks = 148 * 2;
+  CARC_CHECK_CUDA(cudaMalloc(&buf, sizeof(double) * blocks * 256));
+  cudaEvent_t e0, e1;
+  CARC_CHECK_CUDA(cudaEventCreate(&e0));
+  CARC_CHECK_CUDA(cudaEventCreate(&e1));
+  dmma_peak_kernel<<<blocks, 256, 0, stream>>>(buf, 16);
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CARC_CHECK_CUDA(cudaEventRecord(e0, stream));
+    dmma_peak_kernel<<<blocks, 256, 0, stream>>>(buf, iters);
+    CARC_CHECK_CUDA(cudaEventRecord(e1, stream));
+    CARC_CHECK_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    CARC_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  // one DMMA.8x8x4 = 8*8*4 FMA = 512 flop per warp
+  double flops = (double)blocks * 8.0 * iters * 16.0 * 512.0;
+  *tflops_out = flops / (best * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  return CARC_OK;
+}
+
+}  // namespace carc

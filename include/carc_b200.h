@@ -1,0 +1,114 @@
+/* carc_b200.h -- C ABI of libcarc_b200.so: the B200 (sm_100a) implementation of Carcassonne's center-site
+ * optimisation hot path.
+ *
+ * The reference (gcross/Carcassonne) is pure Python and has no FFI; the seam this library sits behind is the
+ * duck-typed tensor class `NDArrayData` (reference carcassonne/data/__init__.py:30-365) plus the `Multiplier`
+ * / `relaxOver` pair (reference carcassonne/utils.py:180-207, 805-878).  Every entry point below names the
+ * reference call it replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - All tensors are complex128, interleaved (re, im), C-contiguous -- the memory layout of numpy.complex128 /
+ *     torch.complex128.  Pointers named `*_dev` / without suffix are DEVICE pointers unless the function name ends
+ *     in `_host`.  Device pointers must be 16-byte aligned.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are asynchronous on that stream
+ *     unless stated otherwise; functions that return scalars to the host synchronise the stream.
+ *   - Every function returns 0 on success or one of the CARC_ERR_* codes; carc_last_error() gives the message.
+ *     Codes map 1:1 onto the reference's exceptions (utils.py:13-41).
+ *   - Single host thread per device; one stream per System.
+ */
+#ifndef CARC_B200_H
+#define CARC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CARC_OK 0
+#define CARC_ERR_CUDA 1               /* CUDA runtime failure                                         */
+#define CARC_ERR_DIMENSION_MISMATCH 2 /* DimensionMismatchError (utils.py:14-24)                      */
+#define CARC_ERR_RANK 3               /* UnexpectedTensorRankError (utils.py:35-41)                   */
+#define CARC_ERR_VALUE 4              /* ValueError                                                   */
+#define CARC_ERR_RELAX_FAILED 5       /* RelaxFailed (utils.py:26-34)                                 */
+#define CARC_ERR_INVARIANT 6          /* InvariantViolatedError (utils.py:25)                         */
+#define CARC_ERR_NO_CONVERGENCE 7     /* the reference's `assert info == 0` after GMRES (utils.py:824) */
+#define CARC_ERR_UNSUPPORTED 8
+
+/* operand flags of carc_zgemm */
+#define CARC_OP_N 0 /* as stored                     */
+#define CARC_OP_T 1 /* transposed                    */
+#define CARC_OP_C 2 /* conjugate-transposed          */
+#define CARC_OP_J 3 /* conjugated, not transposed    */
+
+typedef struct carc_operator carc_operator; /* device-resident expectation / normalization operator */
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+int carc_version(void);
+const char* carc_last_error(void);
+/* Measured issue rate of DMMA.8x8x4 on the current device in TFLOP/s (the FP64 tensor roofline). */
+int carc_dmma_peak(int iters, double* tflops_out, void* stream);
+
+/* ---- device memory for callers that do not bring their own allocator ------------------------------------ */
+int carc_malloc(void** ptr, size_t bytes);
+int carc_free(void* ptr);
+int carc_malloc_host(void** ptr, size_t bytes); /* pinned */
+int carc_free_host(void* ptr);
+int carc_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes, void* stream);
+int carc_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes, void* stream);
+int carc_stream_synchronize(void* stream);
+
+/* ---- NDArrayData.join / transpose / conj (data/__init__.py:247-256, 154) --------------------------------
+ * dst = transpose(src, perm) written C-contiguously; conj != 0 conjugates; accumulate != 0 adds into dst. */
+int carc_permute(const void* src, void* dst, int ndim, const int64_t* shape, const int32_t* perm, int conj,
+                 int accumulate, void* stream);
+
+/* ---- NDArrayData + - * += scalar*  (data/__init__.py:95-147):  y = alpha * (conj_x ? conj(x) : x) + beta * y */
+int carc_axpby(int64_t n, const double alpha[2], const void* x, const double beta[2], void* y, int conj_x,
+               void* stream);
+/* y *= x elementwise (NDArrayData.__imul__) */
+int carc_mul(int64_t n, const void* x, void* y, void* stream);
+
+/* ---- reductions (NDArrayData.norm, contractWithAlongAll, hasNaN; utils.py:845-870 Arnoldi scalars) --------
+ * Results are written to DEVICE memory (two doubles) so iteration loops never synchronise. */
+int carc_dotc(int64_t n, const void* x, const void* y, void* out2_dev, void* stream); /* sum conj(x) y  */
+int carc_sumsq(int64_t n, const void* x, void* out2_dev, void* stream);               /* (sum |x|^2, 0) */
+int carc_count_nonfinite(int64_t n, const void* x, void* out2_dev, void* stream);     /* (#nonfinite, #nan) */
+
+/* ---- NDArrayData.contractWith == numpy.tensordot (data/__init__.py:157-159) after the operands are viewed
+ * as matrices: C[M,N] = alpha * op(A) * op(B) + beta * C, row-major.  See carc_internal.h for the storage each
+ * op flag implies.  out_map (6 x int64: m_div, m_s1, m_s0, n_div, n_s1, n_s0) or NULL for plain row-major with
+ * ldc = N: element (m, n) goes to C[(m / m_div) * m_s1 + (m % m_div) * m_s0 + (n / n_div) * n_s1 + (n % n_div) *
+ * n_s0], which lets a contraction write directly into the layout NDArrayData.join would produce.
+ * k_map (4 x int64: a_kdiv, a_ks1, b_kdiv, b_ks1) or NULL: two-level K index for K-contiguous operands. */
+int carc_zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, const double alpha[2], const void* A, int64_t lda,
+               const void* B, int64_t ldb, const double beta[2], void* C, const int64_t* out_map, const int64_t* k_map,
+               int64_t batch, int64_t strideA, int64_t strideB, int64_t strideC, void* stream);
+
+/* ---- the center-site operator: formExpectationStage3 / formNormalizationStage3 / formDenseStage3
+ * (tensors/_2d/sparse.py:100-161, tensors/_2d/dense.py:115-203).
+ * An operator is a list of terms (A_t, B_t, O_t): A_t = stage-2 half 0 pre-joined to [X_t, P, Q]
+ * (= [(x y), D0*, D1*, D0, D1], dense.py:130), B_t = half 1 pre-joined to [X_t, R, S] (dense.py:131), O_t a d x d
+ * site operator (row-major O[s', s]) or NULL for the identity.  The tensors are NOT copied: the caller keeps them
+ * alive for the life of the operator.  apply computes out[P,R,d] = sum_t B_t . (A_t . (O_t v)) with v[Q,S,d]. */
+int carc_operator_create(carc_operator** op, int P, int Q, int R, int S, int d);
+int carc_operator_add_term(carc_operator* op, const void* A, const void* B, int64_t X, const double* O_host);
+int carc_operator_finalize(carc_operator* op);
+int carc_operator_apply(carc_operator* op, const void* v, void* out, void* stream);
+/* force_path: 0 auto, 1 fused kernel only (error if the shape is unsupported), 2 unfused GEMM path */
+int carc_operator_set_path(carc_operator* op, int force_path);
+int carc_operator_num_terms(const carc_operator* op);
+/* cmac count the reference's CostTracker assigns to one apply (data/cost_tracker.py:17-21) */
+int64_t carc_operator_cost_of_multiply(const carc_operator* op);
+int carc_operator_destroy(carc_operator* op);
+/* End-to-end convenience with HOST buffers (terms, v and out on the host; copies inside the call):
+ * A_host[t], B_host[t] are host pointers to [X[t],P,Q] / [X[t],R,S]; O_host[t] NULL or d*d complex. */
+int carc_stage3_matvec_host(int nterms, const void* const* A_host, const void* const* B_host, const int64_t* X,
+                            const double* const* O_host, int P, int Q, int R, int S, int d, const void* v_host,
+                            void* out_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CARC_B200_H */

@@ -1,0 +1,227 @@
+"""GPU parity tests of the CUDA core (permute, DMMA ZGEMM, tensordot, fused stage-3 matvec) against the CPU
+oracle / NumPy on the same seeded inputs.  All calls go through the C ABI of libcarc_b200.so."""
+import itertools
+
+import numpy as np
+import pytest
+
+from golden_io import load, relerr
+
+pytestmark = pytest.mark.gpu
+
+MATVEC_TOL = 1e-12   # north_star: matvec output relative norm error <= 1e-12
+
+
+def crand(rng, *shape):
+    return rng.uniform(-1, 1, shape) + 1j * rng.uniform(-1, 1, shape)
+
+
+@pytest.fixture(scope="module")
+def dd():
+    from carcassonne_b200.data import DeviceData
+    return DeviceData
+
+
+@pytest.mark.parametrize("shape,perm", [
+    ((3, 4, 5), (2, 0, 1)),
+    ((2, 3, 1, 4, 2), (4, 2, 0, 3, 1)),
+    ((7,), (0,)),
+    ((33, 65), (1, 0)),
+    ((5, 40, 3, 36), (2, 3, 0, 1)),
+    ((2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2), (11, 0, 9, 2, 7, 4, 5, 6, 3, 8, 1, 10)),
+    ((4, 4, 1, 4, 4, 1, 3, 3), (1, 0, 2, 4, 3, 5, 7, 6)),
+])
+def test_permute(dd, shape, perm):
+    rng = np.random.default_rng(0)
+    a = crand(rng, *shape)
+    out = dd.fromArray(a).transpose(*perm).toArray()
+    assert np.array_equal(out, a.transpose(perm))
+    out = dd.fromArray(a)._permuted(perm, conj=1).toArray()
+    assert np.array_equal(out, a.transpose(perm).conj())
+
+
+def test_join_matches_reference_semantics(dd):
+    rng = np.random.default_rng(1)
+    a = crand(rng, 2, 3, 4, 5)
+    out = dd.fromArray(a).join((2, 0), 3, 1).toArray()
+    assert np.array_equal(out, a.transpose(2, 0, 3, 1).reshape(8, 5, 3))
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (5, 7, 3), (128, 64, 16), (130, 70, 37), (64, 300, 129), (257, 33, 8)])
+@pytest.mark.parametrize("opA,opB", list(itertools.product(range(4), range(4))))
+def test_zgemm(dd, M, N, K, opA, opB):
+    import torch
+    from carcassonne_b200 import _lib
+    from carcassonne_b200.data import gemm
+    rng = np.random.default_rng(M * 1000 + N * 10 + K)
+    a = crand(rng, M, K)
+    b = crand(rng, K, N)
+    c0 = crand(rng, M, N)
+    a_st = {0: a, 1: a.T, 2: a.T.conj(), 3: a.conj()}[opA]   # what is stored so that op(stored) == a
+    b_st = {0: b, 1: b.T, 2: b.T.conj(), 3: b.conj()}[opB]
+    A = torch.from_numpy(np.ascontiguousarray(a_st)).cuda()
+    B = torch.from_numpy(np.ascontiguousarray(b_st)).cuda()
+    Cb = torch.from_numpy(c0.copy()).cuda()
+    alpha, beta = 0.7 - 0.2j, -0.3 + 0.5j
+    gemm(opA, opB, M, N, K, A, a_st.shape[1], B, b_st.shape[1], Cb, alpha=alpha, beta=beta)
+    ref = alpha * (a @ b) + beta * c0
+    assert relerr(Cb.cpu().numpy(), ref) < 1e-14
+    assert _lib.lib.carc_version() >= 100
+
+
+def test_zgemm_output_map_and_kmap(dd):
+    import torch
+    from carcassonne_b200 import _lib
+    from carcassonne_b200.data import gemm
+    rng = np.random.default_rng(5)
+    X, P, Q, S, d, R = 5, 6, 7, 9, 2, 4
+    A = crand(rng, X, P, Q)
+    w = crand(rng, Q, S, d)
+    Bm = crand(rng, X, R, S)
+    At, wt, Bt = (torch.from_numpy(x).cuda() for x in (A, w, Bm))
+    T = torch.empty(P, d, X, S, dtype=torch.complex128, device="cuda")
+    gemm(_lib.OP_N, _lib.OP_N, X * P, S * d, Q, At, Q, wt, S * d, T,
+         out_map=(P, S, d * X * S, d, 1, X * S))
+    ref_T = np.einsum("xpq,qSs->psxS", A, w)
+    assert relerr(T.cpu().numpy(), ref_T) < 1e-14
+    out = torch.zeros(P, R, d, dtype=torch.complex128, device="cuda")
+    gemm(_lib.OP_N, _lib.OP_T, P * d, R, X * S, T, X * S, Bt, S, out, beta=1.0,
+         out_map=(d, R * d, 1, R, 0, d), k_map=(0, 0, S, R * S))
+    ref = np.einsum("psxS,xrS->prs", ref_T, Bm)
+    assert relerr(out.cpu().numpy(), ref) < 1e-14
+
+
+@pytest.mark.parametrize("sa,sb,axa,axb", [
+    ((3, 4, 5), (5, 4, 2), (1, 2), (1, 0)),
+    ((6, 2, 3), (2, 3, 7), (1, 2), (0, 1)),
+    ((2, 3, 4), (4, 3, 5, 2), (0, 1), (3, 1)),
+    ((4, 4), (4, 4), (), ()),
+    ((3, 1, 2), (2, 3, 1), (0, 1, 2), (1, 2, 0)),
+])
+def test_contract_with(dd, sa, sb, axa, axb):
+    rng = np.random.default_rng(2)
+    a, b = crand(rng, *sa), crand(rng, *sb)
+    out = dd.fromArray(a).contractWith(dd.fromArray(b), axa, axb)
+    ref = np.tensordot(a, b, (axa, axb))
+    assert out.shape == ref.shape
+    assert relerr(out.toArray(), ref) < 1e-14
+
+
+def test_absorb_matrix_at(dd):
+    g = load("data_ops")
+    for n in range(4):
+        t, axis, m = g["na%d_in" % n], int(g["na%d_axis" % n]), g["am%d_m" % n]
+        out = dd.fromArray(t).absorbMatrixAt(axis, dd.fromArray(m))
+        assert relerr(out.toArray(), g["am%d_out" % n]) < 1e-14
+
+
+def test_elementwise_and_reductions(dd):
+    rng = np.random.default_rng(3)
+    a, b = crand(rng, 37, 5, 3), crand(rng, 37, 5, 3)
+    A, B = dd.fromArray(a), dd.fromArray(b)
+    assert relerr((A + B).toArray(), a + b) < 1e-15
+    assert relerr((A - B).toArray(), a - b) < 1e-15
+    assert relerr((A * B).toArray(), a * b) < 1e-15
+    assert relerr((A * (0.5 - 2j)).toArray(), a * (0.5 - 2j)) < 1e-15
+    assert relerr((-A).toArray(), -a) == 0
+    assert relerr(A.conj().toArray(), a.conj()) == 0
+    assert abs(A.norm() - np.linalg.norm(a)) < 1e-13 * np.linalg.norm(a)
+    assert abs(A.contractWithAlongAll(B) - np.sum(a * b)) < 1e-12
+    Cc = A.copy()
+    Cc += B
+    assert relerr(Cc.toArray(), a + b) < 1e-15
+    assert not A.hasNaN()
+    a2 = a.copy()
+    a2[3, 2, 1] = np.nan
+    assert dd.fromArray(a2).hasNaN()
+
+
+def _stage3_case(rng, chi2, D, d=2, terms=1, dims=None):
+    from oracle import dense
+    d0, d1, d2, d3 = dims if dims else (D, D, D, D)
+    s2_0 = [crand(rng, chi2, chi2, d0, d1, d0, d1) for _ in range(terms)]
+    s2_1 = [crand(rng, chi2, chi2, d2, d3, d2, d3) for _ in range(terms)]
+    ops = [None if t % 2 == 0 else crand(rng, d, d) for t in range(terms)]
+    v = crand(rng, d0, d1, d2, d3, d)
+    ref = sum(dense.stage3_multiply(a, b, v, o) for a, b, o in zip(s2_0, s2_1, ops))
+    return s2_0, s2_1, ops, v, ref
+
+
+@pytest.mark.parametrize("chi2,D,terms", [(2, 2, 1), (4, 2, 3), (3, 3, 2), (4, 4, 2), (9, 3, 4), (5, 5, 1), (4, 6, 2),
+                                          (3, 7, 1), (6, 8, 2)])
+@pytest.mark.parametrize("path", [1, 2])
+def test_stage3_operator(dd, chi2, D, terms, path):
+    from carcassonne_b200.operator import Stage3Operator, prejoin_halves
+    rng = np.random.default_rng(chi2 * 100 + D * 10 + terms)
+    s2_0, s2_1, ops, v, ref = _stage3_case(rng, chi2, D, terms=terms)
+    op = Stage3Operator(v.shape)
+    for a, b, o in zip(s2_0, s2_1, ops):
+        A, B = prejoin_halves(dd.fromArray(a), dd.fromArray(b))
+        op.add_term(A, B, o)
+    op.finalize().set_path(path)
+    out = op(dd.fromArray(v)).toArray()
+    assert relerr(out, ref) < MATVEC_TOL
+    # linearity (size-independent property): op(2v + i v) == (2 + i) op(v)
+    out2 = op(dd.fromArray((2 + 1j) * v)).toArray()
+    assert relerr(out2, (2 + 1j) * ref) < MATVEC_TOL
+
+
+@pytest.mark.parametrize("dims,d", [((2, 3, 3, 2), 2), ((1, 1, 1, 1), 2), ((3, 2, 2, 4), 3), ((2, 2, 2, 2), 1),
+                                     ((4, 4, 2, 2), 2), ((2, 2, 8, 8), 2)])
+def test_stage3_ragged_shapes(dd, dims, d):
+    from carcassonne_b200.operator import Stage3Operator, prejoin_halves
+    rng = np.random.default_rng(sum(dims) + d)
+    s2_0, s2_1, ops, v, ref = _stage3_case(rng, 3, None, d=d, terms=2, dims=dims)
+    op = Stage3Operator(v.shape)
+    for a, b, o in zip(s2_0, s2_1, ops):
+        A, B = prejoin_halves(dd.fromArray(a), dd.fromArray(b))
+        op.add_term(A, B, o)
+    out = op(dd.fromArray(v)).toArray()
+    assert relerr(out, ref) < MATVEC_TOL
+
+
+def test_stage3_golden(dd):
+    """The reference's own multiplier output (tests/golden/dense_recipes.npz)."""
+    from carcassonne_b200.operator import Stage3Operator, prejoin_halves
+    g = load("dense_recipes")
+    A, B = prejoin_halves(dd.fromArray(g["st3_s2_0"]), dd.fromArray(g["st3_s2_1"]))
+    v = dd.fromArray(g["st3_v"])
+    op = Stage3Operator(v.shape).add_term(A, B, None).finalize()
+    assert relerr(op(v).toArray(), g["st3_norm_out"]) < MATVEC_TOL
+    assert op.cost_of_multiply == int(g["st3_norm_cost"][0])
+    op = Stage3Operator(v.shape).add_term(A, B, g["st3_op"]).finalize()
+    assert relerr(op(v).toArray(), g["st3_dense_out"]) < MATVEC_TOL
+    assert op.cost_of_multiply == int(g["st3_dense_cost"][0])
+
+
+def test_stage3_host_entry_point(dd):
+    """carc_stage3_matvec_host: the end-to-end C-ABI call with host buffers."""
+    import ctypes as C
+    from carcassonne_b200 import _lib
+    from oracle import dense
+    rng = np.random.default_rng(9)
+    s2_0, s2_1, ops, v, ref = _stage3_case(rng, 4, 4, terms=2)
+    halves = [dense.stage3_prejoin(a, b) for a, b in zip(s2_0, s2_1)]
+    nt = len(halves)
+    A = [np.ascontiguousarray(h[0]) for h in halves]
+    B = [np.ascontiguousarray(h[1]) for h in halves]
+    Ap = (C.c_void_p * nt)(*[a.ctypes.data for a in A])
+    Bp = (C.c_void_p * nt)(*[b.ctypes.data for b in B])
+    X = (C.c_int64 * nt)(*[a.shape[0] for a in A])
+    opsc = [None if o is None else np.ascontiguousarray(o) for o in ops]
+    Op = (C.POINTER(C.c_double) * nt)(*[
+        C.cast(None, C.POINTER(C.c_double)) if o is None else o.view(np.float64).ctypes.data_as(C.POINTER(C.c_double))
+        for o in opsc])
+    out = np.empty_like(v)
+    _lib.check(_lib.lib.carc_stage3_matvec_host(nt, Ap, Bp, X, Op, 16, 16, 16, 16, 2, v.ctypes.data, out.ctypes.data,
+                                                None))
+    assert relerr(out, ref) < MATVEC_TOL
+
+
+def test_dmma_peak_runs():
+    import ctypes as C
+    from carcassonne_b200 import _lib
+    tf = C.c_double()
+    _lib.check(_lib.lib.carc_dmma_peak(2000, C.byref(tf), None))
+    print("DMMA peak TFLOP/s:", tf.value)
+    assert tf.value > 1.0
