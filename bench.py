@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Headline benchmark: the center-site expectation matvec (BASELINE.json metric "center-site matvec GFLOP/s").
+
+A step is one application of the expectation multiplier H = sum_t B_t . (A_t . (O_t v)) that
+``System.formExpectationMultiplier()`` builds (reference tensors/_2d/sparse.py:100-161, dense.py:115-203) for the
+2D transverse-field Ising Hamiltonian after one absorption round: T = 9 sparse terms over 6 + 6 stage-2
+environment tensors, state bond D and boundary bond chi, d = 2.
+Tensors are synthetic (random complex128) and stay resident in HBM, exactly as they do between the reference's
+formExpectationStage2 and the Arnoldi iteration; the environment is far larger than L2 (12 x 16 X D^4 bytes).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--D 8] [--chi 16] [--impl reference]
+
+N > 1 (under torchrun): the joined environment bond X = chi^4 is split into N slabs, one per GPU (strong
+scaling: the same matvec, sharded); every rank holds the full vector and the partial results are summed by
+one allreduce of the N-vector over NVLink.
+
+FLOP accounting: 8 x the cmac count the reference's CostTracker assigns to the multiplier
+(``Multiplier.cost_of_multiply``, data/cost_tracker.py:17-21) = 16 T X D^6 d -- the work the reference performs
+for this call, whatever shortcuts the device path takes.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "center_site_expectation_matvec_gflops"
+UNIT = "GFLOP/s"
+
+_Z = np.array([[1, 0], [0, -1]], dtype=np.complex128)
+_X = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+
+
+def tfim_terms(J=1.0):
+    """Stage-3 term table of the TFIM operator (Os=[-Z], OO_LRs=[(X,-J X)], OO_UDs=[(X,-J X)]) after one
+    absorption in each direction.  Half-tensor indices: 0 Identity, 1 Complete, 2 TwoSite(0,LEFT,0),
+    3 TwoSite(0,RIGHT,0), 4 TwoSite(0,CENTER,LEFT), 5 TwoSite(0,CENTER,RIGHT).  (a, b, site operator)."""
+    return [
+        (1, 0, None), (0, 1, None), (0, 0, -_Z),
+        (4, 0, _X), (5, 0, -J * _X), (0, 4, -J * _X), (0, 5, _X),
+        (3, 2, None), (2, 3, None),
+    ]
+
+
+def cost_of_multiply(terms, X, D, d):
+    """cmac count of the reference's generated contractors (dense.py:115-128 / 146-160)."""
+    P = D * D
+    cost = 0
+    for _, _, o in terms:
+        if o is not None:
+            cost += d * d * P * P
+        cost += X * P * (P * d) * P + P * (P * d) * (P * X)
+    return cost
+
+
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def cpu_matvec_sample(D, d, terms, X_sample, repeats=1, seed=0):
+    """Times the oracle's restatement of the reference matvec (two tensordots per term, NumPy -> BLAS zgemm)
+    on an X slab of the workload.  Returns (GFLOP/s, seconds, threads)."""
+    from oracle import dense
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        threads = os.cpu_count() or 1
+    rng = np.random.default_rng(seed)
+    P = D * D
+
+    def crand(*shape):
+        return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+    A = [crand(X_sample, D, D, D, D) for _ in range(6)]
+    B = [crand(X_sample, D, D, D, D) for _ in range(6)]
+    v = crand(D, D, D, D, d)
+
+    def matvec():
+        out = np.zeros_like(v)
+        for a, b, o in terms:
+            out += dense.stage3_multiply_joined(A[a], B[b], v, o)
+        return out
+
+    matvec() if X_sample <= 64 else None  # tiny warm-up only when cheap
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        matvec()
+        best = min(best, time.perf_counter() - t0)
+    flops = 8.0 * cost_of_multiply(terms, X_sample, D, d)
+    return flops / best / 1e9, best, threads
+
+
+def pick_cpu_sample(D, X):
+    """X slab that costs about 10-20 s of CPU work at ~10 GFLOP/s."""
+    per_x = 8.0 * 9 * 2 * (D ** 6) * 2
+    xs = int(max(1, min(X, 1.5e11 / per_x)))
+    return xs
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    D, chi, d = args.D, args.chi, 2
+    X = chi ** 4
+    terms = tfim_terms()
+    xs = pick_cpu_sample(D, X)
+    if args.steps * 1.0 > 6:
+        xs = max(1, xs * 6 // args.steps)
+    for _ in range(args.warmup):
+        cpu_matvec_sample(D, d, terms, max(1, xs // 8))
+    vals, secs = [], []
+    threads = 1
+    for _ in range(args.steps):
+        g, s, threads = cpu_matvec_sample(D, d, terms, xs)
+        vals.append(g)
+        secs.append(s)
+    value = float(np.mean(vals))
+    sample = "T=9 TFIM terms, D=%d, X slab of %d of %d (chi=%d)" % (D, xs, X, chi)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3 * (X / xs),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "complex128 (f64)",
+        "data": "synthetic", "config": workload_config(args, X),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, X):
+    return {"workload": "TFIM expectation matvec, T=9 terms, D=%d, chi=%d (X=%d), d=2" % (args.D, args.chi, X),
+            "D": args.D, "chi": args.chi, "terms": 9, "l2": "inputs (12 x 16*X*D^4 B) larger than L2",
+            "sharding": "X slabs over ranks + allreduce(sum) of the output vector"}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_device(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import ctypes as C
+    from carcassonne_b200 import _lib
+    from carcassonne_b200.data import DeviceData
+    from carcassonne_b200.operator import Stage3Operator
+
+    D, chi, d = args.D, args.chi, 2
+    X = chi ** 4
+    x_lo, x_hi = X * rank // world, X * (rank + 1) // world
+    Xl = x_hi - x_lo
+    terms = tfim_terms()
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1234 + rank)
+
+    def rnd(*shape):
+        t = torch.empty(shape, dtype=torch.complex128, device="cuda")
+        torch.view_as_real(t).normal_(generator=gen)
+        return t
+
+    scale = 1.0 / (D * D * np.sqrt(X))
+    A = [DeviceData(rnd(Xl, D, D, D, D).mul_(scale)) for _ in range(6)]
+    B = [DeviceData(rnd(Xl, D, D, D, D).mul_(scale)) for _ in range(6)]
+    op = Stage3Operator((D, D, D, D, d))
+    for a, b, o in terms:
+        op.add_term(A[a], B[b], o)
+    op.finalize()
+    n = D ** 4 * d
+    v_host = torch.empty((D, D, D, D, d), dtype=torch.complex128).pin_memory()
+    torch.view_as_real(v_host).normal_()
+    out_host = torch.empty_like(v_host).pin_memory()
+    v = v_host.cuda()
+    out = torch.empty_like(v)
+    if world > 1:
+        dist.broadcast(v, 0)
+
+    def step():
+        op.apply_raw(v, out)
+        if world > 1:
+            dist.all_reduce(out)
+
+    def step_e2e():
+        v.copy_(v_host, non_blocking=True)
+        op.apply_raw(v, out)
+        if world > 1:
+            dist.all_reduce(out)
+        out_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    t0 = time.time()
+    total_ms = timed(step, args.steps)
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+
+    # kernel-only duration of the dominant kernel (fused stage-3 + its partial-sum pass), no collective
+    kern_ms = timed(lambda: op.apply_raw(v, out), args.steps) / args.steps
+
+    for _ in range(3):
+        step_e2e()
+    e2e_ms = timed(step_e2e, args.steps)
+
+    flops = 8.0 * cost_of_multiply(terms, X, D, d)            # whole job, reference accounting
+    flops_local = 8.0 * cost_of_multiply(terms, Xl, D, d)
+    ms_per_step = total_ms / args.steps
+    value = flops / (ms_per_step * 1e-3) / 1e9
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    tf = C.c_double()
+    _lib.check(_lib.lib.carc_dmma_peak(4000, C.byref(tf), None))
+    achieved_tf = flops_local / (kern_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("D%d_chi%d_n%d" % (D, chi, world))
+        except Exception:
+            traffic = None
+    roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": tf.value, "unit": "TFLOP/s",
+                "frac": achieved_tf / tf.value, "traffic": traffic,
+                "kernel": "stage3_kernel (fused A.v -> O -> B^T, DMMA.8x8x4)",
+                "peak_source": "DMMA.8x8x4 issue-rate microbenchmark run in this process (carc_dmma_peak); "
+                               "MEASURED_PEAKS.json has no FP64 figure",
+                "algorithmic_bytes": 12 * 16 * Xl * D ** 4 + 32 * n,
+                "hbm_gbs": (12 * 16 * Xl * D ** 4 + 32 * n) / (kern_ms * 1e-3) / 1e9}
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        xs = pick_cpu_sample(D, X)
+        g, s, threads = cpu_matvec_sample(D, d, terms, xs)
+        cpu = {"value": g, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "T=9 TFIM terms, D=%d, X slab of %d of %d, %.1f s, oracle.dense.stage3_multiply_joined "
+                         "(NumPy tensordot -> BLAS zgemm)" % (D, xs, X, s)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "complex128 (f64)", "data": "synthetic",
+        "config": workload_config(args, X),
+        "clocks": clocks,
+        "e2e": {"value": flops / (e2e_ms / args.steps * 1e-3) / 1e9, "unit": UNIT,
+                "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n,
+                "what": "Stage3Operator applied to a pinned host vector: H2D of v, matvec (+allreduce), D2H of H v; "
+                        "the environment stays resident as it does behind the reference's Multiplier closure"},
+        "gpu_launches": 2 * args.steps,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--D", type=int, default=8)
+    ap.add_argument("--chi", type=int, default=16)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("bench.py --gpus %d must be launched with torchrun (one rank per GPU)" % args.gpus)
+    run_device(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -52,6 +52,9 @@ SIGNATURES = {
     "carc_operator_num_terms": (c_int, [c_vp]),
     "carc_operator_cost_of_multiply": (c_i64, [c_vp]),
     "carc_operator_destroy": (c_int, [c_vp]),
+    "carc_qr": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "carc_svd_small": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "carc_normalizer_matrices": (c_int, [c_vp, c_vp, c_vp, c_int, C.c_double, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "carc_stage3_matvec_host": (c_int, [c_int, C.POINTER(c_vp), C.POINTER(c_vp), c_i64p, C.POINTER(c_dp),
                                         c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
 }

@@ -226,4 +226,18 @@ int carc_stage3_matvec_host(int nterms, const void* const* A_host, const void* c
   return rc;
 }
 
+int carc_qr(void* A, int64_t m, int n, void* R, void* Q, void* tau, void* stream) {
+  return carc::qr((cplx*)A, m, n, (cplx*)R, (cplx*)Q, (cplx*)tau, S(stream));
+}
+int carc_svd_small(const void* R, int n, void* U, void* Sv, void* Vh, void* stream) {
+  return carc::svd_small((const cplx*)R, n, (cplx*)U, (cplx*)Sv, (cplx*)Vh, S(stream));
+}
+int carc_normalizer_matrices(const void* U, const void* Sv, const void* Vh, int n, double dont_recip_under,
+                             void* polar, void* normalizer, void* denormalizer, void* normalizer_sqrt,
+                             void* denormalizer_sqrt, void* stream) {
+  return carc::normalizer_matrices((const cplx*)U, (const cplx*)Sv, (const cplx*)Vh, n, dont_recip_under,
+                                   (cplx*)polar, (cplx*)normalizer, (cplx*)denormalizer, (cplx*)normalizer_sqrt,
+                                   (cplx*)denormalizer_sqrt, S(stream));
+}
+
 }  // extern "C"

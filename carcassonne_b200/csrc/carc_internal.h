@@ -48,4 +48,10 @@ int stage3_apply(const Stage3Term* terms_host, const Stage3Term* terms_dev, int 
                  cudaStream_t stream);
 int64_t stage3_workspace_elems(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax);
 
+// linalg.cu
+int qr(cplx* A, int64_t m, int n, cplx* R, cplx* Q, cplx* tau, cudaStream_t stream);
+int svd_small(const cplx* R, int n, cplx* U, cplx* S, cplx* Vh, cudaStream_t stream);
+int normalizer_matrices(const cplx* U, const cplx* S, const cplx* Vh, int n, double dont_recip_under, cplx* polar,
+                        cplx* nrm, cplx* den, cplx* nrm_sqrt, cplx* den_sqrt, cudaStream_t stream);
+
 }  // namespace carc

@@ -108,6 +108,21 @@ int carc_stage3_matvec_host(int nterms, const void* const* A_host, const void* c
                             const double* const* O_host, int P, int Q, int R, int S, int d, const void* v_host,
                             void* out_host, void* stream);
 
+/* ---- small factorisations: scipy.linalg.qr / svd call sites of NDArrayData.qr, svd, unitize, normalizeAxis
+ * (data/__init__.py:43-50, 263-301, 344-346; utils.py:879-881).
+ * carc_qr: A [m,n] row-major, m >= n (overwritten with reflectors); R [n,n]; Q [m,n]; tau [n] workspace.
+ *          Householder conventions of LAPACK zgeqr2 / zung2r, so Q matches SciPy's economic Q to rounding.
+ * carc_svd_small: one-sided Jacobi SVD of an n x n matrix (n <= 80): U [n,n], S [n] stored as (s,0) complex,
+ *          descending, Vh [n,n]; null directions of U are completed to an orthonormal basis.
+ * carc_normalizer_matrices: from (U, S, Vh) the n x n matrices normalizeAxis returns: polar = U Vh,
+ *          normalizer = conj(V S^-1 V^H), denormalizer = V S V^H and their sqrt_svals variants
+ *          (S^-1 skipped where S <= dont_recip_under). */
+int carc_qr(void* A, int64_t m, int n, void* R, void* Q, void* tau, void* stream);
+int carc_svd_small(const void* R, int n, void* U, void* S, void* Vh, void* stream);
+int carc_normalizer_matrices(const void* U, const void* S, const void* Vh, int n, double dont_recip_under,
+                             void* polar, void* normalizer, void* denormalizer, void* normalizer_sqrt,
+                             void* denormalizer_sqrt, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
