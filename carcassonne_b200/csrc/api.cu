@@ -8,6 +8,9 @@
 using carc::cplx;
 
 struct carc_operator {
+  int kind = 0;                 // 0: stage-3 term list, 1: dense matrix
+  const cplx* matrix = nullptr; // kind 1: [n, n] row-major (not owned)
+  int64_t n = 0;
   int P, Q, R, S, d;
   std::vector<carc::Stage3Term> terms;
   carc::Stage3Term* terms_dev = nullptr;
@@ -94,6 +97,19 @@ int carc_zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, const double a
                      out_map ? &om : nullptr, k_map ? &km : nullptr, batch, strideA, strideB, strideC, S(stream));
 }
 
+int carc_index_table(int nlevels, const int64_t* extents, const int64_t* strides, void* table_dev, void* stream) {
+  return carc::index_table(nlevels, extents, strides, (int64_t*)table_dev, S(stream));
+}
+
+int carc_zgemm_tab(int opA, int opB, int64_t M, int64_t N, int64_t K, const double alpha[2], const void* A, int64_t lda,
+                   const void* B, int64_t ldb, const double beta[2], void* C, const void* rowoff_dev,
+                   const void* coloff_dev, int64_t batch, int64_t strideA, int64_t strideB, int64_t strideC,
+                   void* stream) {
+  return carc::zgemm(opA, opB, M, N, K, C2(alpha), (const cplx*)A, lda, (const cplx*)B, ldb, C2(beta), (cplx*)C, nullptr,
+                     nullptr, batch, strideA, strideB, strideC, S(stream), (const int64_t*)rowoff_dev,
+                     (const int64_t*)coloff_dev);
+}
+
 // ---------------------------------------------------------------------------------------------------
 int carc_operator_create(carc_operator** op, int P, int Q, int R, int Sd, int d) {
   CARC_REQUIRE(op != nullptr, CARC_ERR_VALUE, "operator_create: null handle pointer");
@@ -101,6 +117,7 @@ int carc_operator_create(carc_operator** op, int P, int Q, int R, int Sd, int d)
                "operator_create: invalid dimensions P=%d Q=%d R=%d S=%d d=%d", P, Q, R, Sd, d);
   carc_operator* o = new carc_operator();
   o->P = P; o->Q = Q; o->R = R; o->S = Sd; o->d = d;
+  o->n = (int64_t)P * R * d;
   *op = o;
   return CARC_OK;
 }
@@ -157,8 +174,25 @@ int64_t carc_operator_cost_of_multiply(const carc_operator* op) {
   return cost;
 }
 
+int carc_operator_create_dense(carc_operator** op, const void* matrix_dev, int64_t n) {
+  CARC_REQUIRE(op != nullptr && matrix_dev != nullptr && n > 0, CARC_ERR_VALUE, "operator_create_dense: invalid argument");
+  carc_operator* o = new carc_operator();
+  o->kind = 1;
+  o->matrix = (const cplx*)matrix_dev;
+  o->n = n;
+  o->P = o->Q = o->R = o->S = o->d = 0;
+  o->finalized = true;
+  *op = o;
+  return CARC_OK;
+}
+
+int64_t carc_operator_dimension(const carc_operator* op) { return op ? op->n : -1; }
+
 int carc_operator_apply(carc_operator* op, const void* v, void* out, void* stream) {
   CARC_REQUIRE(op && op->finalized, CARC_ERR_VALUE, "operator_apply: operator not finalized");
+  if (op->kind == 1)
+    return carc::dense_matvec(op->matrix, op->n, op->n, op->n, (const cplx*)v, (cplx*)out, make_double2(1.0, 0.0),
+                              make_double2(0.0, 0.0), S(stream));
   return carc::stage3_apply(op->terms.data(), op->terms_dev, (int)op->terms.size(), op->P, op->Q, op->R, op->S, op->d,
                             (const cplx*)v, (cplx*)out, op->workspace, op->workspace_elems, op->force_path, S(stream));
 }
@@ -223,6 +257,114 @@ int carc_stage3_matvec_host(int nterms, const void* const* A_host, const void* c
   cudaStreamSynchronize(st);
   carc_operator_destroy(op);
   cleanup();
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+int carc_lu_factor(void* A, int n, void* piv_dev, int* singular_out, void* stream) {
+  CARC_REQUIRE(A && piv_dev && n > 0, CARC_ERR_VALUE, "lu_factor: invalid argument");
+  cudaStream_t st = S(stream);
+  void* scratch = nullptr;
+  CARC_CHECK_CUDA(cudaMallocAsync(&scratch, 64, st));
+  int rc = carc::lu_factor((cplx*)A, n, (int*)piv_dev, (int*)((char*)scratch + 32), (cplx*)scratch, st);
+  int singular = 0;
+  if (!rc) {
+    CARC_CHECK_CUDA(cudaMemcpyAsync(&singular, (char*)scratch + 32, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CARC_CHECK_CUDA(cudaStreamSynchronize(st));
+  }
+  cudaFreeAsync(scratch, st);
+  if (singular_out) *singular_out = singular;
+  return rc;
+}
+
+int carc_lu_solve(const void* LU, int n, const void* piv_dev, void* x, void* stream) {
+  CARC_REQUIRE(LU && piv_dev && x && n > 0, CARC_ERR_VALUE, "lu_solve: invalid argument");
+  return carc::lu_solve((const cplx*)LU, n, (const int*)piv_dev, (cplx*)x, S(stream));
+}
+
+static carc::LinOp as_linop(carc_operator* op) {
+  carc::LinOp l;
+  l.apply = [op](const cplx* in, cplx* out, cudaStream_t st) { return carc_operator_apply(op, in, out, (void*)st); };
+  return l;
+}
+
+int carc_gmres(carc_operator* A, const void* b, void* x, double rtol, int restart, int maxiter, int* iterations_out,
+               double* residual_out, void* stream) {
+  CARC_REQUIRE(A && A->finalized && b && x, CARC_ERR_VALUE, "gmres: invalid argument");
+  cudaStream_t st = S(stream);
+  const int64_t n = A->n;
+  if (restart > n) restart = (int)n;
+  void *work = nullptr, *state = nullptr;
+  CARC_CHECK_CUDA(cudaMallocAsync(&work, sizeof(cplx) * (size_t)(restart + 2) * n, st));
+  CARC_CHECK_CUDA(cudaMallocAsync(&state, carc::gmres_state_bytes(), st));
+  int iters = 0;
+  double resid = 0.0;
+  int rc = carc::gmres(as_linop(A), (const cplx*)b, (cplx*)x, n, rtol, restart, maxiter, (cplx*)work, state, &iters,
+                       &resid, st);
+  cudaFreeAsync(work, st);
+  cudaFreeAsync(state, st);
+  if (iterations_out) *iterations_out = iters;
+  if (residual_out) *residual_out = resid;
+  return rc;
+}
+
+int carc_relax(carc_operator* H, carc_operator* N_op, const void* N_lu, const void* N_piv, void* v, int max_mults,
+               double tolerance, int krylov_dim, double gmres_rtol, int gmres_restart, int gmres_maxiter,
+               double* info_out, void* stream) {
+  CARC_REQUIRE(H && H->finalized && v, CARC_ERR_VALUE, "relax: invalid argument");
+  CARC_REQUIRE(!N_op || N_op->n == H->n, CARC_ERR_DIMENSION_MISMATCH, "relax: H and N act on different spaces");
+  cudaStream_t st = S(stream);
+  const int64_t n = H->n;
+  const int k = krylov_dim > 0 ? krylov_dim : 3;
+  int restart = gmres_restart > 0 ? gmres_restart : 20;
+  if (restart > n) restart = (int)n;
+  void *work = nullptr, *state = nullptr, *hv = nullptr, *gwork = nullptr, *gstate = nullptr;
+  CARC_CHECK_CUDA(cudaMallocAsync(&work, sizeof(cplx) * (size_t)(2 * k + 2) * n, st));
+  CARC_CHECK_CUDA(cudaMallocAsync(&state, carc::relax_state_bytes(), st));
+  const bool use_lu = N_lu != nullptr && N_piv != nullptr;
+  const bool use_gmres = !use_lu && N_op != nullptr;
+  if (use_gmres) {
+    CARC_CHECK_CUDA(cudaMallocAsync(&hv, sizeof(cplx) * n, st));
+    CARC_CHECK_CUDA(cudaMallocAsync(&gwork, sizeof(cplx) * (size_t)(restart + 2) * n, st));
+    CARC_CHECK_CUDA(cudaMallocAsync(&gstate, carc::gmres_state_bytes(), st));
+  }
+  int gm_total = 0;
+  carc::LinOp M;
+  carc::LinOp Nl;
+  if (use_gmres) Nl = as_linop(N_op);
+  M.apply = [&](const cplx* in, cplx* out, cudaStream_t s2) -> int {
+    if (use_lu) {
+      int rc = carc_operator_apply(H, in, out, (void*)s2);
+      if (rc) return rc;
+      return carc::lu_solve((const cplx*)N_lu, (int)n, (const int*)N_piv, out, s2);
+    }
+    if (use_gmres) {
+      int rc = carc_operator_apply(H, in, hv, (void*)s2);
+      if (rc) return rc;
+      int it = 0;
+      double rs = 0.0;
+      rc = carc::gmres(Nl, (const cplx*)hv, out, n, gmres_rtol > 0 ? gmres_rtol : 1e-5, restart,
+                       gmres_maxiter > 0 ? gmres_maxiter : 1000, (cplx*)gwork, gstate, &it, &rs, s2);
+      gm_total += it;
+      return rc;
+    }
+    return carc_operator_apply(H, in, out, (void*)s2);
+  };
+  carc::RelaxInfo info;
+  int rc = carc::relax(M, (cplx*)v, n, max_mults, tolerance, k, (cplx*)work, state, &info, st);
+  cudaFreeAsync(work, st);
+  cudaFreeAsync(state, st);
+  if (use_gmres) {
+    cudaFreeAsync(hv, st);
+    cudaFreeAsync(gwork, st);
+    cudaFreeAsync(gstate, st);
+  }
+  if (info_out && (rc == CARC_OK || rc == CARC_ERR_RELAX_FAILED)) {
+    info_out[0] = info.initial_value[0]; info_out[1] = info.initial_value[1];
+    info_out[2] = info.final_value[0]; info_out[3] = info.final_value[1];
+    info_out[4] = info.ritz_value[0]; info_out[5] = info.ritz_value[1];
+    info_out[6] = info.multiplications; info_out[7] = info.applications; info_out[8] = gm_total;
+  }
   return rc;
 }
 

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
+
 #define CARC_MAX_RANK 12
 
 namespace carc {
@@ -32,7 +34,9 @@ struct GemmKMap {
 };
 int zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, cplx alpha, const cplx* A, int64_t lda, const cplx* B,
           int64_t ldb, cplx beta, cplx* C, const GemmOut* out, const GemmKMap* kmap, int64_t batch, int64_t strideA,
-          int64_t strideB, int64_t strideC, cudaStream_t stream);
+          int64_t strideB, int64_t strideC, cudaStream_t stream, const int64_t* rowoff = nullptr,
+          const int64_t* coloff = nullptr);
+int index_table(int nlevels, const int64_t* extents, const int64_t* strides, int64_t* table, cudaStream_t stream);
 int dmma_peak(int iters, double* tflops_out, cudaStream_t stream);
 
 // stage3.cu
@@ -53,5 +57,24 @@ int qr(cplx* A, int64_t m, int n, cplx* R, cplx* Q, cplx* tau, cudaStream_t stre
 int svd_small(const cplx* R, int n, cplx* U, cplx* S, cplx* Vh, cudaStream_t stream);
 int normalizer_matrices(const cplx* U, const cplx* S, const cplx* Vh, int n, double dont_recip_under, cplx* polar,
                         cplx* nrm, cplx* den, cplx* nrm_sqrt, cplx* den_sqrt, cudaStream_t stream);
+
+// solver.cu
+struct LinOp {
+  std::function<int(const cplx*, cplx*, cudaStream_t)> apply;   // out = A in
+};
+struct RelaxInfo {
+  double initial_value[2], final_value[2], ritz_value[2];
+  int multiplications, applications;
+};
+int dense_matvec(const cplx* M, int64_t rows, int64_t cols, int64_t ld, const cplx* x, cplx* y, cplx alpha, cplx beta,
+                 cudaStream_t stream);
+int lu_factor(cplx* A, int n, int* piv, int* singular_dev, cplx* scratch, cudaStream_t stream);
+int lu_solve(const cplx* LU, int n, const int* piv, cplx* x, cudaStream_t stream);
+int gmres(const LinOp& A, const cplx* b, cplx* x, int64_t n, double rtol, int restart, int maxiter, cplx* work,
+          void* state_dev, int* iters_out, double* resid_out, cudaStream_t stream);
+size_t gmres_state_bytes();
+int relax(const LinOp& M, cplx* v, int64_t n, int max_mults, double tol, int k, cplx* work, void* state_dev,
+          RelaxInfo* info, cudaStream_t stream);
+size_t relax_state_bytes();
 
 }  // namespace carc

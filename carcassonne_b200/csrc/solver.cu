@@ -1,0 +1,762 @@
+// Device-resident center-site eigen-solver: restarted Arnoldi on N^-1 H ("relaxOver", reference utils.py:805-878),
+// with N^-1 applied either by a pivoted LU of the dense normalization matrix (scipy.linalg.lu_factor / lu_solve,
+// utils.py:816-818) or by restarted GMRES on the normalization operator (scipy.sparse.linalg.gmres, utils.py:819-825).
+//
+// The state vector, the Krylov basis and every scalar of the iteration stay in HBM: the host only enqueues kernels
+// and reads back one small record per restart (the Ritz value, to evaluate the stopping rule) -- the eigenvector
+// never leaves the device.  Vector algebra (classical Gram-Schmidt projections, norms, the k x k projected matrix,
+// the Ritz combination) runs in fused single-CTA kernels with warp-shuffle reductions: the vectors are N = D^4 d
+// long (128 KiB at D = 8) and live in L2, so these kernels are latency-bound and one CTA avoids grid-wide
+// synchronisation; the k x k non-Hermitian eigenproblem (scipy.linalg.eig -> zgeev in the reference) is solved
+// by thread 0 of the same kernel with a shifted QR iteration.
+#include <math.h>
+
+#include <vector>
+
+#include "carc_internal.h"
+#include "common.cuh"
+
+namespace carc {
+
+namespace {
+
+constexpr int VT = 1024;      // threads of the single-CTA vector kernels
+constexpr int KMAX = 8;       // largest Krylov dimension supported on device
+constexpr int GM_MAX = 64;    // largest GMRES restart length
+
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ cplx cmulc(cplx a, cplx b) { return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cplx cscale(cplx a, double s) { return make_double2(a.x * s, a.y * s); }
+__device__ __forceinline__ double cabs2(cplx a) { return a.x * a.x + a.y * a.y; }
+__device__ __forceinline__ cplx cdiv(cplx a, cplx b) {
+  const double d = b.x * b.x + b.y * b.y;
+  return make_double2((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d);
+}
+
+// block-wide sum of up to NV complex values per thread (fixed order -> deterministic); result valid in all threads
+template <int NV>
+__device__ __forceinline__ void block_csum(cplx (&v)[NV], cplx* sh /* [32 * NV] */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    v[q].x = warp_sum(v[q].x);
+    v[q].y = warp_sum(v[q].y);
+  }
+  __syncthreads();
+  if (lane == 0)
+#pragma unroll
+    for (int q = 0; q < NV; ++q) sh[w * NV + q] = v[q];
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    cplx t = make_double2(0.0, 0.0);
+    for (int i = 0; i < nw; ++i) t = cadd(t, sh[i * NV + q]);
+    v[q] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// dense operator: y = M x, M [rows, cols] row-major; one warp per row
+__global__ void __launch_bounds__(256) zgemv_kernel(const cplx* __restrict__ M, int64_t rows, int64_t cols, int64_t ld,
+                                                    const cplx* __restrict__ x, cplx* __restrict__ y, cplx alpha,
+                                                    cplx beta) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const cplx* m = M + row * ld;
+  cplx acc = make_double2(0.0, 0.0);
+  for (int64_t c = lane; c < cols; c += 32) acc = cadd(acc, cmul(m[c], x[c]));
+  acc.x = warp_sum(acc.x);
+  acc.y = warp_sum(acc.y);
+  if (lane == 0) {
+    cplx r = cmul(alpha, acc);
+    if (beta.x != 0.0 || beta.y != 0.0) r = cadd(r, cmul(beta, y[row]));
+    y[row] = r;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LU with partial pivoting, row-major, in place.  Per column: (1) pivot search + whole-row swap + reciprocal,
+// (2) scale the column and rank-1 update of the rest of the panel; per panel: triangular solve for the U block row
+// and one DMMA GEMM for the trailing matrix.
+__global__ void __launch_bounds__(1024) lu_pivot_kernel(cplx* __restrict__ A, int n, int j, int* __restrict__ piv,
+                                                        cplx* __restrict__ inv_pivot, int* __restrict__ singular) {
+  __shared__ double s_val[32];
+  __shared__ int s_idx[32];
+  __shared__ int s_p;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  double best = -1.0;
+  int bi = j;
+  for (int i = j + tid; i < n; i += blockDim.x) {
+    const cplx a = A[(int64_t)i * n + j];
+    const double m = fabs(a.x) + fabs(a.y);   // LAPACK izamax uses |re| + |im|
+    if (m > best) { best = m; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (lane == 0) { s_val[w] = best; s_idx[w] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    double b = s_val[0];
+    int p = s_idx[0];
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i)
+      if (s_val[i] > b || (s_val[i] == b && s_idx[i] < p)) { b = s_val[i]; p = s_idx[i]; }
+    s_p = p;
+    piv[j] = p;
+    if (!(b > 0.0)) *singular = 1;
+  }
+  __syncthreads();
+  const int p = s_p;
+  if (p != j) {
+    for (int c = tid; c < n; c += blockDim.x) {
+      const cplx a = A[(int64_t)j * n + c], b = A[(int64_t)p * n + c];
+      A[(int64_t)j * n + c] = b;
+      A[(int64_t)p * n + c] = a;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const cplx d = A[(int64_t)j * n + j];
+    *inv_pivot = (d.x != 0.0 || d.y != 0.0) ? cdiv(make_double2(1.0, 0.0), d) : make_double2(0.0, 0.0);
+  }
+}
+
+// rows i > j: l = A[i][j] * inv; A[i][j] = l; A[i][c] -= l * A[j][c] for j < c < c_end.  32 columns x 8 rows per CTA pass.
+__global__ void __launch_bounds__(256) lu_update_kernel(cplx* __restrict__ A, int n, int j, int c_end,
+                                                        const cplx* __restrict__ inv_pivot) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const cplx inv = *inv_pivot;
+  for (int i = j + 1 + blockIdx.x * 8 + ty; i < n; i += gridDim.x * 8) {
+    cplx* row = A + (int64_t)i * n;
+    const cplx l = cmul(row[j], inv);
+    for (int c = j + 1 + tx; c < c_end; c += 32) row[c] = csub(row[c], cmul(l, A[(int64_t)j * n + c]));
+    __syncwarp();
+    if (tx == 0) row[j] = l;
+  }
+}
+
+// U12 = L11^-1 A12 : rows [j0, j0+nb), columns [c0, n); one thread per column, L11 (unit lower) in shared memory
+__global__ void __launch_bounds__(256) lu_trsm_kernel(cplx* __restrict__ A, int n, int j0, int nb, int c0) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* L = reinterpret_cast<cplx*>(smem_raw);  // nb x nb
+  for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) L[e] = A[(int64_t)(j0 + e / nb) * n + j0 + e % nb];
+  __syncthreads();
+  const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  for (int r = 1; r < nb; ++r) {
+    cplx acc = A[(int64_t)(j0 + r) * n + c];
+    for (int k = 0; k < r; ++k) acc = csub(acc, cmul(L[r * nb + k], A[(int64_t)(j0 + k) * n + c]));
+    A[(int64_t)(j0 + r) * n + c] = acc;
+  }
+}
+
+// b <- P b (apply the recorded row interchanges in order); single thread block, sequential by nature
+__global__ void lu_permute_kernel(cplx* __restrict__ b, const int* __restrict__ piv, int n) {
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    for (int j = 0; j < n; ++j) {
+      const int p = piv[j];
+      if (p != j) { const cplx t = b[j]; b[j] = b[p]; b[p] = t; }
+    }
+}
+
+// diagonal block solve (in place on x[j0 .. j0+nb)): lower => unit lower forward substitution, else upper backward
+__global__ void __launch_bounds__(64) tri_block_kernel(const cplx* __restrict__ A, int n, int j0, int nb, int lower,
+                                                       cplx* __restrict__ x) {
+  __shared__ cplx xs[64];
+  const int t = threadIdx.x;
+  if (t < nb) xs[t] = x[j0 + t];
+  __syncthreads();
+  if (lower) {
+    for (int k = 0; k < nb; ++k) {
+      const cplx xk = xs[k];
+      if (t > k && t < nb) xs[t] = csub(xs[t], cmul(A[(int64_t)(j0 + t) * n + j0 + k], xk));
+      __syncthreads();
+    }
+  } else {
+    for (int k = nb - 1; k >= 0; --k) {
+      if (t == k) xs[k] = cdiv(xs[k], A[(int64_t)(j0 + k) * n + j0 + k]);
+      __syncthreads();
+      const cplx xk = xs[k];
+      if (t < k) xs[t] = csub(xs[t], cmul(A[(int64_t)(j0 + t) * n + j0 + k], xk));
+      __syncthreads();
+    }
+  }
+  if (t < nb) x[j0 + t] = xs[t];
+}
+
+// x[r] -= sum_{k in block} A[r][j0 + k] * x[j0 + k] for rows r in [r0, r1); one warp per row
+__global__ void __launch_bounds__(256) tri_update_kernel(const cplx* __restrict__ A, int n, int j0, int nb, int r0, int r1,
+                                                         cplx* __restrict__ x) {
+  const int lane = threadIdx.x & 31;
+  const int r = r0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= r1) return;
+  cplx acc = make_double2(0.0, 0.0);
+  for (int k = lane; k < nb; k += 32) acc = cadd(acc, cmul(A[(int64_t)r * n + j0 + k], x[j0 + k]));
+  acc.x = warp_sum(acc.x);
+  acc.y = warp_sum(acc.y);
+  if (lane == 0) x[r] = csub(x[r], acc);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// small dense complex eigenproblem (k <= KMAX), thread 0 only.  Eigenvalues by Hessenberg reduction + shifted QR
+// with deflation; the eigenvector of the selected eigenvalue by inverse iteration.
+__device__ void small_eig_min_real(int k, const cplx* Min /* k x k row-major */, cplx* lambda_out, cplx* vec_out) {
+  cplx H[KMAX][KMAX];
+  for (int i = 0; i < k; ++i)
+    for (int j = 0; j < k; ++j) H[i][j] = Min[i * k + j];
+  // Hessenberg form by Givens rotations (similarity)
+  for (int col = 0; col + 2 < k; ++col)
+    for (int row = k - 1; row > col + 1; --row) {
+      const cplx a = H[row - 1][col], b = H[row][col];
+      const double nb2 = cabs2(b);
+      if (nb2 == 0.0) continue;
+      const double r = sqrt(cabs2(a) + nb2);
+      const cplx c = cscale(a, 1.0 / r), s = cscale(b, 1.0 / r);   // G = [[conj c, conj s], [-s, c]]
+      for (int j = 0; j < k; ++j) {
+        const cplx x = H[row - 1][j], y = H[row][j];
+        H[row - 1][j] = cadd(cmulc(c, x), cmulc(s, y));
+        H[row][j] = csub(cmul(c, y), cmul(s, x));
+      }
+      for (int i = 0; i < k; ++i) {   // right-multiply by G^H
+        const cplx x = H[i][row - 1], y = H[i][row];
+        H[i][row - 1] = cadd(cmul(x, c), cmul(y, s));
+        H[i][row] = csub(cmulc(c, y), cmulc(s, x));   // y conj(c) - x conj(s)
+      }
+    }
+  cplx ev[KMAX];
+  int hi = k - 1;
+  int iter = 0;
+  double hnorm = 0.0;
+  for (int i = 0; i < k; ++i)
+    for (int j = 0; j < k; ++j) hnorm += cabs2(H[i][j]);
+  hnorm = sqrt(hnorm);
+  while (hi >= 0 && iter < 500) {
+    if (hi == 0) { ev[0] = H[0][0]; break; }
+    // deflation check
+    int l = hi;
+    while (l > 0) {
+      const double sc = sqrt(cabs2(H[l - 1][l - 1])) + sqrt(cabs2(H[l][l]));
+      if (sqrt(cabs2(H[l][l - 1])) <= 2.3e-16 * (sc > 0.0 ? sc : hnorm)) { H[l][l - 1] = make_double2(0.0, 0.0); break; }
+      --l;
+    }
+    if (l == hi) { ev[hi] = H[hi][hi]; --hi; iter = 0; continue; }
+    // Wilkinson shift from the trailing 2x2 of the active block
+    const cplx a = H[hi - 1][hi - 1], b = H[hi - 1][hi], c = H[hi][hi - 1], d = H[hi][hi];
+    const cplx tr = cadd(a, d), det = csub(cmul(a, d), cmul(b, c));
+    cplx disc = csub(cmul(cscale(tr, 0.5), cscale(tr, 0.5)), det);
+    // complex sqrt
+    const double dm = sqrt(sqrt(cabs2(disc)));
+    const double ang = 0.5 * atan2(disc.y, disc.x);
+    const cplx sq = make_double2(dm * cos(ang), dm * sin(ang));
+    const cplx e1 = cadd(cscale(tr, 0.5), sq), e2 = csub(cscale(tr, 0.5), sq);
+    cplx mu = cabs2(csub(e1, d)) < cabs2(csub(e2, d)) ? e1 : e2;
+    if (iter == 10 || iter == 20) mu = cadd(mu, make_double2(sqrt(cabs2(c)), 0.0));  // exceptional shift
+    // QR step on the active block [l, hi] with Givens rotations
+    cplx cs[KMAX], sn[KMAX];
+    for (int i = l; i <= hi; ++i) H[i][i] = csub(H[i][i], mu);
+    for (int i = l; i < hi; ++i) {
+      const cplx x = H[i][i], y = H[i + 1][i];
+      const double r = sqrt(cabs2(x) + cabs2(y));
+      if (r == 0.0) { cs[i] = make_double2(1.0, 0.0); sn[i] = make_double2(0.0, 0.0); continue; }
+      cs[i] = cscale(x, 1.0 / r);
+      sn[i] = cscale(y, 1.0 / r);
+      for (int j = 0; j < k; ++j) {
+        const cplx u = H[i][j], v = H[i + 1][j];
+        H[i][j] = cadd(cmulc(cs[i], u), cmulc(sn[i], v));
+        H[i + 1][j] = csub(cmul(cs[i], v), cmul(sn[i], u));
+      }
+    }
+    for (int i = l; i < hi; ++i) {
+      for (int r2 = 0; r2 < k; ++r2) {
+        const cplx u = H[r2][i], v = H[r2][i + 1];
+        H[r2][i] = cadd(cmul(u, cs[i]), cmul(v, sn[i]));
+        H[r2][i + 1] = csub(cmulc(cs[i], v), cmulc(sn[i], u));
+      }
+    }
+    for (int i = l; i <= hi; ++i) H[i][i] = cadd(H[i][i], mu);
+    ++iter;
+  }
+  while (hi > 0 && iter >= 500) { ev[hi] = H[hi][hi]; --hi; if (hi == 0) ev[0] = H[0][0]; }
+  int best = 0;
+  for (int i = 1; i < k; ++i)
+    if (ev[i].x < ev[best].x) best = i;
+  const cplx lam = ev[best];
+  *lambda_out = lam;
+  // inverse iteration on the original matrix with a slightly perturbed shift
+  double mnorm = 0.0;
+  for (int i = 0; i < k * k; ++i) mnorm += cabs2(Min[i]);
+  mnorm = sqrt(mnorm);
+  const cplx shift = cadd(lam, make_double2(1e-10 * (mnorm > 0.0 ? mnorm : 1.0), 0.0));
+  cplx x[KMAX];
+  for (int i = 0; i < k; ++i) x[i] = make_double2(1.0 / (1.0 + i), 0.3 / (2.0 + i));
+  for (int it = 0; it < 3; ++it) {
+    cplx M[KMAX][KMAX + 1];
+    for (int i = 0; i < k; ++i) {
+      for (int j = 0; j < k; ++j) M[i][j] = Min[i * k + j];
+      M[i][i] = csub(M[i][i], shift);
+      M[i][k] = x[i];
+    }
+    for (int col = 0; col < k; ++col) {
+      int p = col;
+      for (int r = col + 1; r < k; ++r)
+        if (cabs2(M[r][col]) > cabs2(M[p][col])) p = r;
+      if (p != col)
+        for (int j = 0; j <= k; ++j) { const cplx t = M[col][j]; M[col][j] = M[p][j]; M[p][j] = t; }
+      if (cabs2(M[col][col]) < 1e-300) M[col][col] = make_double2(1e-150, 0.0);
+      for (int r = col + 1; r < k; ++r) {
+        const cplx f = cdiv(M[r][col], M[col][col]);
+        for (int j = col; j <= k; ++j) M[r][j] = csub(M[r][j], cmul(f, M[col][j]));
+      }
+    }
+    for (int r = k - 1; r >= 0; --r) {
+      cplx acc = M[r][k];
+      for (int j = r + 1; j < k; ++j) acc = csub(acc, cmul(M[r][j], x[j]));
+      x[r] = cdiv(acc, M[r][r]);
+    }
+    double nx = 0.0;
+    for (int i = 0; i < k; ++i) nx += cabs2(x[i]);
+    nx = 1.0 / sqrt(nx);
+    for (int i = 0; i < k; ++i) x[i] = cscale(x[i], nx);
+  }
+  // LAPACK zgeev convention: unit Euclidean norm, component of largest modulus real (and positive).  With it a
+  // converged restart returns the previous state unchanged instead of rotated by an arbitrary phase, which the
+  // state-difference convergence policies rely on.
+  int big = 0;
+  for (int i = 1; i < k; ++i)
+    if (cabs2(x[i]) > cabs2(x[big])) big = i;
+  const double mod = sqrt(cabs2(x[big]));
+  if (mod > 0.0) {
+    const cplx ph = make_double2(x[big].x / mod, -x[big].y / mod);
+    for (int i = 0; i < k; ++i) x[i] = cmul(x[i], ph);
+    x[big].y = 0.0;
+  }
+  for (int i = 0; i < k; ++i) vec_out[i] = x[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Arnoldi state shared by the kernels below (device memory)
+struct RelaxState {
+  cplx ritz;          // lowest Ritz value of the last restart
+  cplx initial_value; // <v0, M v0>
+  cplx final_value;   // <v, M v> at exit
+  int kk;             // number of valid basis vectors in the current restart
+  int complete;       // Krylov space exhausted (breakdown)
+  int pad[2];
+};
+
+__global__ void restart_kernel(RelaxState* st) { st->kk = 1; }
+
+// v <- v / ||v||
+__global__ void __launch_bounds__(VT) normalize_kernel(cplx* __restrict__ v, int64_t n) {
+  __shared__ cplx sh[32];
+  cplx s[1] = {make_double2(0.0, 0.0)};
+  for (int64_t i = threadIdx.x; i < n; i += VT) s[0].x += cabs2(v[i]);
+  block_csum<1>(s, sh);
+  const double inv = 1.0 / sqrt(s[0].x);
+  for (int64_t i = threadIdx.x; i < n; i += VT) v[i] = cscale(v[i], inv);
+}
+
+// out = <a, b> (conjugating a) written to *dst
+__global__ void __launch_bounds__(VT) dot_kernel(const cplx* __restrict__ a, const cplx* __restrict__ b, int64_t n,
+                                                 cplx* __restrict__ dst) {
+  __shared__ cplx sh[32];
+  cplx s[1] = {make_double2(0.0, 0.0)};
+  for (int64_t i = threadIdx.x; i < n; i += VT) s[0] = cadd(s[0], cmulc(a[i], b[i]));
+  block_csum<1>(s, sh);
+  if (threadIdx.x == 0) *dst = s[0];
+}
+
+// Classical Gram-Schmidt step i (utils.py:852-858): w = MV_i - sum_{j<=i} <V_j, MV_i> V_j ; V_{i+1} = w / ||w||, or
+// flag breakdown when ||w|| <= 1e-14.  V, MV: [k, n] row-major.
+__global__ void __launch_bounds__(VT) arnoldi_step_kernel(cplx* __restrict__ V, const cplx* __restrict__ MV, int64_t n,
+                                                          int i, RelaxState* __restrict__ st) {
+  __shared__ cplx sh[32 * KMAX];
+  if (st->complete) return;
+  const cplx* w = MV + (int64_t)i * n;
+  cplx c[KMAX];
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) c[j] = make_double2(0.0, 0.0);
+  for (int64_t e = threadIdx.x; e < n; e += VT) {
+    const cplx we = w[e];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j)
+      if (j <= i) c[j] = cadd(c[j], cmulc(V[(int64_t)j * n + e], we));
+  }
+  block_csum<KMAX>(c, sh);
+  cplx* out = V + (int64_t)(i + 1) * n;
+  cplx nrm[1] = {make_double2(0.0, 0.0)};
+  for (int64_t e = threadIdx.x; e < n; e += VT) {
+    cplx we = w[e];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j)
+      if (j <= i) we = csub(we, cmul(c[j], V[(int64_t)j * n + e]));
+    out[e] = we;
+    nrm[0].x += cabs2(we);
+  }
+  block_csum<1>(nrm, sh);
+  const double norm = sqrt(nrm[0].x);
+  if (norm <= 1e-14) {
+    if (threadIdx.x == 0) { st->complete = 1; st->kk = i + 1; }
+    return;
+  }
+  const double inv = 1.0 / norm;
+  for (int64_t e = threadIdx.x; e < n; e += VT) out[e] = cscale(out[e], inv);
+  if (threadIdx.x == 0) st->kk = i + 2;
+}
+
+// projected matrix (utils.py:862), its lowest-real-part eigenpair (863-866), and the normalised Ritz vector
+// written to `next` (869-870 / 875-876).
+__global__ void __launch_bounds__(VT) ritz_kernel(const cplx* __restrict__ V, const cplx* __restrict__ MV, int64_t n,
+                                                  int kmax, cplx* __restrict__ next, RelaxState* __restrict__ st) {
+  __shared__ cplx sh[32 * KMAX];
+  __shared__ cplx small[KMAX * KMAX];
+  __shared__ cplx y[KMAX];
+  const int kk = st->kk < kmax ? st->kk : kmax;
+  for (int a = 0; a < kk; ++a) {
+    cplx c[KMAX];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) c[j] = make_double2(0.0, 0.0);
+    for (int64_t e = threadIdx.x; e < n; e += VT) {
+      const cplx va = V[(int64_t)a * n + e];
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j)
+        if (j < kk) c[j] = cadd(c[j], cmulc(va, MV[(int64_t)j * n + e]));
+    }
+    block_csum<KMAX>(c, sh);
+    if (threadIdx.x == 0)
+      for (int j = 0; j < kk; ++j) small[a * kk + j] = c[j];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    cplx lam;
+    cplx vec[KMAX];
+    small_eig_min_real(kk, small, &lam, vec);
+    st->ritz = lam;
+    for (int j = 0; j < kk; ++j) y[j] = vec[j];
+  }
+  __syncthreads();
+  cplx nrm[1] = {make_double2(0.0, 0.0)};
+  for (int64_t e = threadIdx.x; e < n; e += VT) {
+    cplx acc = make_double2(0.0, 0.0);
+    for (int j = 0; j < kk; ++j) acc = cadd(acc, cmul(y[j], V[(int64_t)j * n + e]));
+    next[e] = acc;
+    nrm[0].x += cabs2(acc);
+  }
+  block_csum<1>(nrm, sh);
+  const double inv = 1.0 / sqrt(nrm[0].x);
+  for (int64_t e = threadIdx.x; e < n; e += VT) next[e] = cscale(next[e], inv);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GMRES(m) pieces.  Hessenberg column, Givens rotations and the residual recurrence are kept on device.
+struct GmresState {
+  cplx h[(GM_MAX + 1) * GM_MAX];   // column-major: h[j * (m+1) + i]
+  cplx cs[GM_MAX], sn[GM_MAX];
+  cplx g[GM_MAX + 1];
+  cplx y[GM_MAX];
+  double resid;                    // |g[j+1]| after step j
+  double bnorm;
+  double rnorm0;
+  int breakdown;
+  int pad;
+};
+
+// r = b - (have_ax ? ax : 0); V0 = r / ||r||; g = (||r||, 0, ...)
+__global__ void __launch_bounds__(VT) gmres_start_kernel(const cplx* __restrict__ b, const cplx* __restrict__ ax,
+                                                         int64_t n, cplx* __restrict__ V0, GmresState* __restrict__ gs,
+                                                         int first) {
+  __shared__ cplx sh[32 * 2];
+  cplx s[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
+  for (int64_t i = threadIdx.x; i < n; i += VT) {
+    cplx r = b[i];
+    s[1].x += cabs2(r);
+    if (ax) r = csub(r, ax[i]);
+    V0[i] = r;
+    s[0].x += cabs2(r);
+  }
+  block_csum<2>(s, sh);
+  const double nr = sqrt(s[0].x);
+  const double inv = nr > 0.0 ? 1.0 / nr : 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += VT) V0[i] = cscale(V0[i], inv);
+  if (threadIdx.x == 0) {
+    if (first) gs->bnorm = sqrt(s[1].x);
+    gs->rnorm0 = nr;
+    gs->resid = nr;
+    gs->breakdown = 0;
+    for (int i = 0; i <= GM_MAX; ++i) gs->g[i] = make_double2(0.0, 0.0);
+    gs->g[0] = make_double2(nr, 0.0);
+  }
+}
+
+// step j: w (= A V_j, already stored in V_{j+1}) is orthogonalised against V_0..V_j (modified Gram-Schmidt),
+// normalised, the new Hessenberg column is rotated and the residual norm updated.
+__global__ void __launch_bounds__(VT) gmres_step_kernel(cplx* __restrict__ V, int64_t n, int j, int m,
+                                                        GmresState* __restrict__ gs) {
+  __shared__ cplx sh[32];
+  __shared__ cplx hcol[GM_MAX + 1];
+  cplx* w = V + (int64_t)(j + 1) * n;
+  for (int i = 0; i <= j; ++i) {
+    const cplx* vi = V + (int64_t)i * n;
+    cplx s[1] = {make_double2(0.0, 0.0)};
+    for (int64_t e = threadIdx.x; e < n; e += VT) s[0] = cadd(s[0], cmulc(vi[e], w[e]));
+    block_csum<1>(s, sh);
+    for (int64_t e = threadIdx.x; e < n; e += VT) w[e] = csub(w[e], cmul(s[0], vi[e]));
+    if (threadIdx.x == 0) hcol[i] = s[0];
+    __syncthreads();
+  }
+  cplx s[1] = {make_double2(0.0, 0.0)};
+  for (int64_t e = threadIdx.x; e < n; e += VT) s[0].x += cabs2(w[e]);
+  block_csum<1>(s, sh);
+  const double hn = sqrt(s[0].x);
+  const double inv = hn > 0.0 ? 1.0 / hn : 0.0;
+  for (int64_t e = threadIdx.x; e < n; e += VT) w[e] = cscale(w[e], inv);
+  if (threadIdx.x == 0) {
+    hcol[j + 1] = make_double2(hn, 0.0);
+    for (int i = 0; i < j; ++i) {   // previous rotations
+      const cplx a = hcol[i], b = hcol[i + 1];
+      hcol[i] = cadd(cmulc(gs->cs[i], a), cmulc(gs->sn[i], b));
+      hcol[i + 1] = csub(cmul(gs->cs[i], b), cmul(gs->sn[i], a));
+    }
+    const cplx a = hcol[j], b = hcol[j + 1];
+    const double r = sqrt(cabs2(a) + cabs2(b));
+    cplx c = make_double2(1.0, 0.0), sN = make_double2(0.0, 0.0);
+    if (r > 0.0) { c = cscale(a, 1.0 / r); sN = cscale(b, 1.0 / r); }
+    gs->cs[j] = c;
+    gs->sn[j] = sN;
+    hcol[j] = make_double2(r, 0.0);
+    hcol[j + 1] = make_double2(0.0, 0.0);
+    const cplx g0 = gs->g[j];
+    gs->g[j] = cmulc(c, g0);
+    gs->g[j + 1] = cscale(cmul(sN, g0), -1.0);
+    gs->resid = sqrt(cabs2(gs->g[j + 1]));
+    if (hn <= 1e-300) gs->breakdown = 1;
+    for (int i = 0; i <= j + 1; ++i) gs->h[j * (m + 1) + i] = hcol[i];
+  }
+}
+
+// x += V[:, 0..jj) y with R y = g (back substitution by thread 0)
+__global__ void __launch_bounds__(VT) gmres_update_kernel(const cplx* __restrict__ V, int64_t n, int jj, int m,
+                                                          cplx* __restrict__ x, GmresState* __restrict__ gs) {
+  __shared__ cplx y[GM_MAX];
+  if (threadIdx.x == 0) {
+    for (int i = jj - 1; i >= 0; --i) {
+      cplx acc = gs->g[i];
+      for (int l = i + 1; l < jj; ++l) acc = csub(acc, cmul(gs->h[l * (m + 1) + i], y[l]));
+      const cplx d = gs->h[i * (m + 1) + i];
+      y[i] = (d.x != 0.0 || d.y != 0.0) ? cdiv(acc, d) : make_double2(0.0, 0.0);
+    }
+  }
+  __syncthreads();
+  for (int64_t e = threadIdx.x; e < n; e += VT) {
+    cplx acc = x[e];
+    for (int l = 0; l < jj; ++l) acc = cadd(acc, cmul(y[l], V[(int64_t)l * n + e]));
+    x[e] = acc;
+  }
+}
+
+}  // namespace
+
+// ===================================================================================================
+int dense_matvec(const cplx* M, int64_t rows, int64_t cols, int64_t ld, const cplx* x, cplx* y, cplx alpha, cplx beta,
+                 cudaStream_t stream) {
+  if (rows <= 0) return CARC_OK;
+  zgemv_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(M, rows, cols, ld, x, y, alpha, beta);
+  CARC_CHECK_CUDA(cudaGetLastError());
+  return CARC_OK;
+}
+
+int lu_factor(cplx* A, int n, int* piv, int* singular_dev, cplx* scratch, cudaStream_t stream) {
+  CARC_REQUIRE(n >= 1, CARC_ERR_VALUE, "lu_factor: n must be positive");
+  const int NB = 64;
+  const cplx minus_one = make_double2(-1.0, 0.0), one = make_double2(1.0, 0.0);
+  CARC_CHECK_CUDA(cudaMemsetAsync(singular_dev, 0, sizeof(int), stream));
+  static bool configured[16] = {false};
+  int dev = 0;
+  CARC_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 16 && !configured[dev]) {
+    CARC_CHECK_CUDA(cudaFuncSetAttribute(lu_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NB * NB * 16));
+    configured[dev] = true;
+  }
+  for (int j0 = 0; j0 < n; j0 += NB) {
+    const int nb = n - j0 < NB ? n - j0 : NB;
+    const int pe = j0 + nb;
+    for (int j = j0; j < pe; ++j) {
+      lu_pivot_kernel<<<1, 1024, 0, stream>>>(A, n, j, piv, scratch, singular_dev);
+      const int rows = n - j - 1;
+      if (rows > 0) {
+        int blocks = (rows + 7) / 8;
+        if (blocks > 148 * 4) blocks = 148 * 4;
+        lu_update_kernel<<<blocks, 256, 0, stream>>>(A, n, j, pe, scratch);
+      }
+    }
+    if (pe < n) {
+      const int cols = n - pe;
+      lu_trsm_kernel<<<(cols + 255) / 256, 256, nb * nb * 16, stream>>>(A, n, j0, nb, pe);
+      // A22 -= L21 U12
+      GemmOut o;
+      o.m_div = n; o.m_s1 = 0; o.m_s0 = n;
+      o.n_div = n; o.n_s1 = 0; o.n_s0 = 1;
+      int rc = zgemm(OP_N, OP_N, cols, cols, nb, minus_one, A + (int64_t)pe * n + j0, n, A + (int64_t)j0 * n + pe, n, one,
+                     A + (int64_t)pe * n + pe, &o, nullptr, 1, 0, 0, 0, stream);
+      if (rc) return rc;
+    }
+  }
+  CARC_CHECK_CUDA(cudaGetLastError());
+  return CARC_OK;
+}
+
+int lu_solve(const cplx* LU, int n, const int* piv, cplx* x, cudaStream_t stream) {
+  const int NB = 64;
+  lu_permute_kernel<<<1, 32, 0, stream>>>(x, piv, n);
+  for (int j0 = 0; j0 < n; j0 += NB) {
+    const int nb = n - j0 < NB ? n - j0 : NB;
+    tri_block_kernel<<<1, 64, 0, stream>>>(LU, n, j0, nb, 1, x);
+    const int r0 = j0 + nb;
+    if (r0 < n) tri_update_kernel<<<(n - r0 + 7) / 8, 256, 0, stream>>>(LU, n, j0, nb, r0, n, x);
+  }
+  for (int j0 = ((n - 1) / NB) * NB; j0 >= 0; j0 -= NB) {
+    const int nb = n - j0 < NB ? n - j0 : NB;
+    tri_block_kernel<<<1, 64, 0, stream>>>(LU, n, j0, nb, 0, x);
+    if (j0 > 0) tri_update_kernel<<<(j0 + 7) / 8, 256, 0, stream>>>(LU, n, j0, nb, 0, j0, x);
+  }
+  CARC_CHECK_CUDA(cudaGetLastError());
+  return CARC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+int gmres(const LinOp& A, const cplx* b, cplx* x, int64_t n, double rtol, int restart, int maxiter, cplx* work,
+          void* state_dev, int* iters_out, double* resid_out, cudaStream_t stream) {
+  // work: (restart + 2) * n complex; state_dev: sizeof(GmresState)
+  CARC_REQUIRE(restart >= 1 && restart <= GM_MAX, CARC_ERR_VALUE, "gmres: restart %d outside 1..%d", restart, GM_MAX);
+  GmresState* gs = reinterpret_cast<GmresState*>(state_dev);
+  cplx* V = work;
+  cplx* ax = work + (int64_t)(restart + 1) * n;
+  CARC_CHECK_CUDA(cudaMemsetAsync(x, 0, sizeof(cplx) * n, stream));
+  int total = 0;
+  double host[3];
+  bool first = true;
+  for (int cycle = 0; cycle < maxiter; ++cycle) {
+    if (!first) {
+      int rc = A.apply(x, ax, stream);
+      if (rc) return rc;
+    }
+    gmres_start_kernel<<<1, VT, 0, stream>>>(b, first ? nullptr : ax, n, V, gs, first ? 1 : 0);
+    CARC_CHECK_CUDA(cudaMemcpyAsync(host, &gs->resid, sizeof(double) * 3, cudaMemcpyDeviceToHost, stream));
+    CARC_CHECK_CUDA(cudaStreamSynchronize(stream));
+    first = false;
+    const double target = rtol * host[1];
+    if (host[0] <= target || host[1] == 0.0) {
+      *iters_out = total;
+      *resid_out = host[0];
+      return CARC_OK;
+    }
+    int jj = 0;
+    bool converged = false;
+    for (int j = 0; j < restart; ++j) {
+      int rc = A.apply(V + (int64_t)j * n, V + (int64_t)(j + 1) * n, stream);
+      if (rc) return rc;
+      gmres_step_kernel<<<1, VT, 0, stream>>>(V, n, j, restart, gs);
+      ++total;
+      jj = j + 1;
+      CARC_CHECK_CUDA(cudaMemcpyAsync(host, &gs->resid, sizeof(double), cudaMemcpyDeviceToHost, stream));
+      int bd = 0;
+      CARC_CHECK_CUDA(cudaMemcpyAsync(&bd, &gs->breakdown, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      CARC_CHECK_CUDA(cudaStreamSynchronize(stream));
+      if (host[0] <= target || bd) { converged = true; break; }
+    }
+    gmres_update_kernel<<<1, VT, 0, stream>>>(V, n, jj, restart, x, gs);
+    CARC_CHECK_CUDA(cudaGetLastError());
+    if (converged) {
+      *iters_out = total;
+      *resid_out = host[0];
+      return CARC_OK;
+    }
+  }
+  *iters_out = total;
+  *resid_out = host[0];
+  set_error("gmres: no convergence after %d iterations (residual %.3e)", total, host[0]);
+  return CARC_ERR_NO_CONVERGENCE;
+}
+
+size_t gmres_state_bytes() { return sizeof(GmresState); }
+
+// ---------------------------------------------------------------------------------------------------
+int relax(const LinOp& M, cplx* v, int64_t n, int max_mults, double tol, int k, cplx* work, void* state_dev,
+          RelaxInfo* info, cudaStream_t stream) {
+  // work: (2k + 2) * n complex.  M applies N^-1 H.
+  CARC_REQUIRE(k >= 1 && k <= KMAX, CARC_ERR_UNSUPPORTED, "relax: Krylov dimension %d outside 1..%d", k, KMAX);
+  RelaxState* st = reinterpret_cast<RelaxState*>(state_dev);
+  cplx* V = work;                       // [k+1, n] (one spare row for the last CGS output)
+  cplx* MV = work + (int64_t)(k + 1) * n;  // [k, n]
+  cplx* tmp = MV + (int64_t)k * n;      // [n]
+  CARC_CHECK_CUDA(cudaMemsetAsync(st, 0, sizeof(RelaxState), stream));
+  normalize_kernel<<<1, VT, 0, stream>>>(v, n);
+  int rc = M.apply(v, tmp, stream);
+  if (rc) return rc;
+  dot_kernel<<<1, VT, 0, stream>>>(v, tmp, n, &st->initial_value);
+  int mults = 0, total_applies = 1;
+  bool have_last = false;
+  double last_re = 0.0, last_im = 0.0;
+  bool complete = (int64_t)k == n;
+  RelaxState host;
+  for (;;) {
+    CARC_CHECK_CUDA(cudaMemcpyAsync(V, v, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, stream));
+    restart_kernel<<<1, 1, 0, stream>>>(st);
+    for (int i = 0; i < k; ++i) {
+      // after a breakdown the remaining multiplications act on stale rows and are ignored by the Ritz step; the
+      // reference stops multiplying at that point (utils.py:854-858) -- so do we, at the next host check below
+      rc = M.apply(V + (int64_t)i * n, MV + (int64_t)i * n, stream);
+      if (rc) return rc;
+      ++total_applies;
+      if (i < k - 1) {
+        arnoldi_step_kernel<<<1, VT, 0, stream>>>(V, MV, n, i, st);
+        if ((int64_t)(i + 2) > n) {   // tiny spaces: check for breakdown before touching row i+1 again
+          CARC_CHECK_CUDA(cudaMemcpyAsync(&host, st, sizeof(RelaxState), cudaMemcpyDeviceToHost, stream));
+          CARC_CHECK_CUDA(cudaStreamSynchronize(stream));
+          if (host.complete) break;
+        }
+      }
+    }
+    mults += k;
+    ritz_kernel<<<1, VT, 0, stream>>>(V, MV, n, k, v, st);
+    CARC_CHECK_CUDA(cudaMemcpyAsync(&host, st, sizeof(RelaxState), cudaMemcpyDeviceToHost, stream));
+    CARC_CHECK_CUDA(cudaStreamSynchronize(stream));
+    if (host.complete) complete = true;
+    const double dre = host.ritz.x - last_re, dim = host.ritz.y - last_im;
+    const bool small_change = have_last && sqrt(dre * dre + dim * dim) <= tol;
+    const bool out_of_budget = max_mults > 0 && mults >= max_mults;
+    if (complete || small_change || out_of_budget) break;
+    last_re = host.ritz.x;
+    last_im = host.ritz.y;
+    have_last = true;
+  }
+  rc = M.apply(v, tmp, stream);
+  if (rc) return rc;
+  ++total_applies;
+  dot_kernel<<<1, VT, 0, stream>>>(v, tmp, n, &st->final_value);
+  CARC_CHECK_CUDA(cudaMemcpyAsync(&host, st, sizeof(RelaxState), cudaMemcpyDeviceToHost, stream));
+  CARC_CHECK_CUDA(cudaStreamSynchronize(stream));
+  info->initial_value[0] = host.initial_value.x; info->initial_value[1] = host.initial_value.y;
+  info->final_value[0] = host.final_value.x; info->final_value[1] = host.final_value.y;
+  info->ritz_value[0] = host.ritz.x; info->ritz_value[1] = host.ritz.y;
+  info->multiplications = mults;
+  info->applications = total_applies;
+  // utils.py:871: (final - initial) / (|final| + |initial|) > 1 + 1e-7 (compared on the real part)
+  const double fi = host.final_value.x - host.initial_value.x;
+  const double den = hypot(host.final_value.x, host.final_value.y) + hypot(host.initial_value.x, host.initial_value.y);
+  if (den > 0.0 && fi / den > 1.0 + 1e-7) {
+    set_error("relax: expectation rose from %.17g to %.17g", host.initial_value.x, host.final_value.x);
+    return CARC_ERR_RELAX_FAILED;
+  }
+  return CARC_OK;
+}
+
+size_t relax_state_bytes() { return sizeof(RelaxState); }
+
+}  // namespace carc

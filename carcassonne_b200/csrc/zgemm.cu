@@ -37,6 +37,8 @@ struct GemmParams {
   uint32_t a_sign, b_sign;    // 0x80000000 to conjugate
   cplx alpha, beta;
   GemmOut out;
+  const int64_t* rowoff;      // optional per-row / per-column output offset tables (override `out`)
+  const int64_t* coloff;
 };
 
 __device__ __forceinline__ double flip(double x, uint32_t mask) {
@@ -142,14 +144,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) zgemm_kernel(GemmParams p) {
   for (int i = 0; i < 4; ++i) {
     const int64_t m = m0 + wm * 32 + i * 8 + r;
     if (m >= p.M) continue;
-    const int64_t moff = (m / p.out.m_div) * p.out.m_s1 + (m % p.out.m_div) * p.out.m_s0;
+    const int64_t moff = p.rowoff ? p.rowoff[m] : (m / p.out.m_div) * p.out.m_s1 + (m % p.out.m_div) * p.out.m_s0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int64_t n = n0 + wn * 32 + j * 8 + 2 * c + h;
         if (n >= p.N) continue;
-        const int64_t off = moff + (n / p.out.n_div) * p.out.n_s1 + (n % p.out.n_div) * p.out.n_s0;
+        const int64_t off =
+            moff + (p.coloff ? p.coloff[n] : (n / p.out.n_div) * p.out.n_s1 + (n % p.out.n_div) * p.out.n_s0);
         const double re = h ? acc[i][j].re1 : acc[i][j].re0;
         const double im = h ? acc[i][j].im1 : acc[i][j].im0;
         cplx v;
@@ -183,11 +186,44 @@ __global__ void __launch_bounds__(256, 1) dmma_peak_kernel(double* out, int iter
   if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// table[i] = sum_l digit_l(i) * stride_l, digits of i taken row-major over `extent` (last level fastest)
+struct IndexLevels {
+  int n;
+  int64_t extent[CARC_MAX_RANK], stride[CARC_MAX_RANK];
+};
+__global__ void __launch_bounds__(256) index_table_kernel(IndexLevels lv, int64_t total, int64_t* __restrict__ table) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int64_t rem = i, off = 0;
+  for (int l = lv.n - 1; l >= 0; --l) {
+    const int64_t q = rem / lv.extent[l];
+    off += (rem - q * lv.extent[l]) * lv.stride[l];
+    rem = q;
+  }
+  table[i] = off;
+}
+
 }  // namespace
+
+int index_table(int nlevels, const int64_t* extents, const int64_t* strides, int64_t* table, cudaStream_t stream) {
+  CARC_REQUIRE(nlevels >= 0 && nlevels <= CARC_MAX_RANK, CARC_ERR_RANK, "index_table: %d levels unsupported", nlevels);
+  IndexLevels lv;
+  lv.n = nlevels;
+  int64_t total = 1;
+  for (int l = 0; l < nlevels; ++l) {
+    CARC_REQUIRE(extents[l] > 0, CARC_ERR_VALUE, "index_table: non-positive extent");
+    lv.extent[l] = extents[l];
+    lv.stride[l] = strides[l];
+    total *= extents[l];
+  }
+  index_table_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(lv, total, table);
+  CARC_CHECK_CUDA(cudaGetLastError());
+  return CARC_OK;
+}
 
 int zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, cplx alpha, const cplx* A, int64_t lda, const cplx* B,
           int64_t ldb, cplx beta, cplx* C, const GemmOut* out, const GemmKMap* kmap, int64_t batch, int64_t strideA,
-          int64_t strideB, int64_t strideC, cudaStream_t stream) {
+          int64_t strideB, int64_t strideC, cudaStream_t stream, const int64_t* rowoff, const int64_t* coloff) {
   CARC_REQUIRE(opA >= 0 && opA <= 3 && opB >= 0 && opB <= 3, CARC_ERR_VALUE, "zgemm: invalid op");
   CARC_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 0, CARC_ERR_VALUE, "zgemm: negative dimension");
   if (M == 0 || N == 0 || batch == 0) return CARC_OK;
@@ -207,6 +243,7 @@ int zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, cplx alpha, const c
   p.a_sign = (opA == OP_C || opA == OP_J) ? 0x80000000u : 0u;
   p.b_sign = (opB == OP_C || opB == OP_J) ? 0x80000000u : 0u;
   p.alpha = alpha; p.beta = beta;
+  p.rowoff = rowoff; p.coloff = coloff;
   p.a_kdiv = p.a_ks1 = p.b_kdiv = p.b_ks1 = 0;
   if (kmap) {
     CARC_REQUIRE((!kmap->a_kdiv || p.a_kcontig) && (!kmap->b_kdiv || p.b_kcontig), CARC_ERR_VALUE,

@@ -57,6 +57,45 @@ def gemm(opA, opB, M, N, K, A, lda, B, ldb, Cbuf, alpha=1.0, beta=0.0, out_map=N
         done += nb
 
 
+_TABLES = {}
+
+
+def index_table(levels):
+    """Device int64 table t[i] = sum_l digit_l(i) * stride_l for levels = ((extent, stride), ...), digits taken
+    row-major (last level fastest).  Cached: the same few layouts recur on every sweep iteration."""
+    levels = tuple((int(e), int(s)) for e, s in levels if int(e) != 1) or ((1, 0),)
+    key = (torch.cuda.current_device(), levels)
+    t = _TABLES.get(key)
+    if t is None:
+        if len(_TABLES) > 512:
+            _TABLES.clear()
+        total = _prod(e for e, _ in levels)
+        t = torch.empty(max(total, 1), dtype=torch.int64, device="cuda")
+        nl = len(levels)
+        check(lib.carc_index_table(nl, (C.c_int64 * nl)(*[e for e, _ in levels]),
+                                   (C.c_int64 * nl)(*[s for _, s in levels]), C.c_void_p(t.data_ptr()), _stream()))
+        _TABLES[key] = t
+    return t
+
+
+def gemm_scatter(opA, opB, M, N, K, A, lda, B, ldb, Cbuf, row_levels, col_levels, alpha=1.0, beta=0.0,
+                 batch=1, strideA=0, strideB=0, strideC=0, a_offset=0, b_offset=0, c_offset=0):
+    """C[rowoff(m) + coloff(n)] = alpha * op(A) op(B) + beta * C: a contraction written straight into the layout
+    the reference's final ``join`` would produce (carc_zgemm_tab)."""
+    if M * N * batch == 0:
+        return
+    rt = index_table(row_levels)
+    ct = index_table(col_levels)
+    done = 0
+    while done < batch:
+        nb = min(_MAX_BATCH, batch - done)
+        check(lib.carc_zgemm_tab(opA, opB, M, N, K, _lib.cplx2(alpha), _ptr(A, a_offset + done * strideA), lda,
+                                 _ptr(B, b_offset + done * strideB), ldb, _lib.cplx2(beta),
+                                 _ptr(Cbuf, c_offset + done * strideC), C.c_void_p(rt.data_ptr()),
+                                 C.c_void_p(ct.data_ptr()), nb, strideA, strideB, strideC, _stream()))
+        done += nb
+
+
 class DeviceData:
     """complex128 tensor in device memory; API of the reference's NDArrayData."""
 
@@ -315,6 +354,23 @@ class DeviceData:
         if self.ndim != 2:
             raise ValueError("Adjoint may only be computed for rank 2 tensors.")
         return self._permuted([1, 0], conj=1)
+
+    def reverseLastAxis(self):  # data/__init__.py:321-323
+        return DeviceData(torch.flip(self._t, dims=(-1,)).contiguous())
+
+    def splitAtByRoot(self, index, root):  # data/__init__.py:336-340
+        d = round(self.shape[index] ** (1.0 / root))
+        return self.splitAt(index, *(d,) * root)
+
+    def __getitem__(self, index):
+        """Sub-block copy (used for the column slices of the operator compressors, system/_2d.py:312-356)."""
+        return DeviceData(self._t[index].contiguous())
+
+    def __setitem__(self, index, value):
+        self._t[index] = value._t if isinstance(value, DeviceData) else value
+
+    def __str__(self):
+        return "DeviceData({})".format(self.toArray())
 
     # -- contraction ------------------------------------------------------------------------------------
     def contractWith(self, other, self_axes, other_axes):

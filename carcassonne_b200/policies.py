@@ -1,0 +1,269 @@
+"""Run-loop policies: when to grow the bandwidth, which way to contract, how hard to compress, when to stop.
+
+Host-side orchestration with the class names and behaviour of the reference's ``carcassonne/policies.py``; the
+numerical work each policy triggers runs on the device through the bound ``System``.  A policy object is a
+template: ``createBindingToSystem(system)`` returns a bound copy-on-read view whose ``apply`` / ``update`` /
+``reset`` / ``converged`` see ``self.system`` (reference policies.py:12-44).
+"""
+import logging
+
+import numpy as np
+
+from .utils import O
+
+log = logging.getLogger(__name__)
+
+
+class _Binding:
+    """View of a policy bound to one system.  Attribute reads fall through to the template policy; attribute writes
+    stay on the binding, so one template can serve several systems."""
+
+    def __init__(self, policy, system):
+        object.__setattr__(self, "forward", policy)
+        object.__setattr__(self, "system", system)
+
+    def __getattr__(self, name):
+        value = getattr(object.__getattribute__(self, "forward"), name)
+        if callable(value) and hasattr(value, "__func__"):
+            return value.__func__.__get__(self, type(self))   # rebind methods so that they see self.system
+        return value
+
+
+class Policy:
+    def createBindingToSystem(self, system):
+        return _Binding(self, system)
+
+
+# kept for API compatibility with code that names the reference's proxy classes
+Proxy = ApplyProxy = ConvergedProxy = ResetProxy = UpdateProxy = _Binding
+
+
+# -- bandwidth increase ---------------------------------------------------------------------------------------------
+class BandwidthIncreasePolicy(Policy):
+    pass
+
+
+class AllDirectionsIncrementBandwidthIncreasePolicy(BandwidthIncreasePolicy):
+    def __init__(self, increment=1):
+        self.increment = increment
+
+    def apply(self):
+        log.info("Increasing bandwidth in all directions by %s", self.increment)
+        for direction in (0, 1):
+            self.system.increaseBandwidth(direction, by=self.increment, do_as_much_as_possible=True)
+
+
+class OneDirectionIncrementBandwidthIncreasePolicy(BandwidthIncreasePolicy):
+    def __init__(self, direction, increment=1):
+        self.direction = direction
+        self.increment = increment
+
+    def apply(self):
+        log.info("Increasing bandwidth in direction %s by %s", self.direction, self.increment)
+        self.system.increaseBandwidth(self.direction, by=self.increment, do_as_much_as_possible=True)
+
+
+class AlternatingDirectionsIncrementBandwidthIncreasePolicy(BandwidthIncreasePolicy):
+    """The reference's version reads an ``increment`` it never sets (policies.py:50-56) and so cannot run; here the
+    increment is a constructor argument (default 1) and the direction alternates between the two axes."""
+
+    def __init__(self, directions=(0, 1), increment=1):
+        self.directions = directions
+        self.increment = increment
+        self.direction = 0
+
+    def apply(self):
+        self.system.increaseBandwidth(self.direction, by=self.increment, do_as_much_as_possible=True)
+        self.direction = 1 - self.direction
+
+
+# -- compression ----------------------------------------------------------------------------------------------------
+class CompressionPolicy(Policy):
+    pass
+
+
+class ConstantStateCompressionPolicy(CompressionPolicy):
+    def __init__(self, new_dimension):
+        self.new_dimension = new_dimension
+
+    def apply(self):
+        log.debug("Compressing to %s", self.new_dimension)
+        for corner_id in range(4):
+            for direction in range(2):
+                self.system.compressCornerStateTowards(corner_id, direction, self.new_dimension)
+
+
+class ConstantOperatorCompressionPolicy(CompressionPolicy):
+    """Fills the reference's empty "operator compression" slot (system/base.py:49): folds the two-site halves of
+    every corner into a compressed operator bond of at most ``new_dimension``."""
+
+    def __init__(self, new_dimension, normalize=False):
+        self.new_dimension = new_dimension
+        self.normalize = normalize
+
+    def apply(self):
+        for corner_id in range(4):
+            for direction in range(2):
+                self.system.compressCornerTwoSiteOperatorTowards(corner_id, direction, self.new_dimension,
+                                                                 self.normalize)
+
+
+# -- contraction ----------------------------------------------------------------------------------------------------
+class ContractionPolicy(Policy):
+    pass
+
+
+class RepeatPatternContractionPolicy(ContractionPolicy):
+    def __init__(self, directions):
+        self.directions = directions
+        self.position = 0
+
+    def apply(self):
+        directions = list(self.directions)
+        if not directions:
+            raise ValueError("An empty sequence of contraction directions was provided! ({})".format(self.directions))
+        direction = directions[self.position % len(directions)]
+        self.position = self.position % len(directions) + 1
+        log.debug("Contracting towards direction %s", direction)
+        self.system.contractTowards(direction)
+
+    def reset(self):
+        self.position = 0
+
+
+# -- convergence ----------------------------------------------------------------------------------------------------
+class ConvergencePolicy(Policy):
+    def reset(self):
+        pass
+
+    def update(self):
+        pass
+
+
+def _relative_change(current, last):
+    return abs(current - last) / abs(current + last) * 2
+
+
+class PeriodicyThresholdConvergencePolicy(ConvergencePolicy):
+    def __init__(self, threshold, *directions):
+        if not directions:
+            raise ValueError("at least one direction must be specified")
+        self.threshold = threshold
+        self.directions = directions
+
+    def converged(self):
+        state = self.system.state_center_data
+        difference = 0
+        for direction in self.directions:
+            normalized = state.normalizeAxis(direction)[0]
+            denormalizer = state.normalizeAxis(O(direction))[-1]
+            difference += (state - normalized.absorbMatrixAt(direction, denormalizer)).norm()
+        return difference < self.threshold
+
+
+class _LastCurrent(ConvergencePolicy):
+    def reset(self):
+        self.last = None
+        self.current = None
+
+
+class RelativeEstimatedOneSiteExpectationDifferenceThresholdConvergencePolicy(_LastCurrent):
+    def __init__(self, threshold, direction=0):
+        self.threshold = threshold
+        self.direction = direction
+        self.last = self.current = None
+
+    def converged(self):
+        if self.last is None or self.current is None:
+            return None
+        magnitude = abs(self.current + self.last)
+        return magnitude < 1e-15 or _relative_change(self.current, self.last) < self.threshold
+
+    def update(self):
+        self.last = self.current
+        self.current = self.system.computeEstimatedOneSiteExpectation(self.direction)
+
+
+class RelativeExpectationDifferenceDifferenceThresholdConvergencePolicy(ConvergencePolicy):
+    def __init__(self, threshold):
+        self.threshold = threshold
+        self.reset()
+
+    def reset(self):
+        self.last_value = self.last_difference = self.current_value = self.current_difference = None
+
+    def converged(self):
+        last, current = self.last_difference, self.current_difference
+        if last is None or current is None:
+            return None
+        absolute = abs(current - last)
+        return absolute < 1e-15 or absolute / abs(current + last) * 2 < self.threshold
+
+    def update(self):
+        self.last_value, self.last_difference = self.current_value, self.current_difference
+        self.current_value = self.system.computeExpectation()
+        if self.last_value is not None:
+            self.current_difference = self.current_value - self.last_value
+
+
+class RelativeOneSiteExpectationDifferenceThresholdConvergencePolicy(_LastCurrent):
+    def __init__(self, threshold):
+        self.threshold = threshold
+        self.last = self.current = None
+
+    def converged(self):
+        if self.last is None or self.current is None:
+            return None
+        if (self.current - self.last).real > self.threshold:
+            log.info("Current expectation (%s) is greater than last expectation (%s)!", self.current, self.last)
+        absolute = abs(self.current - self.last)
+        return absolute < 1e-15 or _relative_change(self.current, self.last) < self.threshold
+
+    def update(self):
+        self.last = self.current
+        self.current = self.system.computeOneSiteExpectation()
+
+
+class RelativeStateDifferenceThresholdConvergencePolicy(_LastCurrent):
+    """Compares successive center tensors.  The comparison runs on device (two norms) instead of pulling both
+    tensors to the host as the reference does (policies.py:217-232)."""
+
+    def __init__(self, threshold):
+        self.threshold = threshold
+        self.last = self.current = None
+
+    def converged(self):
+        if self.last is None or self.current is None or self.last.shape != self.current.shape:
+            return False
+        magnitude = (self.current + self.last).norm()
+        if magnitude < 1e-15:
+            return True
+        return (self.current - self.last).norm() / magnitude * 2 < self.threshold
+
+    def update(self):
+        self.last = self.current
+        self.current = self.system.state_center_data
+
+
+# -- hooks ----------------------------------------------------------------------------------------------------------
+class HookPolicy(Policy):
+    def __init__(self, callback):
+        self.callback = callback
+
+    def apply(self):
+        return self.callback(self.system)
+
+
+__all__ = [
+    "Policy", "Proxy", "ApplyProxy", "ConvergedProxy", "ResetProxy", "UpdateProxy",
+    "BandwidthIncreasePolicy", "AllDirectionsIncrementBandwidthIncreasePolicy",
+    "AlternatingDirectionsIncrementBandwidthIncreasePolicy", "OneDirectionIncrementBandwidthIncreasePolicy",
+    "CompressionPolicy", "ConstantStateCompressionPolicy", "ConstantOperatorCompressionPolicy",
+    "ContractionPolicy", "RepeatPatternContractionPolicy",
+    "ConvergencePolicy", "PeriodicyThresholdConvergencePolicy",
+    "RelativeEstimatedOneSiteExpectationDifferenceThresholdConvergencePolicy",
+    "RelativeExpectationDifferenceDifferenceThresholdConvergencePolicy",
+    "RelativeOneSiteExpectationDifferenceThresholdConvergencePolicy",
+    "RelativeStateDifferenceThresholdConvergencePolicy",
+    "HookPolicy",
+]

@@ -1,0 +1,465 @@
+"""The 2D system: one center tensor inside a ring of four corners and four sides, all resident in HBM.
+
+Public interface of the reference's ``carcassonne.system._2d.System`` (constructors, ``minimizeExpectation``,
+``contractTowards``, ``compressCornerStateTowards``, ``increaseBandwidth``, ``computeExpectation`` ...) with every
+tensor a ``DeviceData`` and every operation a CUDA kernel behind libcarc_b200.so.  ``corners`` / ``sides`` are
+lists of ``{tag: DeviceData}``; tensors are treated as immutable values, so the shallow ``__copy__`` of the
+reference (system/_2d.py:122-131) is safe here as well.
+"""
+from copy import copy
+from random import randint
+
+import numpy as np
+
+from ..compression import computeProductCompressor
+from ..data import DeviceData, _init_constants
+from ..sparse import (Identity, OneSiteOperator, TwoSiteOperator, TwoSiteOperatorCompressed, makeSimpleSparseOperator,
+                      makeSparseOperator, mapOverSparseData, stripAllButIdentityFrom)
+from ..tensors._2d.dense import formNormalizationMultiplier, formNormalizationSubmatrix
+from ..tensors._2d.sparse import (absorbSparseCenterSOSIntoSide, absorbSparseSideIntoCornerFromLeft,
+                                  absorbSparseSideIntoCornerFromRight, formExpectationAndNormalizationMultipliers)
+from ..utils import InvariantViolatedError, L, Multiplier, O, R, computeCompressor, relaxOver
+from .base import BaseSystem
+
+
+def sideFromCorner(corner_id, direction):
+    """reference system/_2d.py:573-575."""
+    return (corner_id + 1 - direction) % 4
+
+
+def _hermitian_partner(data):
+    """Swap every (state, state*) leg pair and conjugate (system/_2d.py:44,47)."""
+    if data.ndim == 8:
+        return data.join(1, 0, 2, 4, 3, 5, 7, 6).conj()
+    return data.join(1, 0, 2, 4, 3, 5).conj()
+
+
+class System(BaseSystem):
+    # -- constructors (reference system/_2d.py:21-94) ---------------------------------------------------------------
+    def __init__(self, corners, sides, state_center_data, operator_center_tensor, state_center_data_conj=None):
+        BaseSystem.__init__(self)
+        _init_constants()
+        self.corners = list(corners)
+        self.sides = list(sides)
+        self.operator_center_tensor = operator_center_tensor
+        self.state_center_data = state_center_data
+        self.state_center_data_conj = state_center_data.conj() if state_center_data_conj is None \
+            else state_center_data_conj
+        self.just_increased_bandwidth = False
+
+    @classmethod
+    def newRandom(cls, makeOperator=None, DataClass=DeviceData, maximum_dimension=2, O=None):
+        """Random Hermitian environment; draws come from Python's ``random`` and the NumPy stream in the reference's
+        order (system/_2d.py:35-69)."""
+        assert not (makeOperator is not None and O is not None)
+        spoke_sizes = tuple(randint(1, maximum_dimension) for _ in range(2)) * 2
+        bond = [randint(1, maximum_dimension) for _ in range(4)]
+        sides_data = []
+        for i in range(4):
+            side = DataClass.newRandom(*((bond[i],) * 2 + (1,)) * 2 + (spoke_sizes[i],) * 2)
+            side += _hermitian_partner(side)
+            sides_data.append(side)
+        corners_data = []
+        for i in range(4):
+            corner = DataClass.newRandom(*(sides_data[L(i)].shape[3],) * 2 + (1,) + (sides_data[i].shape[0],) * 2 + (1,))
+            corner += _hermitian_partner(corner)
+            corners_data.append(corner)
+        physical_dimension = O.shape[0] if O is not None else max(2, randint(1, maximum_dimension))
+        state_center_data = DataClass.newRandom(*spoke_sizes + (physical_dimension,))
+        if O is None:
+            if makeOperator is None:
+                O = DataClass.newRandom(physical_dimension, physical_dimension)
+                O += O.join(1, 0).conj()
+            else:
+                O = makeOperator(physical_dimension)
+        system = cls(
+            tuple({Identity(): corner} for corner in corners_data),
+            tuple({Identity(): side} for side in sides_data),
+            state_center_data,
+            {Identity(): DataClass.newIdentity(physical_dimension), OneSiteOperator(None): O},
+        )
+        system.assertDimensionsAreConsistent()
+        system.assertNormalizationIsHermitian()
+        system.assertHasNoNaNs()
+        return system
+
+    @classmethod
+    def newTrivial(cls, operator_center_tensor, DataClass=DeviceData):
+        physical_dimension = None
+        for data in operator_center_tensor.values():
+            if data is not None:
+                physical_dimension = data.shape[0]
+                break
+        if physical_dimension is None:
+            raise ValueError("Operator tensor must have at least one non-identity component.")
+        return cls(
+            tuple({Identity(): DataClass.newTrivial((1,) * 6)} for _ in range(4)),
+            tuple({Identity(): DataClass.newTrivial((1,) * 8)} for _ in range(4)),
+            DataClass.newFilled((1, 1, 1, 1, physical_dimension), 1.0 / np.sqrt(physical_dimension)),
+            operator_center_tensor,
+        )
+
+    @classmethod
+    def newTrivialWithSimpleSparseOperator(cls, O=None, OO_UD=None, OO_LR=None):
+        return cls.newTrivial(makeSimpleSparseOperator(O=O, OO_UD=OO_UD, OO_LR=OO_LR))
+
+    @classmethod
+    def newTrivialWithSparseOperator(cls, Os=[], OO_UDs=[], OO_LRs=[]):
+        return cls.newTrivial(makeSparseOperator(Os=Os, OO_UDs=OO_UDs, OO_LRs=OO_LRs))
+
+    def __copy__(self):
+        return type(self)(copy(self.corners), copy(self.sides), self.state_center_data,
+                          copy(self.operator_center_tensor), self.state_center_data_conj)
+
+    # -- consistency checks (reference system/_2d.py:132-190) -----------------------------------------------------------
+    def assertDimensionsAreConsistent(self):
+        center = self.state_center_data.shape
+        assert center == self.state_center_data_conj.shape
+        if center[0] != center[2]:
+            raise AssertionError("state center's left and right dimensions do not agree ({} != {})".format(
+                center[2], center[0]))
+        if center[1] != center[3]:
+            raise AssertionError("state center's up and down dimensions do not agree ({} != {})".format(
+                center[1], center[3]))
+        for kind, tensors, rank in (("side", self.sides, 8), ("corner", self.corners, 6)):
+            for i, sparse in enumerate(tensors):
+                reference = sparse[Identity()]
+                if reference.ndim != rank:
+                    raise AssertionError("for {} {} the normalization data has rank {} instead of rank {}".format(
+                        kind, i, reference.ndim, rank))
+                for tag, data in sparse.items():
+                    if data.shape != reference.shape:
+                        raise AssertionError("for {} {} the data tagged with {} does not match the shape of the data "
+                                             "tagged with Identity() ({} != {})".format(kind, i, tag, data.shape,
+                                                                                        reference.shape))
+                shape = reference.shape
+                for d in range(0, rank, 3):
+                    if shape[d] != shape[d + 1]:
+                        raise AssertionError("{} {}'s dimension {} does not match its dimension {} ({} != {})".format(
+                            kind, i, d, d + 1, shape[d], shape[d + 1]))
+        for i in range(4):
+            side, corner = self.sides[i][Identity()].shape, self.corners[i][Identity()].shape
+            if side[0] != side[3]:
+                raise AssertionError("side {}'s left and right dimensions do not agree ({} != {})".format(
+                    i, side[0], side[3]))
+            if side[6] != center[i]:
+                raise AssertionError("side {}'s center-facing dimensions do not match the corresponding state dimension "
+                                     "({} != {})".format(i, side[6], center[i]))
+            if corner[3] != side[0]:
+                raise AssertionError("corner {}'s right dimensions do not match side {}'s left dimensions "
+                                     "({} != {})".format(i, i, corner[3], side[0]))
+            left_side = self.sides[L(i)][Identity()].shape
+            if corner[0] != left_side[3]:
+                raise AssertionError("corner {}'s left dimensions do not match side {}'s right dimensions "
+                                     "({} != {})".format(i, L(i), corner[0], left_side[3]))
+
+    def assertHasNoNaNs(self):
+        for kind, tensors in (("corner", self.corners), ("side", self.sides)):
+            for i, sparse in enumerate(tensors):
+                for tag, data in sparse.items():
+                    if data.hasNaN():
+                        raise AssertionError("{} {} has a NaN in component {}".format(kind, i, tag))
+        if self.state_center_data.hasNaN():
+            raise AssertionError("state center has a NaN")
+        for tag, data in self.operator_center_tensor.items():
+            if data is not None and data.hasNaN():
+                raise AssertionError("operator center has a NaN in component {}".format(tag))
+
+    def assertNormalizationIsHermitian(self):
+        for i in range(4):
+            for kind, data in (("side", self.sides[i][Identity()]), ("corner", self.corners[i][Identity()])):
+                if not data.allcloseTo(_hermitian_partner(data)):
+                    raise AssertionError("{} {} is not hermitian".format(kind, i))
+
+    # -- expectation values (reference system/_2d.py:364-434, 455-479) ----------------------------------------------
+    def formExpectationAndNormalizationMultipliers(self, operator_center_tensor=None):
+        if operator_center_tensor is None:
+            operator_center_tensor = self.operator_center_tensor
+        return formExpectationAndNormalizationMultipliers(self.corners, self.sides, operator_center_tensor)
+
+    def formExpectationMultiplier(self):
+        return self.formExpectationAndNormalizationMultipliers()[0]
+
+    def formExpectationMatrix(self):
+        return self.formExpectationMultiplier().formMatrix()
+
+    def _identity_ring(self):
+        return (tuple(corner[Identity()] for corner in self.corners), tuple(side[Identity()] for side in self.sides))
+
+    def formNormalizationMultiplier(self):
+        return formNormalizationMultiplier(*self._identity_ring(), self.operator_center_tensor[Identity()])
+
+    def formNormalizationMatrix(self):
+        return self.formNormalizationMultiplier().formMatrix()
+
+    def formNormalizationSubmatrix(self):
+        return formNormalizationSubmatrix(*self._identity_ring())
+
+    def computeScalarUsingMultiplier(self, multiply):
+        """<center| multiply |center> with the stored conjugate (no extra conjugation)."""
+        return self.state_center_data_conj.contractWithAlongAll(multiply(self.state_center_data))
+
+    def computeExpectationAndNormalization(self, operator_center_tensor=None):
+        expectation, normalization = self.formExpectationAndNormalizationMultipliers(operator_center_tensor)
+        unnormalized = self.computeScalarUsingMultiplier(expectation)
+        norm = self.computeScalarUsingMultiplier(normalization)
+        return unnormalized / norm, norm
+
+    def computeExpectation(self, operator_center_tensor=None):
+        return self.computeExpectationAndNormalization(operator_center_tensor)[0]
+
+    def computeUnnormalizedExpectation(self):
+        return self.computeScalarUsingMultiplier(self.formExpectationMultiplier())
+
+    def computeNormalization(self):
+        return self.computeScalarUsingMultiplier(self.formNormalizationMultiplier())
+
+    def computeNormalizationMatrixConditionNumber(self):
+        return np.linalg.cond(self.formNormalizationMatrix().toArray())
+
+    def computeExpectationAndNormalizationWithoutCenter(self):
+        return self.computeExpectationAndNormalization({
+            tag: value for tag, value in self.operator_center_tensor.items()
+            if tag == Identity() or (isinstance(tag, TwoSiteOperator) and tag.position == 0 and tag.direction in (2, 3))
+        })
+
+    def computeExpectationWithoutCenter(self):
+        return self.computeExpectationAndNormalizationWithoutCenter()[0]
+
+    def computeCenterSiteExpectation(self):
+        return self.computeExpectation() - self.computeExpectationWithoutCenter()
+
+    def stripExpectationEnvironment(self):
+        return type(self)(
+            [stripAllButIdentityFrom(corner) for corner in self.corners],
+            [stripAllButIdentityFrom(side) for side in self.sides],
+            self.state_center_data,
+            stripAllButIdentityFrom(self.operator_center_tensor),
+            self.state_center_data_conj,
+        )
+
+    def computeOneSiteExpectation(self):
+        """Energy per site: each one-site term on a bare environment, each two-site term after absorbing one center
+        towards its partner (reference system/_2d.py:396-428)."""
+        expectation = 0
+        bare = self.stripExpectationEnvironment()
+        for tag, value in self.operator_center_tensor.items():
+            if isinstance(tag, OneSiteOperator):
+                system = copy(bare)
+                system.operator_center_tensor[tag] = value
+                expectation += system.computeExpectation()
+            elif isinstance(tag, TwoSiteOperator) and tag.position == 0 and tag.direction in (0, 1):
+                partner = tag.withNewDirectionAndPosition(tag.direction + 2, 0)
+                system = copy(bare)
+                system.operator_center_tensor[tag] = value
+                system.operator_center_tensor[partner] = self.operator_center_tensor[partner]
+                system.contractTowards(tag.direction)
+                expectation += system.computeExpectation()
+        return expectation
+
+    # -- absorption (reference system/_2d.py:435-454) ----------------------------------------------------------------------
+    def contractUnnormalizedTowards(self, direction, state_center_data=None, state_center_data_conj=None):
+        if state_center_data is None:
+            state_center_data = self.state_center_data
+            state_center_data_conj = self.state_center_data_conj
+        if state_center_data_conj is None:
+            state_center_data_conj = state_center_data.conj()
+        self.corners[direction] = absorbSparseSideIntoCornerFromLeft(self.corners[direction], self.sides[L(direction)])
+        self.sides[direction] = absorbSparseCenterSOSIntoSide(
+            direction, self.sides[direction], state_center_data, self.operator_center_tensor, state_center_data_conj)
+        self.corners[R(direction)] = absorbSparseSideIntoCornerFromRight(self.corners[R(direction)],
+                                                                         self.sides[R(direction)])
+        if self.just_increased_bandwidth:
+            raise InvariantViolatedError(
+                "Contracting the current center would blow up the condition number of the normalization matrix;  "
+                "optimize it or replace it first.")
+
+    def contractNormalizedTowards(self, direction, state_center_data):
+        self.contractUnnormalizedTowards(direction, state_center_data.normalizeAxis(O(direction))[0])
+
+    def contractTowards(self, direction):
+        isometry, _, denormalizer = self.state_center_data.normalizeAxis(O(direction))
+        self.contractUnnormalizedTowards(direction, isometry)
+        self.setStateCenter(self.state_center_data.normalizeAxis(direction)[0].absorbMatrixAt(direction, denormalizer))
+
+    def setStateCenter(self, state_center_data, state_center_data_conj=None):
+        self.state_center_data = state_center_data
+        self.state_center_data_conj = state_center_data.conj() if state_center_data_conj is None \
+            else state_center_data_conj
+        self.just_increased_bandwidth = False
+
+    # -- optimisation (reference system/_2d.py:489-502) ----------------------------------------------------------------------
+    def minimizeExpectation(self, statistics=None):
+        self.setStateCenter(relaxOver(self.state_center_data, *self.formExpectationAndNormalizationMultipliers(),
+                                      maximum_number_of_multiplications=100, statistics=statistics))
+
+    def minimizeExpectationUsingFullEigensolver(self):
+        """Dense cross-check (reference system/_2d.py:498-502): host LAPACK on matrices formed on device."""
+        from scipy.linalg import eigh
+        expectation, normalization = self.formExpectationAndNormalizationMultipliers()
+        evals, evecs = eigh(expectation.formMatrix().toArray(), normalization.formMatrix().toArray())
+        self.setStateCenter(DeviceData.fromArray(evecs[:, 0].reshape(self.state_center_data.shape)))
+        return evals[0]
+
+    # -- bandwidth (reference system/_2d.py:480-488) ----------------------------------------------------------------------
+    def increaseBandwidth(self, direction, by=None, to=None, do_as_much_as_possible=False, enlargeners=None):
+        if direction not in (0, 1):
+            raise ValueError("Direction for bandwidth increase must be either 0 (for horizontal axes) or 1 (for "
+                             "vertical axes), not {}.".format(direction))
+        return self._increaseBandwidth(direction, by, to, do_as_much_as_possible, enlargeners)
+
+    def increaseBandwidthAndThenNormalize(self, direction, by=None, to=None):
+        self.increaseBandwidth(direction, by, to)
+        self.normalize()
+
+    # -- state-bond compression (reference system/_2d.py:191-228) ----------------------------------------------------------
+    def compressCornerStateTowards(self, corner_id, direction, new_dimension, initial=None):
+        if direction == 0:
+            return self.compressCornerStateTowardsLeft(corner_id, new_dimension, initial)
+        if direction == 1:
+            return self.compressCornerStateTowardsRight(corner_id, new_dimension, initial)
+        raise ValueError("compression direction must be 0 or 1, not " + str(direction))
+
+    @staticmethod
+    def _project(sparse, first_axis, compressor, conjugate_first):
+        a, b = (compressor.conj(), compressor) if conjugate_first else (compressor, compressor.conj())
+        return mapOverSparseData(lambda data: data.absorbMatrixAt(first_axis, a).absorbMatrixAt(first_axis + 1, b),
+                                 sparse)
+
+    def compressCornerStateTowardsLeft(self, corner_id, new_dimension, initial=None):
+        side_id = L(corner_id)
+        side_joined = self.sides[side_id][Identity()].join((0, 1, 2, 6, 7), 3, 4, 5)
+        corner_joined = self.corners[corner_id][Identity()].join(0, 1, 2, (3, 4, 5))
+        compressor = computeProductCompressor(side_joined, corner_joined, new_dimension, initial)
+        self.sides[side_id] = self._project(self.sides[side_id], 3, compressor, False)
+        self.corners[corner_id] = self._project(self.corners[corner_id], 0, compressor, True)
+        return compressor
+
+    def compressCornerStateTowardsRight(self, corner_id, new_dimension, initial=None):
+        corner_joined = self.corners[corner_id][Identity()].join((0, 1, 2), 3, 4, 5)
+        side_joined = self.sides[corner_id][Identity()].join(0, 1, 2, (3, 4, 5, 6, 7))
+        compressor = computeProductCompressor(corner_joined, side_joined, new_dimension, initial)
+        self.corners[corner_id] = self._project(self.corners[corner_id], 3, compressor, False)
+        self.sides[corner_id] = self._project(self.sides[corner_id], 0, compressor, True)
+        return compressor
+
+    # -- operator-bond compression (reference system/_2d.py:229-363) -------------------------------------------------------
+    def compressCornerTwoSiteOperatorTowards(self, corner_id, direction, new_dimension, normalize=False):
+        """Fold every ``TwoSiteOperator`` half of one direction on a corner (and the matching halves on the adjacent
+        side) into one ``TwoSiteOperatorCompressed`` tensor with an operator bond of ``new_dimension``, keeping the
+        dominant eigenvectors of the Gram matrix of the flattened halves."""
+        axis = 3 * direction + 2
+        corner = self.corners[corner_id]
+        kept, halves, slots, old_compressed = {}, [], {}, None
+        for tag, data in corner.items():
+            if isinstance(tag, TwoSiteOperator) and tag.direction == direction:
+                assert tag.position not in slots
+                slots[tag.position] = len(halves)
+                halves.append(data)
+            elif isinstance(tag, TwoSiteOperatorCompressed) and tag.direction == direction:
+                assert old_compressed is None
+                old_compressed = data
+            else:
+                kept[tag] = data
+        n_sparse = len(halves)
+        old_dimension = n_sparse + (old_compressed.shape[axis] if old_compressed is not None else 0)
+        if old_dimension == 0:
+            return
+        # Gram matrices of the flattened halves: <half_a | half_b> on device, a handful of numbers back to the host
+        if n_sparse:
+            stacked = DeviceData.newCollected([h.ravel() for h in halves])               # [n_sparse, size]
+            gram_sparse = stacked.conj().contractWith(stacked, (1,), (1,)).toArray()
+        else:
+            stacked, gram_sparse = None, np.zeros((0, 0), dtype=np.complex128)
+        if old_compressed is not None:
+            folded = old_compressed.fold(axis)
+            gram_compressed = folded.conj().contractWith(folded, (1,), (1,)).toArray()
+        else:
+            gram_compressed = np.zeros((0, 0), dtype=np.complex128)
+        gram = np.zeros((old_dimension,) * 2, dtype=np.complex128)
+        gram[:n_sparse, :n_sparse] = gram_sparse
+        gram[n_sparse:, n_sparse:] = gram_compressed
+        corner_multiplier, side_multiplier_conj = computeCompressor(
+            old_dimension, new_dimension,
+            Multiplier((old_dimension,) * 2, lambda v: gram @ v, gram_sparse.size + gram_compressed.size,
+                       lambda: gram, 0),
+            np.complex128, normalize)
+        side_multiplier = side_multiplier_conj.conj()
+
+        def fold_in(reference_shape, axis, collected, compressed, multiplier):
+            """sum of (stacked halves) x multiplier[:, :n_sparse] and (old compressed bond) x multiplier[:, n_sparse:]"""
+            result = None
+            if collected is not None:
+                shape = list(reference_shape)
+                del shape[axis]
+                order = list(range(1, len(reference_shape)))
+                order.insert(axis, 0)
+                mixed = collected.split(n_sparse, *shape).absorbMatrixAt(
+                    0, DeviceData.fromArray(multiplier[:, :n_sparse]))
+                result = mixed.transpose(order)
+            if compressed is not None:
+                term = compressed.absorbMatrixAt(axis, DeviceData.fromArray(multiplier[:, n_sparse:]))
+                if result is None:
+                    result = term
+                else:
+                    result = result.copy()
+                    result += term
+            return result
+
+        kept[TwoSiteOperatorCompressed(direction)] = fold_in(corner[Identity()].shape, axis, stacked, old_compressed,
+                                                             corner_multiplier)
+        self.corners[corner_id] = kept
+
+        side_id = sideFromCorner(corner_id, direction)
+        side_direction = 1 - direction
+        side_axis = 3 * side_direction + 2
+        side = self.sides[side_id]
+        kept_side, side_halves, side_compressed = {}, [None] * n_sparse, None
+        for tag, data in side.items():
+            if isinstance(tag, TwoSiteOperator) and tag.direction == side_direction:
+                side_halves[slots[tag.position]] = data
+            elif isinstance(tag, TwoSiteOperatorCompressed) and tag.direction == side_direction:
+                assert old_compressed is not None and side_compressed is None
+                side_compressed = data
+            else:
+                kept_side[tag] = data
+        assert None not in side_halves
+        assert (side_compressed is not None) == (old_compressed is not None)
+        side_stacked = DeviceData.newCollected([h.ravel() for h in side_halves]) if n_sparse else None
+        kept_side[TwoSiteOperatorCompressed(side_direction)] = fold_in(side[Identity()].shape, side_axis, side_stacked,
+                                                                       side_compressed, side_multiplier)
+        self.sides[side_id] = kept_side
+
+    # -- gauge normalisation of the environment (reference system/_2d.py:503-549) ----------------------------------------
+    def normalize(self):
+        for corner_id in range(4):
+            for direction in range(2):
+                self.normalizeCornerAndDenormalizeSide(corner_id, direction)
+        for side_id in range(4):
+            self.normalizeSideAndDenormalizeCenter(side_id)
+
+    @staticmethod
+    def _absorb_pair(sparse, axis, matrix):
+        conj = matrix.conj()
+        return {tag: data.absorbMatrixAt(axis, matrix).absorbMatrixAt(axis + 1, conj) for tag, data in sparse.items()}
+
+    def normalizeCenterAndDenormalizeSide(self, direction):
+        normalizer, denormalizer = self.state_center_data.normalizeAxis(direction, True)
+        self.state_center_data = self.state_center_data.absorbMatrixAt(direction, normalizer)
+        self.state_center_data_conj = self.state_center_data.conj()
+        self.sides[direction] = self._absorb_pair(self.sides[direction], 6, denormalizer)
+
+    def normalizeCornerAndDenormalizeSide(self, corner_id, direction):
+        side_id = sideFromCorner(corner_id, direction)
+        normalizer, denormalizer = self.corners[corner_id][Identity()].normalizeAxis(direction * 3, True)
+        self.corners[corner_id] = self._absorb_pair(self.corners[corner_id], direction * 3, normalizer)
+        self.sides[side_id] = self._absorb_pair(self.sides[side_id], (1 - direction) * 3, denormalizer)
+
+    def normalizeSideAndDenormalizeCenter(self, side_id):
+        normalizer, denormalizer = self.sides[side_id][Identity()].normalizeAxis(6, True)
+        self.sides[side_id] = self._absorb_pair(self.sides[side_id], 6, normalizer)
+        self.state_center_data = self.state_center_data.absorbMatrixAt(side_id, denormalizer)
+        self.state_center_data_conj = self.state_center_data.conj()
+
+
+__all__ = ["System", "sideFromCorner"]

@@ -1,0 +1,137 @@
+"""Sparse (tagged) versions of the 2D contraction recipes and the expectation / normalization multipliers.
+
+Mirror of the reference's ``carcassonne/tensors/_2d/sparse.py``.  The host plans which tag pairs multiply
+(``carcassonne_b200.sparse``); the device executes one GEMM per pair with the ``+=`` of the result tag folded into
+the epilogue.  Stage 2 writes its output directly in the layout the fused stage-3 matvec streams, and stage 3
+collects all sparse terms into ONE device operator (one kernel launch per matvec over a device-side term table)
+instead of the reference's Python loop over per-term multipliers (sparse.py:129-133).
+"""
+import itertools
+from math import prod
+
+import numpy as np
+
+from ...sparse import (Identity, contractSparseTensors, getInformationFromOperatorCenter,
+                       rule_center_into_side, rule_side_into_corner_from_left, rule_side_into_corner_from_right,
+                       rule_stage1, rule_stage2, stage3_term_allowed)
+from ...utils import Multiplier
+from . import dense as _dense
+from .dense import *  # noqa: F401,F403  (the reference re-exports the dense recipes from here too)
+
+
+class Stage2Half(dict):
+    """{tag: tensor} of one half-ring in the stage-3 streaming layout [(x y), D*, D*, D, D] (``half`` = 0 or 1);
+    ``bonds`` keeps the two environment bond extents of the reference layout."""
+
+    def __init__(self, half, bonds=None):
+        dict.__init__(self)
+        self.half = half
+        self.bonds = bonds
+
+
+def absorbSparseSideIntoCornerFromLeft(corner, side):
+    """reference tensors/_2d/sparse.py:12-23."""
+    return contractSparseTensors(rule_side_into_corner_from_left,
+                                 lambda c, s, acc, _: _dense.absorbDenseSideIntoCornerFromLeft(c, s, acc), corner, side)
+
+
+def absorbSparseSideIntoCornerFromRight(corner, side):
+    """reference tensors/_2d/sparse.py:24-35."""
+    return contractSparseTensors(rule_side_into_corner_from_right,
+                                 lambda c, s, acc, _: _dense.absorbDenseSideIntoCornerFromRight(c, s, acc), corner, side)
+
+
+def absorbSparseCenterSOSIntoSide(direction, side, state_center_data, operator_center_data,
+                                  state_center_data_conj=None):
+    """reference tensors/_2d/sparse.py:36-58.  The double-layer center tensor of each site operator is built once
+    and shared by all side tags that pair with it."""
+    if state_center_data_conj is None:
+        state_center_data_conj = state_center_data.conj()
+    cache = {}
+
+    def absorb(side_data, operator_data, acc, needs_operator):
+        return _dense.absorbDenseCenterSOSIntoSide(direction, side_data, state_center_data,
+                                                   operator_data if needs_operator else None,
+                                                   state_center_data_conj, acc, cache)
+
+    return contractSparseTensors(lambda s, c: rule_center_into_side(direction, s, c), absorb, side,
+                                 operator_center_data)
+
+
+def formExpectationStage1(corner, side):
+    """reference tensors/_2d/sparse.py:72-85."""
+    return contractSparseTensors(rule_stage1, lambda c, s, acc, _: _dense.formNormalizationStage1(c, s, acc),
+                                 corner, side)
+
+
+def formExpectationStage2(right, left, half=None):
+    """reference tensors/_2d/sparse.py:86-99.  ``half`` = 0 / 1 produces a ``Stage2Half`` in the stage-3 layout."""
+    result = contractSparseTensors(
+        rule_stage2, lambda r, l, acc, _: _dense.formNormalizationStage2(r, l, acc, half=half), right, left)
+    if half is None:
+        return result
+    out = Stage2Half(half, (left[Identity()].shape[0], right[Identity()].shape[1]))
+    out.update(result)
+    return out
+
+
+def _as_half(stage2, half):
+    if isinstance(stage2, Stage2Half):
+        if stage2.half != half:
+            raise ValueError("stage-2 tensor was built for half {} but is used as half {}".format(stage2.half, half))
+        return stage2
+    out = Stage2Half(half, tuple(stage2[Identity()].shape[:2]))
+    for tag, data in stage2.items():
+        out[tag] = _dense.prejoinStage2(data, half)
+    return out
+
+
+def stage3Terms(stage2_0, stage2_1, operator_center):
+    """Term list [(tag_0, tag_1, tag_center)] in the reference's itertools.product order (sparse.py:119-127)."""
+    return [tags for tags in itertools.product(stage2_0, stage2_1, operator_center) if stage3_term_allowed(*tags)]
+
+
+def formExpectationStage3(stage2_0, stage2_1, operator_center):
+    """reference tensors/_2d/sparse.py:100-161 -> (expectation Multiplier, normalization Multiplier)."""
+    from ...operator import Stage3Operator
+    half_0, half_1 = _as_half(stage2_0, 0), _as_half(stage2_1, 1)
+    physical_dimension, _, DataClass = getInformationFromOperatorCenter(operator_center)
+    A_id, B_id = half_0[Identity()], half_1[Identity()]
+    state_shape = (A_id.shape[3], A_id.shape[4], B_id.shape[3], B_id.shape[4], physical_dimension)
+    dimension = prod(state_shape)
+    terms = stage3Terms(half_0, half_1, operator_center)
+
+    expectation_operator = Stage3Operator(state_shape)
+    cost_of_multiply = cost_of_formMatrix = 0
+    for x, y, z in terms:
+        site = None if z == Identity() else operator_center[z]
+        expectation_operator.add_term(half_0[x], half_1[y], site)
+        cost_of_multiply += _dense.stage3CostOfMultiply(half_0[x], half_1[y], physical_dimension, site is not None)
+        cost_of_formMatrix += _dense.stage3CostOfFormMatrix(half_0[x], half_1[y], physical_dimension)
+    expectation_operator.finalize()
+
+    identity = np.eye(physical_dimension, dtype=np.complex128)
+
+    def formExpectationMatrix():
+        matrix = DataClass.newZeros((dimension, dimension))
+        for x, y, z in terms:
+            _dense.stage3FormMatrix(half_0[x], half_1[y], identity if z == Identity() else operator_center[z], matrix)
+        return matrix
+
+    expectation_multiplier = Multiplier((dimension, dimension), expectation_operator, cost_of_multiply,
+                                        formExpectationMatrix, cost_of_formMatrix)
+    expectation_multiplier.device_operator = expectation_operator
+    expectation_multiplier.terms = terms
+    normalization_multiplier = _dense._stage3_multiplier(A_id, B_id, None, physical_dimension)
+    return expectation_multiplier, normalization_multiplier
+
+
+def formExpectationAndNormalizationMultipliers(corners, sides, operator_center_data):
+    """reference tensors/_2d/sparse.py:59-71."""
+    return formExpectationStage3(
+        formExpectationStage2(formExpectationStage1(corners[0], sides[0]),
+                              formExpectationStage1(corners[1], sides[1]), half=0),
+        formExpectationStage2(formExpectationStage1(corners[2], sides[2]),
+                              formExpectationStage1(corners[3], sides[3]), half=1),
+        operator_center_data,
+    )

@@ -86,6 +86,16 @@ int carc_zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, const double a
                const void* B, int64_t ldb, const double beta[2], void* C, const int64_t* out_map, const int64_t* k_map,
                int64_t batch, int64_t strideA, int64_t strideB, int64_t strideC, void* stream);
 
+/* Same product with arbitrary output scatter: element (m, n) goes to C[rowoff[m] + coloff[n]] (device int64 tables,
+ * either may be NULL = plain row-major factor).  This is how the dense recipes (tensors/_2d/dense.py:11-112) write
+ * their GEMM result straight into the layout their final `join` asks for -- up to 12 interleaved axes -- without the
+ * transposing copy.  carc_index_table fills a table: table[i] = sum_l digit_l(i) * strides[l], digits row-major. */
+int carc_index_table(int nlevels, const int64_t* extents, const int64_t* strides, void* table_dev, void* stream);
+int carc_zgemm_tab(int opA, int opB, int64_t M, int64_t N, int64_t K, const double alpha[2], const void* A, int64_t lda,
+                   const void* B, int64_t ldb, const double beta[2], void* C, const void* rowoff_dev,
+                   const void* coloff_dev, int64_t batch, int64_t strideA, int64_t strideB, int64_t strideC,
+                   void* stream);
+
 /* ---- the center-site operator: formExpectationStage3 / formNormalizationStage3 / formDenseStage3
  * (tensors/_2d/sparse.py:100-161, tensors/_2d/dense.py:115-203).
  * An operator is a list of terms (A_t, B_t, O_t): A_t = stage-2 half 0 pre-joined to [X_t, P, Q]
@@ -107,6 +117,38 @@ int carc_operator_destroy(carc_operator* op);
 int carc_stage3_matvec_host(int nterms, const void* const* A_host, const void* const* B_host, const int64_t* X,
                             const double* const* O_host, int P, int Q, int R, int S, int d, const void* v_host,
                             void* out_host, void* stream);
+
+/* A dense operator (the `isCheaperToFormMatrix` branches of relaxOver, utils.py:814-832): matrix [n, n] row-major,
+ * not copied. */
+int carc_operator_create_dense(carc_operator** op, const void* matrix_dev, int64_t n);
+int64_t carc_operator_dimension(const carc_operator* op);
+
+/* ---- the center-site eigen-solver: relaxOver (utils.py:805-878) -------------------------------------------------
+ * Restarted Arnoldi of dimension krylov_dim (0 = the reference's default 3) on N^-1 H with classical Gram-Schmidt,
+ * a k x k non-Hermitian eigen-solve and a restart on the Ritz vector of lowest real part, entirely on device; `v`
+ * (n = carc_operator_dimension(H) complex numbers) is normalised in place, as the reference does with the caller's
+ * array (utils.py:808-809), and holds the result on return.  N^-1 is applied by
+ *   - N_lu / N_piv != NULL : the LU factors of the dense normalization matrix from carc_lu_factor
+ *                            (scipy.linalg.lu_factor / lu_solve, utils.py:816-818);
+ *   - else N_op != NULL    : GMRES(gmres_restart) on the operator to relative residual gmres_rtol
+ *                            (scipy.sparse.linalg.gmres defaults 20 / 1e-5, utils.py:819-825); failure to converge
+ *                            returns CARC_ERR_NO_CONVERGENCE (the reference's `assert info == 0`);
+ *   - else                  : identity (standard eigenproblem).
+ * Stops when |ritz - last ritz| <= tolerance, after max_mults multiplications (0 = no limit; counted in blocks of
+ * krylov_dim like utils.py:860) or when the Krylov space is exhausted (norm <= 1e-14).  Returns
+ * CARC_ERR_RELAX_FAILED under the reference's RelaxFailed condition (utils.py:871).
+ * info_out (9 doubles, host): initial <v,Mv> (re, im), final (re, im), last Ritz value (re, im), multiplications
+ * counted, operator applications performed, GMRES inner iterations. */
+int carc_relax(carc_operator* H, carc_operator* N_op, const void* N_lu, const void* N_piv, void* v, int max_mults,
+               double tolerance, int krylov_dim, double gmres_rtol, int gmres_restart, int gmres_maxiter,
+               double* info_out, void* stream);
+/* x = A^-1 b by restarted GMRES from x0 = 0 (scipy.sparse.linalg.gmres call sites utils.py:823, compression.py:39). */
+int carc_gmres(carc_operator* A, const void* b, void* x, double rtol, int restart, int maxiter, int* iterations_out,
+               double* residual_out, void* stream);
+/* In-place LU with partial pivoting of a row-major n x n matrix (LAPACK zgetrf pivoting rule); piv_dev: int32[n] on
+ * device.  Synchronises to report *singular_out (1 if a zero pivot was met).  carc_lu_solve overwrites x with A^-1 x. */
+int carc_lu_factor(void* A, int n, void* piv_dev, int* singular_out, void* stream);
+int carc_lu_solve(const void* LU, int n, const void* piv_dev, void* x, void* stream);
 
 /* ---- small factorisations: scipy.linalg.qr / svd call sites of NDArrayData.qr, svd, unitize, normalizeAxis
  * (data/__init__.py:43-50, 263-301, 344-346; utils.py:879-881).

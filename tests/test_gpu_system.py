@@ -1,0 +1,584 @@
+"""GPU parity tests of the device host layer -- dense recipes, sparse absorption, multipliers, relaxOver,
+compression, bandwidth increase and full runs -- against the reference's golden vectors and the CPU oracle.
+The structure follows the reference's own tests (tests/test_tensors_dense.py, test_system.py, test_utils.py,
+test_compression.py, test_simulator_2d_in_1d.py, test_simulator_2d_in_15d.py)."""
+import random
+
+import numpy as np
+import pytest
+
+from golden_io import load, relerr, sparse, system_parts
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def dd():
+    from carcassonne_b200.data import DeviceData, _init_constants
+    _init_constants()
+    return DeviceData
+
+
+def to_tag(t):
+    """oracle tuple tag -> product tag object"""
+    from carcassonne_b200 import sparse as sp
+    if t[0] == "I":
+        return sp.Identity()
+    if t[0] == "C":
+        return sp.Complete()
+    if t[0] == "1":
+        return sp.OneSiteOperator(None)
+    if t[0] == "2":
+        return sp.TwoSiteOperator(t[1], t[2], t[3])
+    if t[0] == "Z":
+        return sp.TwoSiteOperatorCompressed(t[1])
+    raise ValueError(t)
+
+
+def to_device_sparse(dd, d):
+    return {to_tag(t): dd.fromArray(x) for t, x in d.items()}
+
+
+def device_system(dd, corners, sides, center, operator):
+    from carcassonne_b200.system import System
+    return System([to_device_sparse(dd, c) for c in corners], [to_device_sparse(dd, s) for s in sides],
+                  dd.fromArray(center), to_device_sparse(dd, operator))
+
+
+def crand(rng, *shape):
+    return rng.uniform(-1, 1, shape) + 1j * rng.uniform(-1, 1, shape)
+
+
+# -- dense recipes (reference tests/test_tensors_dense.py) ------------------------------------------------------------
+def test_absorb_side_into_corner_golden(dd):
+    from carcassonne_b200.tensors._2d import dense
+    g = load("dense_recipes")
+    out = dense.absorbDenseSideIntoCornerFromLeft(dd.fromArray(g["afl_corner"]), dd.fromArray(g["afl_side"]))
+    assert relerr(out.toArray(), g["afl_out"]) < TOL
+    out = dense.absorbDenseSideIntoCornerFromRight(dd.fromArray(g["afr_corner"]), dd.fromArray(g["afr_side"]))
+    assert relerr(out.toArray(), g["afr_out"]) < TOL
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_absorb_center_into_side_golden(dd, i):
+    from carcassonne_b200.tensors._2d import dense
+    g = load("dense_recipes")
+    side, center, op = (dd.fromArray(g[k % i]) for k in ("ss%d_side", "ss%d_center", "ss%d_op"))
+    out = dense.absorbDenseCenterSSIntoSide(i, side, center, center.conj())
+    assert relerr(out.toArray(), g["ss%d_out" % i]) < TOL
+    out = dense.absorbDenseCenterSOSIntoSide(i, side, center, op, center.conj())
+    assert relerr(out.toArray(), g["sos%d_out" % i]) < TOL
+
+
+def test_stages_golden(dd):
+    from carcassonne_b200.tensors._2d import dense
+    g = load("dense_recipes")
+    out = dense.formNormalizationStage1(dd.fromArray(g["st1_corner"]), dd.fromArray(g["st1_side"]))
+    assert relerr(out.toArray(), g["st1_out"]) < TOL
+    a, b = dd.fromArray(g["st2_a"]), dd.fromArray(g["st2_b"])
+    plain = dense.formNormalizationStage2(a, b)
+    assert relerr(plain.toArray(), g["st2_out"]) < TOL
+    for half in (0, 1):
+        direct = dense.formNormalizationStage2(a, b, half=half)
+        assert np.array_equal(direct.toArray(), dense.prejoinStage2(plain, half).toArray())
+        x, y = plain.shape[:2]
+        assert np.array_equal(dense.unjoinStage2(direct, half, x, y).toArray(), plain.toArray())
+    s0, s1, op, v = (dd.fromArray(g[k]) for k in ("st3_s2_0", "st3_s2_1", "st3_op", "st3_v"))
+    mn = dense.formNormalizationStage3(s0, s1, dd.newIdentity(2))
+    md = dense.formDenseStage3(s0, s1, op)
+    assert relerr(mn(v).toArray(), g["st3_norm_out"]) < TOL
+    assert relerr(md(v).toArray(), g["st3_dense_out"]) < TOL
+    assert [mn.cost_of_multiply, mn.cost_of_formMatrix] == list(g["st3_norm_cost"])
+    assert [md.cost_of_multiply, md.cost_of_formMatrix] == list(g["st3_dense_cost"])
+    assert relerr(mn.formMatrix().toArray(), g["st3_norm_matrix"]) < TOL
+    assert relerr(md.formMatrix().toArray(), g["st3_dense_matrix"]) < TOL
+
+
+@pytest.mark.parametrize("chi,D,p", [(1, 1, 1), (2, 3, 1), (3, 2, 2), (5, 4, 1), (3, 4, 2)])
+def test_dense_recipes_vs_oracle(dd, chi, D, p):
+    """Seeded random shapes incl. operator bonds > 1 (compressed operators) against the oracle."""
+    from carcassonne_b200.tensors._2d import dense
+    from oracle import dense as od
+    rng = np.random.default_rng(chi * 100 + D * 10 + p)
+    corner = crand(rng, chi, chi + 1, p, chi + 1, chi, p)
+    side_l = crand(rng, chi + 2, chi, p + 1, chi, chi + 1, p, D, D + 1)
+    assert relerr(dense.absorbDenseSideIntoCornerFromLeft(dd.fromArray(corner), dd.fromArray(side_l)).toArray(),
+                  od.absorb_side_into_corner_from_left(corner, side_l)) < TOL
+    side_r = crand(rng, chi + 1, chi, p, chi + 2, chi, p + 1, D + 1, D)
+    assert relerr(dense.absorbDenseSideIntoCornerFromRight(dd.fromArray(corner), dd.fromArray(side_r)).toArray(),
+                  od.absorb_side_into_corner_from_right(corner, side_r)) < TOL
+    assert relerr(dense.formNormalizationStage1(dd.fromArray(corner), dd.fromArray(side_r)).toArray(),
+                  od.stage1(corner, side_r)) < TOL
+    s1a, s1b = crand(rng, chi + 1, chi + 2, D, D + 1), crand(rng, chi, chi + 1, D + 1, D)
+    assert relerr(dense.formNormalizationStage2(dd.fromArray(s1a), dd.fromArray(s1b)).toArray(),
+                  od.stage2(s1a, s1b)) < TOL
+    dims = [D, D + 1, D, D + 1]
+    center = crand(rng, *dims, 2)
+    op = crand(rng, 2, 2)
+    for i in range(4):
+        side = crand(rng, chi, chi + 1, p, chi + 1, chi, p + 1, dims[i], dims[i])
+        S, Cn = dd.fromArray(side), dd.fromArray(center)
+        assert relerr(dense.absorbDenseCenterSSIntoSide(i, S, Cn, Cn.conj()).toArray(),
+                      od.absorb_center_ss_into_side(i, side, center)) < TOL
+        assert relerr(dense.absorbDenseCenterSOSIntoSide(i, S, Cn, dd.fromArray(op), Cn.conj()).toArray(),
+                      od.absorb_center_sos_into_side(i, side, center, op)) < TOL
+        # accumulation into an existing result (the sparse layer's +=)
+        acc = dense.absorbDenseCenterSSIntoSide(i, S, Cn, Cn.conj())
+        dense.absorbDenseCenterSOSIntoSide(i, S, Cn, dd.fromArray(op), Cn.conj(), accumulate_into=acc)
+        assert relerr(acc.toArray(), od.absorb_center_ss_into_side(i, side, center) +
+                      od.absorb_center_sos_into_side(i, side, center, op)) < TOL
+
+
+def test_recipe_errors(dd):
+    """The generated contractors of the reference raise before computing (utils.py:613-625)."""
+    from carcassonne_b200.tensors._2d import dense
+    from carcassonne_b200.utils import DimensionMismatchError, UnexpectedTensorRankError
+    rng = np.random.default_rng(0)
+    corner = dd.fromArray(crand(rng, 2, 2, 1, 2, 2, 1))
+    with pytest.raises(UnexpectedTensorRankError):
+        dense.formNormalizationStage1(corner, corner)
+    side = dd.fromArray(crand(rng, 3, 2, 1, 2, 2, 1, 2, 2))
+    with pytest.raises(DimensionMismatchError):
+        dense.formNormalizationStage1(corner, side)
+
+
+# -- sparse walks (reference tests/test_two_site_operator.py, test_system.py) ----------------------------------------
+WALKS = ["walk_tfim_chi2_D2", "walk_heis_chi1_D2", "walk_tfim_chi2_D3"]
+
+
+@pytest.mark.parametrize("name", WALKS)
+def test_system_walk(dd, name):
+    g = load(name)
+    corners, sides, center = system_parts(g, "init")
+    s = device_system(dd, corners, sides, center, sparse(g, "operator"))
+    s.assertDimensionsAreConsistent()
+    s.assertNormalizationIsHermitian()
+    s.assertHasNoNaNs()
+    for direction in g["moves"]:
+        s.contractUnnormalizedTowards(int(direction))
+    wc, ws, _ = system_parts(g, "walked")
+    for i in range(4):
+        assert list(s.corners[i]) == [to_tag(t) for t in wc[i]]
+        assert list(s.sides[i]) == [to_tag(t) for t in ws[i]]
+        for t in wc[i]:
+            assert relerr(s.corners[i][to_tag(t)].toArray(), wc[i][t]) < TOL, ("corner", i, t)
+        for t in ws[i]:
+            assert relerr(s.sides[i][to_tag(t)].toArray(), ws[i][t]) < TOL, ("side", i, t)
+    H, N = s.formExpectationAndNormalizationMultipliers()
+    v = dd.fromArray(g["v"])
+    assert relerr(H(v).toArray(), g["Hv"]) < TOL
+    assert relerr(N(v).toArray(), g["Nv"]) < TOL
+    assert [H.cost_of_multiply, H.cost_of_formMatrix, N.cost_of_multiply, N.cost_of_formMatrix] == list(g["costs"])
+    if "Hmat" in g:
+        assert relerr(H.formMatrix().toArray(), g["Hmat"]) < TOL
+        assert relerr(N.formMatrix().toArray(), g["Nmat"]) < TOL
+        # multiplier == explicit matrix == submatrix (reference tests/test_system.py:222-275)
+        assert relerr((H.formMatrix().toArray() @ g["v"].ravel()).reshape(g["v"].shape), g["Hv"]) < TOL
+        sub = s.formNormalizationSubmatrix().toArray()
+        n4 = sub.shape[0]
+        assert relerr(np.kron(sub, np.eye(2)), g["Nmat"]) < TOL and n4 * 2 == g["Nmat"].shape[0]
+    e, n = s.computeExpectationAndNormalization()
+    assert abs(e - g["expectation"]) <= 1e-12 * abs(g["expectation"])
+    assert abs(n - g["normalization"]) <= 1e-12 * abs(g["normalization"])
+    assert abs(s.computeNormalization() - g["normalization"]) <= 1e-12 * abs(g["normalization"])
+    s.contractTowards(int(g["moves"][0]))
+    assert relerr(s.state_center_data.toArray(), g["after_ct.center"]) < 1e-10
+    e, n = s.computeExpectationAndNormalization()
+    assert abs(e - g["after_ct.expectation"]) <= 1e-10 * abs(g["after_ct.expectation"])
+    assert abs(n - g["after_ct.normalization"]) <= 1e-10 * abs(g["after_ct.normalization"])
+
+
+def test_stage3_terms_tfim(dd):
+    g = load("walk_tfim_chi2_D2")
+    corners, sides, center = system_parts(g, "walked")
+    s = device_system(dd, corners, sides, center, sparse(g, "operator"))
+    H, _ = s.formExpectationAndNormalizationMultipliers()
+    assert len(H.terms) == 9
+    assert H.device_operator.num_terms == 9
+
+
+def test_copy_is_shallow_and_safe(dd):
+    from copy import copy
+    g = load("walk_tfim_chi2_D2")
+    corners, sides, center = system_parts(g, "walked")
+    s = device_system(dd, corners, sides, center, sparse(g, "operator"))
+    before = s.computeExpectation()
+    estimate = s.computeEstimatedOneSiteExpectation(0)      # works on a copy
+    assert np.isfinite(estimate)
+    assert s.computeExpectation() == before
+    c = copy(s)
+    c.contractTowards(1)
+    assert s.computeExpectation() == before
+
+
+# -- relaxOver (reference tests/test_utils.py:857-878 + our own eigenvalue pins) --------------------------------------
+def _dense_multiplier(dd, m, operator_branch):
+    from carcassonne_b200.utils import Multiplier, _DenseOperator
+    M = dd.fromArray(m)
+    mult = Multiplier.fromMatrix(M)
+    if operator_branch:      # make forming the matrix look expensive -> operator branches of relaxOver
+        mult.cost_of_formMatrix = 10 ** 12
+        mult.device_operator = _DenseOperator(M)
+    else:
+        mult.cost_of_multiply = 10 ** 12
+    return mult
+
+
+def test_relax_over_golden(dd):
+    from carcassonne_b200.utils import relaxOver
+    g = load("relax")
+    h, nm, v0 = g["H"], g["N"], g["v0"]
+    w = np.linalg.eigvals(np.linalg.solve(nm, h))
+    exact = np.min(w.real)
+    # LU + dense-matrix branches are deterministic: same iterates as the reference
+    stats = {}
+    res = relaxOver(dd.fromArray(v0), _dense_multiplier(dd, h, False), _dense_multiplier(dd, nm, False), 100,
+                    statistics=stats).toArray()
+    ray = np.vdot(res, h @ res) / np.vdot(res, nm @ res)
+    assert stats["normalization"] == "lu"
+    assert abs(ray - g["lu_rayleigh"]) < 1e-10
+    assert min(relerr(res, g["lu_result"]), relerr(-res, g["lu_result"])) < 1e-6 or \
+        abs(abs(np.vdot(res, g["lu_result"])) - 1) < 1e-8
+    assert ray.real >= exact - 1e-9
+    # GMRES branch for N^-1, operator branch for H (GMRES rtol 1e-5 inside: loosely comparable)
+    stats = {}
+    res = relaxOver(dd.fromArray(v0), _dense_multiplier(dd, h, True), _dense_multiplier(dd, nm, True), 100,
+                    statistics=stats).toArray()
+    ray = np.vdot(res, h @ res) / np.vdot(res, nm @ res)
+    assert stats["normalization"] == "gmres" and stats["gmres_iterations"] > 0
+    assert abs(ray - g["gmres_rayleigh"]) < 1e-5
+    # no normalization multiplier, exactly one restart
+    res = relaxOver(dd.fromArray(v0), _dense_multiplier(dd, h, False), None, 3).toArray()
+    assert abs(abs(np.vdot(res, g["one_restart_result"])) - 1) < 1e-10
+
+
+@pytest.mark.parametrize("n", [3, 4, 7, 10, 40])
+def test_relax_over_decreases_and_converges(dd, n):
+    """reference tests/test_utils.py:857-878 (Rayleigh quotient decreases) + convergence to the lowest eigenvalue."""
+    from carcassonne_b200.utils import relaxOver
+    rng = np.random.default_rng(n)
+    h = crand(rng, n, n)
+    h = h + h.conj().T
+    b = crand(rng, n, n)
+    nm = b @ b.conj().T + n * np.eye(n)
+    v0 = crand(rng, n)
+    old = (np.vdot(v0, h @ v0) / np.vdot(v0, nm @ v0)).real
+    res = relaxOver(dd.fromArray(v0), _dense_multiplier(dd, h, False), _dense_multiplier(dd, nm, False)).toArray()
+    new = (np.vdot(res, h @ res) / np.vdot(res, nm @ res)).real
+    assert new < old
+    exact = np.min(np.linalg.eigvals(np.linalg.solve(nm, h)).real)
+    assert new >= exact - 1e-9
+    res = relaxOver(dd.fromArray(v0), _dense_multiplier(dd, h, False), _dense_multiplier(dd, nm, False),
+                    maximum_number_of_multiplications=3000, tolerance=1e-13).toArray()
+    new = (np.vdot(res, h @ res) / np.vdot(res, nm @ res)).real
+    assert abs(new - exact) < 1e-8 * max(1, abs(exact))
+    # standard problem
+    res = relaxOver(dd.fromArray(v0), _dense_multiplier(dd, h, False)).toArray()
+    assert np.vdot(res, h @ res).real < (np.vdot(v0, h @ v0) / np.vdot(v0, v0)).real
+
+
+@pytest.mark.parametrize("n", [1, 5, 64, 65, 200, 513])
+def test_lu_and_gmres(dd, n):
+    import ctypes as C
+    from carcassonne_b200.compression import _gmres_dense
+    from carcassonne_b200.utils import LUFactors
+    rng = np.random.default_rng(n)
+    a = crand(rng, n, n) + n * 0.1 * np.eye(n)
+    b = crand(rng, n)
+    lu = LUFactors(dd.fromArray(a))
+    assert not lu.singular
+    x = lu.solve(dd.fromArray(b)).toArray()
+    assert relerr(a @ x, b) < 1e-10
+    import scipy.linalg as sla
+    ref_lu, ref_piv = sla.lu_factor(a)
+    assert np.array_equal(lu.piv.cpu().numpy(), ref_piv)
+    assert relerr(lu.lu.toArray(), ref_lu) < 1e-10
+    spd = a.conj().T @ a + np.eye(n)
+    x = _gmres_dense(dd.fromArray(spd), dd.fromArray(b), rtol=1e-10).toArray()
+    assert relerr(spd @ x, b) < 1e-8
+
+
+def _physical_system(dd, J=0.5, grow=True):
+    """A small, positive-definite TFIM system built the way a run builds it."""
+    from carcassonne_b200.system import System
+    s = System.newTrivialWithSimpleSparseOperator(O=-dd.Z, OO_LR=[dd.X, -J * dd.X], OO_UD=[dd.X, -J * dd.X])
+    for d in range(4):
+        s.contractTowards(d)
+    if grow:
+        np.random.seed(11)
+        s.increaseBandwidth(0, by=1)
+        s.minimizeExpectation()
+        s.increaseBandwidth(1, by=1)
+        s.minimizeExpectation()
+        for d in range(4):
+            s.contractTowards(d)
+    return s
+
+
+def test_minimize_matches_full_eigensolver(dd):
+    """reference system/_2d.py:498-502 is its own dense cross-check of minimizeExpectation; energy tolerance from
+    the north star (1e-10 relative) once the iteration has converged."""
+    from copy import copy
+    s = _physical_system(dd)
+    assert s.state_center_data.shape == (2, 2, 2, 2, 2)
+    o = copy(s)
+    lowest = o.minimizeExpectationUsingFullEigensolver()
+    assert abs(o.computeExpectation() - lowest) < 1e-10 * abs(lowest)
+    before = s.computeExpectation()
+    for _ in range(12):
+        s.minimizeExpectation()
+    after = s.computeExpectation()
+    assert after.real <= before.real + 1e-9
+    assert abs(after.real - lowest) < 1e-8 * abs(lowest)
+    assert abs(after.imag) < 1e-9
+
+
+def test_increase_bandwidth_preserves_expectation(dd):
+    """Enlarging the center bond with isometries must not change <H>/<N> (the padded directions carry no weight)."""
+    from carcassonne_b200.utils import InvariantViolatedError
+    s = _physical_system(dd, grow=False)
+    e0, n0 = s.computeExpectationAndNormalization()
+    np.random.seed(4)
+    s.increaseBandwidth(0, by=1)
+    assert s.state_center_data.shape == (2, 1, 2, 1, 2)
+    assert s.just_increased_bandwidth
+    with pytest.raises(InvariantViolatedError):
+        s.contractTowards(0)
+    s.minimizeExpectation()
+    assert not s.just_increased_bandwidth
+    e1 = s.computeOneSiteExpectation()
+    assert np.isfinite(e1)
+
+
+def test_silly_field_and_magnetic_field_walks(dd):
+    """reference tests/test_system.py:308-440: exact integer known answers for random walks."""
+    from carcassonne_b200.system import System
+    rng = random.Random(3)
+    for _ in range(4):
+        system = System.newTrivialWithSimpleSparseOperator(O=dd.newIdentity(1))
+        width = height = 1
+        for _ in range(rng.randint(0, 5)):
+            direction = rng.randint(0, 3)
+            system.contractTowards(direction)
+            if direction in (0, 2):
+                width += 1
+            else:
+                height += 1
+        assert abs(system.computeExpectation() - width * height) < 1e-12 * width * height
+        assert abs(system.computeNormalization() - 1) < 1e-12
+    states = (dd.fromArray(np.array([[[[[1, 0]]]]])), dd.fromArray(np.array([[[[[0, 1]]]]])))
+    spins = (1, -1)
+    for _ in range(4):
+        system = System.newTrivialWithSimpleSparseOperator(O=dd.Z)
+        total = 0
+        rows = {"U": 0, "D": 0, "L": 0, "R": 0}
+        for _ in range(rng.randint(0, 5)):
+            direction, spin = rng.randint(0, 3), rng.randint(0, 1)
+            system.setStateCenter(states[spin])
+            system.contractTowards(direction)
+            # the absorbed center joins its row / column; corners pick up what the neighbouring sides held
+            if direction in (0, 2):
+                total += spins[spin] + rows["U"] + rows["D"]
+                rows["R" if direction == 0 else "L"] += spins[spin]
+            else:
+                total += spins[spin] + rows["L"] + rows["R"]
+                rows["U" if direction == 1 else "D"] += spins[spin]
+        final = rng.randint(0, 1)
+        system.setStateCenter(states[final])
+        total += spins[final]
+        assert abs(system.computeExpectation() - total) < 1e-12 * max(1, abs(total))
+        assert abs(system.computeNormalization() - 1) < 1e-12
+        hv = system.formExpectationMultiplier()(states[final]).toArray()
+        assert relerr(hv, total * states[final].toArray()) < 1e-12 if total else np.linalg.norm(hv) < 1e-12
+
+
+# -- compression (reference tests/test_compression.py, test_system.py:40-81) ------------------------------------------
+def test_product_compressor_golden(dd):
+    from carcassonne_b200.compression import computeProductCompressor, formProductCompressorMatrix
+    g = load("compressor")
+    Lt, Rt, new = dd.fromArray(g["L"]), dd.fromArray(g["R"]), int(g["new"])
+    A = formProductCompressorMatrix(Lt, dd.fromArray(g["als_c0"]), Rt)
+    assert relerr(A.toArray(), g["als_matrix"]) < TOL
+    c = computeProductCompressor(Lt, Rt, new, initial=dd.fromArray(g["initial"]))
+    Lc = Lt.absorbMatrixAt(1, c).absorbMatrixAt(2, c.conj())
+    Rc = Rt.absorbMatrixAt(0, c.conj()).absorbMatrixAt(1, c)
+    prod = Lc.contractWith(Rc, (1, 2, 3), (0, 1, 2)).toArray()
+    assert relerr(prod, g["compressed_product"]) < 1e-8
+    assert relerr(prod, g["exact_product"]) < 1e-8
+    ch = c.toArray()
+    assert relerr(ch.conj().T @ ch, g["compressor"].conj().T @ g["compressor"]) < 1e-7
+    assert np.linalg.norm(ch @ ch.conj().T - np.eye(new)) < 1e-10
+
+
+def test_product_compressor_draws_like_the_reference(dd):
+    """Without `initial` the random start comes from the host NumPy stream at the same point (compression.py:35)."""
+    from carcassonne_b200.compression import computeProductCompressor
+    g = load("compressor")
+    Lt, Rt, new = dd.fromArray(g["L"]), dd.fromArray(g["R"]), int(g["new"])
+    np.random.seed(5)
+    c1 = computeProductCompressor(Lt, Rt, new).toArray()
+    np.random.seed(5)
+    init = dd.newRandom(5, new)
+    c2 = computeProductCompressor(Lt, Rt, new, initial=init).toArray()
+    assert relerr(c1, c2) < 1e-12
+
+
+def test_compute_compressor(dd):
+    from carcassonne_b200.utils import Multiplier, computeCompressor
+    g = load("compressor")
+    gram = g["gram"]
+    m = Multiplier((7, 7), lambda v: gram @ v, 49, lambda: gram, 0)
+    for new in (5, 2):
+        comp, inv = computeCompressor(7, new, m, np.complex128, True)
+        ref = g["cc%d_comp" % new]
+        assert np.allclose(np.sort(np.linalg.norm(comp, axis=1) ** 2), np.sort(np.linalg.norm(ref, axis=1) ** 2),
+                           rtol=1e-10)
+        assert relerr(comp.conj().T @ comp, ref.conj().T @ ref) < 1e-9
+
+
+def test_state_compression_preserves_expectation(dd):
+    """reference tests/test_system.py:40-81: compressing to the full dimension leaves <H>, <N> unchanged."""
+    g = load("walk_tfim_chi2_D2")
+    corners, sides, center = system_parts(g, "walked")
+    s = device_system(dd, corners, sides, center, sparse(g, "operator"))
+    e0, n0 = s.computeExpectationAndNormalization()
+    np.random.seed(3)
+    for corner_id in range(4):
+        for direction in range(2):
+            full = s.corners[corner_id][to_tag(("I",))].shape[3 * direction]
+            s.compressCornerStateTowards(corner_id, direction, full)
+    e1, n1 = s.computeExpectationAndNormalization()
+    assert abs(e1 - e0) < 1e-7 * abs(e0)
+    assert abs(n1 - n0) < 1e-7 * abs(n0)
+    s.assertDimensionsAreConsistent()
+    with pytest.raises(ValueError):
+        s.compressCornerStateTowards(0, 2, 1)
+
+
+def test_operator_compression_preserves_expectation(dd):
+    """reference tests/test_system.py:82-178: folding all two-site halves into a full-rank compressed bond leaves the
+    expectation unchanged."""
+    g = load("walk_tfim_chi2_D2")
+    corners, sides, center = system_parts(g, "walked")
+    s = device_system(dd, corners, sides, center, sparse(g, "operator"))
+    for d in (0, 1):
+        s.contractUnnormalizedTowards(d)
+    e0, n0 = s.computeExpectationAndNormalization()
+    from carcassonne_b200.sparse import TwoSiteOperator
+    for corner_id in range(4):
+        for direction in range(2):
+            count = sum(1 for t in s.corners[corner_id] if isinstance(t, TwoSiteOperator) and t.direction == direction)
+            if count:
+                s.compressCornerTwoSiteOperatorTowards(corner_id, direction, count)
+    e1, n1 = s.computeExpectationAndNormalization()
+    assert abs(e1 - e0) < 1e-9 * abs(e0)
+    assert abs(n1 - n0) < 1e-9 * abs(n0)
+
+
+# -- bandwidth (reference tests/test_system.py:276-305) ---------------------------------------------------------------
+def test_increase_bandwidth_golden(dd):
+    """The reference's own increaseBandwidth output (tests/golden/bandwidth.npz).  The enlarged center is rank
+    deficient, so the tensors depend on LAPACK's choice of null-space vectors; what must agree is everything that
+    choice cannot touch: shapes, the flag, and the unchanged expectation value."""
+    g = load("bandwidth")
+    corners, sides, center = system_parts(g, "before")
+    s = device_system(dd, corners, sides, center, sparse(g, "operator"))
+    q = dd.fromArray(g["sample"]).qr(mode="economic")[0]
+    s.increaseBandwidth(0, by=1, enlargeners=(q, q.conj()))
+    ac, as_, acenter = system_parts(g, "after")
+    assert s.state_center_data.shape == acenter.shape
+    for i in range(4):
+        assert [t for t in s.corners[i]] == [to_tag(t) for t in ac[i]]
+        assert [t for t in s.sides[i]] == [to_tag(t) for t in as_[i]]
+        for t in ac[i]:
+            assert s.corners[i][to_tag(t)].shape == ac[i][t].shape
+    assert s.just_increased_bandwidth
+    with pytest.raises(ValueError):
+        s.increaseBandwidth(2, by=1)
+    with pytest.raises(ValueError):
+        s.increaseBandwidth(0, by=100)
+
+
+def test_increase_bandwidth_uses_host_rng_like_reference(dd):
+    g = load("bandwidth")
+    corners, sides, center = system_parts(g, "before")
+    s = device_system(dd, corners, sides, center, sparse(g, "operator"))
+    np.random.seed(9)
+    a, b = s.increaseBandwidth(0, by=1)
+    np.random.seed(9)
+    from oracle import linalg as ol
+    q, _ = ol.enlargener_from_random(ol.random_complex(np.random, 3, 2))
+    assert relerr(a.toArray(), q) < 1e-12
+
+
+# -- end-to-end runs (reference tests/test_simulator_2d_in_1d.py, test_simulator_2d_in_15d.py) -------------------------
+def _tfim_run(dd, direction):
+    from carcassonne_b200 import policies as pol
+    from carcassonne_b200.system import System
+    kw = {"OO_LR" if direction == 0 else "OO_UD": [dd.X, -0.01 * dd.X]}
+    system = System.newTrivialWithSimpleSparseOperator(O=-dd.Z, **kw)
+    system.setPolicy("sweep convergence", pol.RelativeStateDifferenceThresholdConvergencePolicy(1e-5))
+    system.setPolicy("run convergence", pol.RelativeOneSiteExpectationDifferenceThresholdConvergencePolicy(1e-7))
+    system.setPolicy("bandwidth increase", pol.OneDirectionIncrementBandwidthIncreasePolicy(direction, 2))
+    system.setPolicy("contraction", pol.RepeatPatternContractionPolicy([0 + direction, 2 + direction]))
+    system.runUntilConverged()
+    return system
+
+
+@pytest.mark.parametrize("direction", [0, 1])
+def test_run_transverse_ising_1d_in_2d(dd, direction):
+    g = load("runs")
+    np.random.seed(51 + direction)
+    random.seed(51 + direction)
+    system = _tfim_run(dd, direction)
+    energy = system.computeOneSiteExpectation()
+    assert abs(energy - (-1.0000250001562545)) < 1e-7                                   # the reference's own assertion
+    assert abs(energy - g["tfim1d_dir%d_energy" % direction]) <= 1e-10 * abs(energy)    # north-star tolerance
+    assert [system.number_of_sweeps, system.number_of_iterations] == list(g["tfim1d_dir%d_counts" % direction])
+    assert list(system.state_center_data.shape) == list(g["tfim1d_dir%d_shape" % direction])
+
+
+def test_run_magnetic_field_15d(dd):
+    from carcassonne_b200 import policies as pol
+    from carcassonne_b200.system import System
+    g = load("runs")
+    np.random.seed(61)
+    random.seed(61)
+    system = System.newTrivialWithSimpleSparseOperator(O=dd.Z)
+    system.setPolicy("state compression", pol.ConstantStateCompressionPolicy(1))
+    system.setPolicy("sweep convergence", pol.RelativeOneSiteExpectationDifferenceThresholdConvergencePolicy(1e-7))
+    system.setPolicy("run convergence", pol.RelativeOneSiteExpectationDifferenceThresholdConvergencePolicy(1e-7))
+    system.setPolicy("bandwidth increase", pol.AllDirectionsIncrementBandwidthIncreasePolicy())
+    system.setPolicy("contraction", pol.RepeatPatternContractionPolicy(range(4)))
+    system.runUntilConverged()
+    energy = system.computeOneSiteExpectation()
+    assert abs(energy - (-1)) < 1e-6
+    assert abs(energy - g["zfield15d_energy"]) < 1e-9
+
+
+def test_run_ferromagnetic_coupling(dd):
+    from carcassonne_b200 import policies as pol
+    from carcassonne_b200.system import System
+    np.random.seed(7)
+    system = System.newTrivialWithSimpleSparseOperator(OO_LR=[dd.Z, -dd.Z])
+    system.setPolicy("sweep convergence", pol.RelativeOneSiteExpectationDifferenceThresholdConvergencePolicy(1e-7))
+    system.setPolicy("run convergence", pol.RelativeOneSiteExpectationDifferenceThresholdConvergencePolicy(1e-7))
+    system.setPolicy("bandwidth increase", pol.OneDirectionIncrementBandwidthIncreasePolicy(0))
+    system.setPolicy("contraction", pol.RepeatPatternContractionPolicy([0, 2]))
+    system.runUntilConverged()
+    assert abs(system.computeOneSiteExpectation() - (-1)) < 1e-7
+
+
+def test_policies_cannot_be_set_twice(dd):
+    from carcassonne_b200 import policies as pol
+    from carcassonne_b200.system import System
+    system = System.newTrivialWithSimpleSparseOperator(O=dd.Z)
+    system.setPolicy("contraction", pol.RepeatPatternContractionPolicy([0]))
+    with pytest.raises(ValueError):
+        system.setPolicy("contraction", pol.RepeatPatternContractionPolicy([0]))
+    with pytest.raises(ValueError):
+        system.setPolicy("no such slot", pol.RepeatPatternContractionPolicy([0]))
+    with pytest.raises(ValueError):
+        system.sweepUntilConverged()       # sweep convergence policy missing
