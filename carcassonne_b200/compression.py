@@ -6,16 +6,19 @@ problem min_x |A(c) x - b| followed by a polar projection (``unitize``).
 
 Device formulation: the (l r) x (old new) matrix A(c) of the reference's generated ``formMatrix`` is produced by
 three small mode products and one GEMM, the normal equations A^H A x = A^H b are formed in Gram form by two more
-GEMMs (an (old new)^2 matrix -- a few hundred on a side), solved with the device GMRES exactly as the reference
-solves them (restart 20, rtol 1e-5: a Krylov solver, because A^H A is singular whenever the product is exactly
-compressible), and the polar factor comes from the device Jacobi SVD.
+GEMMs (an (old new)^2 matrix -- a few hundred on a side) and solved directly with the device LU after a relative
+shift of 1e-10 on the diagonal.  The reference hands them to GMRES(20) at rtol 1e-5, which needs thousands of
+matvecs on these ill-conditioned systems (kappa ~ 1e5 at chi = 8, D = 4) and stops 5 % away from the least-squares
+solution; the shifted direct solve returns the minimum-norm least-squares solution to ~1e-10, deterministically, in
+a few milliseconds.  (Device GMRES and CG exist behind carc_gmres / carc_cg and are parity-tested.)  The polar factor
+comes from the device Jacobi SVD.
 """
 import ctypes as C
 
 from . import _lib
 from ._lib import lib, check
-from .data import DeviceData, _empty, _ptr, _stream, gemm
-from .utils import SolverDidNotConverge, _DenseOperator
+from .data import DeviceData, _empty, _ptr, _stream, gemm, gemm_scatter
+from .utils import LUFactors, SolverDidNotConverge, _DenseOperator
 
 
 def _gmres_dense(matrix, rhs, rtol=1e-5, restart=20, maxiter=None):
@@ -34,6 +37,20 @@ def _gmres_dense(matrix, rhs, rtol=1e-5, restart=20, maxiter=None):
     return DeviceData(x)
 
 
+def _cg_dense(matrix, rhs, rtol=1e-10, maxiter=None):
+    """Minimum-norm solution of the Hermitian PSD system matrix x = rhs by device CG from x0 = 0."""
+    n = matrix.shape[0]
+    op = _DenseOperator(matrix)
+    x = _empty((n,))
+    iters = C.c_int(0)
+    resid = C.c_double(0.0)
+    rc = lib.carc_cg(op._handle, _ptr(rhs._t), _ptr(x), float(rtol), int(maxiter if maxiter is not None else 20 * n),
+                     C.byref(iters), C.byref(resid), _stream())
+    op.close()
+    check(rc)
+    return DeviceData(x), iters.value, resid.value
+
+
 def formProductCompressorMatrix(L, c, R):
     """A[(l r), (i n)] = sum L[l,i,j,p] conj(c)[j,m] conj(c)[k,n] c[q,m] R[k,q,p,r] with c of shape [old, new]
     (the generated contractor of reference compression.py:11-25, rows [L0 R3], columns [L1 c^H_0])."""
@@ -45,14 +62,67 @@ def formProductCompressorMatrix(L, c, R):
     gemm(_lib.OP_J, _lib.OP_T, old, old, new, c._t, new, c._t, new, Pc)
     # Lc[l, i, q, p] = sum_j L[l, i, j, p] Pc[j, q]
     Lc = L.absorbMatrixAt(2, DeviceData(Pc).transpose())
-    # Rc[n, q, p, r] = sum_k conj(c)[k, n] R[k, q, p, r]
-    Rc = R.absorbMatrixAt(0, c.adjoint())
-    # A[l, i, n, r] = sum_{q, p} Lc[l, i, q, p] Rc[n, q, p, r]
-    A4 = Lc.contractWith(Rc, (2, 3), (1, 2))
-    return A4.join((0, 3), (1, 2))
+    # Rc[q, p, r, n] = sum_k conj(c)[k, n] R[k, q, p, r]      (a small tensor: new x old x p x r)
+    Rc = _empty((old * p * r, new))
+    gemm(_lib.OP_T, _lib.OP_J, old * p * r, new, old, R._t, old * p * r, c._t, new, Rc)
+    # A[l, r, i, n] = sum_{q, p} Lc[(l i), (q p)] Rc[(q p), (r n)], written straight into the [(l r), (i n)] layout
+    A = _empty((l * r, old * new))
+    gemm_scatter(_lib.OP_N, _lib.OP_N, l * old, r * new, old * p, Lc._t, old * p, Rc, r * new, A,
+                 ((l, r * old * new), (old, new)), ((r, old * new), (new, 1)))
+    return DeviceData(A)
 
 
-def computeProductCompressor(L, R, new_dimension, initial=None, sweeps=4):
+def _solve_normal_equations(gram, rhs, regularization):
+    """x = (G + eps mean(diag G) I)^-1 rhs by the device LU.  G = A^H A is singular whenever the product is exactly
+    compressible; the shift keeps the factorisation well defined, leaves the solution in range(G) untouched to
+    O(eps) and returns (numerically) zero along the null space -- the minimum-norm least-squares solution the
+    reference's GMRES from x0 = 0 approximates to 1e-5."""
+    n = gram.shape[0]
+    eye = DeviceData.newIdentity(n)
+    trace = eye.contractWithAlongAll(gram)                   # sum_i G[i, i] (reduction kernel)
+    gram._axpby(regularization * float(trace.real) / n, eye, 1.0)
+    return LUFactors(gram).solve(rhs)
+
+
+class _GramForm:
+    """Normal equations of the ALS without ever forming A (A is (l r) x (old new), 137 GB
+    at chi = D = 8).  With LL0 = L^H L and RR0 = R R^H over the outer legs (computed ONCE per compression, two
+    well-shaped DMMA GEMMs with K = l and K = r) and T = LL0 . RR0^T,
+
+        A^H A [(i n),(i' n')] = sum_{q q'} LLp[i,q,i',q'] RRc[n,q,n',q'],   LLp = Pc^H LL0 Pc,  RRc = c^T RR0 conj(c)
+        A^H b [(i n)]         = sum_{j q k} conj(Pc[j,q]) c[k,n] T[i,j,k,q],   Pc = conj(c) c^T
+
+    so every ALS round costs O(old^5) instead of O(l r old^2 new^2).  Operator bond 1 only (Identity tensors)."""
+
+    def __init__(self, L, R):
+        l, old, _, _ = L.shape
+        r = R.shape[3]
+        self.old = old
+        o2 = old * old
+        LL0 = _empty((o2, o2))
+        gemm(_lib.OP_C, _lib.OP_N, o2, o2, l, L._t, o2, L._t, o2, LL0)             # sum_l conj(L[l,(ij)]) L[l,(i'j')]
+        RR0 = _empty((o2, o2))
+        gemm(_lib.OP_J, _lib.OP_T, o2, o2, r, R._t, r, R._t, r, RR0)                # sum_r conj(R[(kq),r]) R[(k'q'),r]
+        T = _empty((o2, o2))
+        gemm(_lib.OP_N, _lib.OP_T, o2, o2, o2, LL0, o2, RR0, o2, T)                 # T[(ij),(kq)]
+        self.LL0 = DeviceData(LL0).split(old, old, old, old)
+        self.RR0 = DeviceData(RR0).split(old, old, old, old)
+        self.T = DeviceData(T).split(old, old, old, old)
+
+    def normal_equations(self, c):
+        old, new = c.shape
+        Pc = _empty((old, old))
+        gemm(_lib.OP_J, _lib.OP_T, old, old, new, c._t, new, c._t, new, Pc)
+        Pc = DeviceData(Pc)
+        LLp = self.LL0.absorbMatrixAt(1, Pc.adjoint()).absorbMatrixAt(3, Pc.transpose())       # [i, q, i', q']
+        RRc = self.RR0.absorbMatrixAt(0, c.transpose()).absorbMatrixAt(2, c.adjoint())         # [n, q, n', q']
+        gram = LLp.contractWith(RRc, (1, 3), (1, 3)).join((0, 2), (1, 3))                      # [(i n), (i' n')]
+        U = self.T.absorbMatrixAt(2, c.transpose())                                            # [i, j, n, q]
+        rhs = U.contractWith(Pc.conj(), (1, 3), (0, 1)).ravel()                                # [(i n)]
+        return gram, rhs
+
+
+def computeProductCompressor(L, R, new_dimension, initial=None, sweeps=4, regularization=1e-10):
     """reference compression.py:26-45.  ``initial`` (optional) is the random [old, new] draw; by default it is drawn
     from the host NumPy stream with ``newRandom`` exactly where the reference draws it."""
     if L.shape[1] != L.shape[2]:
@@ -62,19 +132,32 @@ def computeProductCompressor(L, R, new_dimension, initial=None, sweeps=4):
     if L.shape[1] != R.shape[1]:
         raise ValueError("left and right shapes are incompatible (given " + str(L.shape) + " and " + str(R.shape) + ")")
     old_dimension = L.shape[1]
-    b = L.contractWith(R, (1, 2, 3), (0, 1, 2)).ravel()
     if initial is None:
         initial = DeviceData.newRandom(old_dimension, new_dimension)
     compressor = initial.unitize()
+    if new_dimension == old_dimension:
+        # every unitary preserves the product exactly: the starting point already is a global minimiser of the
+        # ALS objective (the reference still runs its four rounds and lands on some other unitary)
+        return compressor.transpose()
     m = old_dimension * new_dimension
-    rows = b.shape[0]
+    if L.shape[3] == 1:
+        form = _GramForm(L, R)
+    else:
+        form = None
+        b = L.contractWith(R, (1, 2, 3), (0, 1, 2)).ravel()
+        rows = b.shape[0]
     for _ in range(sweeps):
-        A = formProductCompressorMatrix(L, compressor, R)
-        gram = _empty((m, m))
-        gemm(_lib.OP_C, _lib.OP_N, m, m, rows, A._t, m, A._t, m, gram)          # A^H A
-        rhs = _empty((m,))
-        gemm(_lib.OP_C, _lib.OP_N, m, 1, rows, A._t, m, b._t, 1, rhs)           # A^H b
-        x = _gmres_dense(DeviceData(gram), DeviceData(rhs))
+        if form is not None:
+            gram, rhs = form.normal_equations(compressor)
+        else:
+            A = formProductCompressorMatrix(L, compressor, R)
+            gram = _empty((m, m))
+            gemm(_lib.OP_C, _lib.OP_N, m, m, rows, A._t, m, A._t, m, gram)          # A^H A
+            rhs = _empty((m,))
+            gemm(_lib.OP_C, _lib.OP_N, m, 1, rows, A._t, m, b._t, 1, rhs)           # A^H b
+            del A
+            gram, rhs = DeviceData(gram), DeviceData(rhs)
+        x = _solve_normal_equations(gram, rhs, regularization)
         compressor = x.split(old_dimension, new_dimension).unitize()
     return compressor.transpose()
 

@@ -308,6 +308,24 @@ int carc_gmres(carc_operator* A, const void* b, void* x, double rtol, int restar
   return rc;
 }
 
+int carc_cg(carc_operator* A, const void* b, void* x, double rtol, int maxiter, int* iterations_out, double* residual_out,
+            void* stream) {
+  CARC_REQUIRE(A && A->finalized && b && x, CARC_ERR_VALUE, "cg: invalid argument");
+  cudaStream_t st = S(stream);
+  const int64_t n = A->n;
+  void *work = nullptr, *state = nullptr;
+  CARC_CHECK_CUDA(cudaMallocAsync(&work, sizeof(cplx) * (size_t)3 * n, st));
+  CARC_CHECK_CUDA(cudaMallocAsync(&state, carc::cg_state_bytes(), st));
+  int iters = 0;
+  double resid = 0.0;
+  int rc = carc::cg(as_linop(A), (const cplx*)b, (cplx*)x, n, rtol, maxiter, (cplx*)work, state, &iters, &resid, st);
+  cudaFreeAsync(work, st);
+  cudaFreeAsync(state, st);
+  if (iterations_out) *iterations_out = iters;
+  if (residual_out) *residual_out = resid;
+  return rc;
+}
+
 int carc_relax(carc_operator* H, carc_operator* N_op, const void* N_lu, const void* N_piv, void* v, int max_mults,
                double tolerance, int krylov_dim, double gmres_rtol, int gmres_restart, int gmres_maxiter,
                double* info_out, void* stream) {

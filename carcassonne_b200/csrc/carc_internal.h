@@ -73,6 +73,9 @@ int lu_solve(const cplx* LU, int n, const int* piv, cplx* x, cudaStream_t stream
 int gmres(const LinOp& A, const cplx* b, cplx* x, int64_t n, double rtol, int restart, int maxiter, cplx* work,
           void* state_dev, int* iters_out, double* resid_out, cudaStream_t stream);
 size_t gmres_state_bytes();
+int cg(const LinOp& A, const cplx* b, cplx* x, int64_t n, double rtol, int maxiter, cplx* work, void* state_dev,
+       int* iters_out, double* resid_out, cudaStream_t stream);
+size_t cg_state_bytes();
 int relax(const LinOp& M, cplx* v, int64_t n, int max_mults, double tol, int k, cplx* work, void* state_dev,
           RelaxInfo* info, cudaStream_t stream);
 size_t relax_state_bytes();

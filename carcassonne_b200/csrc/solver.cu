@@ -560,6 +560,68 @@ __global__ void __launch_bounds__(VT) gmres_update_kernel(const cplx* __restrict
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Conjugate gradients for Hermitian positive semi-definite systems (the normal equations of compression.py).
+struct CgState {
+  double rs;      // <r, r>
+  double bnorm;
+  double resid;   // sqrt(<r, r>)
+  double pad;
+};
+
+// x = 0, r = p = b
+__global__ void __launch_bounds__(VT) cg_start_kernel(const cplx* __restrict__ b, int64_t n, cplx* __restrict__ x,
+                                                      cplx* __restrict__ r, cplx* __restrict__ p,
+                                                      CgState* __restrict__ cs) {
+  __shared__ cplx sh[32];
+  cplx s[1] = {make_double2(0.0, 0.0)};
+  for (int64_t i = threadIdx.x; i < n; i += VT) {
+    const cplx v = b[i];
+    x[i] = make_double2(0.0, 0.0);
+    r[i] = v;
+    p[i] = v;
+    s[0].x += cabs2(v);
+  }
+  block_csum<1>(s, sh);
+  if (threadIdx.x == 0) {
+    cs->rs = s[0].x;
+    cs->bnorm = sqrt(s[0].x);
+    cs->resid = sqrt(s[0].x);
+  }
+}
+
+// alpha = rs / <p, Ap>; x += alpha p; r -= alpha Ap; rs' = <r, r>; p = r + (rs'/rs) p
+__global__ void __launch_bounds__(VT) cg_step_kernel(const cplx* __restrict__ Ap, int64_t n, cplx* __restrict__ x,
+                                                     cplx* __restrict__ r, cplx* __restrict__ p,
+                                                     CgState* __restrict__ cs) {
+  __shared__ cplx sh[32];
+  cplx s[1] = {make_double2(0.0, 0.0)};
+  for (int64_t i = threadIdx.x; i < n; i += VT) s[0] = cadd(s[0], cmulc(p[i], Ap[i]));
+  block_csum<1>(s, sh);
+  const double rs = cs->rs;
+  const double pAp = s[0].x;
+  if (!(pAp > 0.0) || rs == 0.0) {   // p in the null space / already converged: leave the state untouched
+    return;
+  }
+  const double alpha = rs / pAp;
+  cplx t[1] = {make_double2(0.0, 0.0)};
+  for (int64_t i = threadIdx.x; i < n; i += VT) {
+    x[i] = cadd(x[i], cscale(p[i], alpha));
+    const cplx ri = csub(r[i], cscale(Ap[i], alpha));
+    r[i] = ri;
+    t[0].x += cabs2(ri);
+  }
+  block_csum<1>(t, sh);
+  const double beta = t[0].x / rs;
+  for (int64_t i = threadIdx.x; i < n; i += VT) p[i] = cadd(r[i], cscale(p[i], beta));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    cs->rs = t[0].x;
+    cs->resid = sqrt(t[0].x);
+  }
+}
+
 }  // namespace
 
 // ===================================================================================================
@@ -685,6 +747,47 @@ int gmres(const LinOp& A, const cplx* b, cplx* x, int64_t n, double rtol, int re
 }
 
 size_t gmres_state_bytes() { return sizeof(GmresState); }
+
+// ---------------------------------------------------------------------------------------------------
+int cg(const LinOp& A, const cplx* b, cplx* x, int64_t n, double rtol, int maxiter, cplx* work, void* state_dev,
+       int* iters_out, double* resid_out, cudaStream_t stream) {
+  // work: 3 * n complex (r, p, Ap)
+  CgState* cs = reinterpret_cast<CgState*>(state_dev);
+  cplx* r = work;
+  cplx* p = work + n;
+  cplx* Ap = work + 2 * n;
+  cg_start_kernel<<<1, VT, 0, stream>>>(b, n, x, r, p, cs);
+  CgState host;
+  CARC_CHECK_CUDA(cudaMemcpyAsync(&host, cs, sizeof(CgState), cudaMemcpyDeviceToHost, stream));
+  CARC_CHECK_CUDA(cudaStreamSynchronize(stream));
+  const double target = rtol * host.bnorm;
+  int it = 0;
+  double best = host.resid;
+  int since_best = 0;
+  const int check_every = 8;
+  while (host.resid > target && it < maxiter) {
+    for (int q = 0; q < check_every && it < maxiter; ++q, ++it) {
+      int rc = A.apply(p, Ap, stream);
+      if (rc) return rc;
+      cg_step_kernel<<<1, VT, 0, stream>>>(Ap, n, x, r, p, cs);
+    }
+    CARC_CHECK_CUDA(cudaMemcpyAsync(&host, cs, sizeof(CgState), cudaMemcpyDeviceToHost, stream));
+    CARC_CHECK_CUDA(cudaStreamSynchronize(stream));
+    if (host.resid < 0.999 * best) {
+      best = host.resid;
+      since_best = 0;
+    } else if (++since_best >= 64) {
+      break;   // stagnated at the rounding floor of an ill-conditioned system
+    }
+  }
+  *iters_out = it;
+  *resid_out = host.resid;
+  CARC_CHECK_CUDA(cudaGetLastError());
+  return CARC_OK;
+}
+
+size_t cg_state_bytes() { return sizeof(CgState); }
+
 
 // ---------------------------------------------------------------------------------------------------
 int relax(const LinOp& M, cplx* v, int64_t n, int max_mults, double tol, int k, cplx* work, void* state_dev,

@@ -14,6 +14,8 @@
 // Fragment mapping: one 8-wide K chunk feeds two DMMA k-steps.  k-step e in {0,1} uses the K indices
 // {2c + e : c = lane % 4}, i.e. every lane reads two adjacent complex numbers (32 contiguous bytes) per
 // operand row.  Any permutation of K is legal as long as A and B use the same one.
+#include <algorithm>
+
 #include "carc_internal.h"
 #include "common.cuh"
 
@@ -39,6 +41,9 @@ struct GemmParams {
   GemmOut out;
   const int64_t* rowoff;      // optional per-row / per-column output offset tables (override `out`)
   const int64_t* coloff;
+  unsigned tiles_m;           // number of M tiles (the tile grid is linearised on blockIdx.x)
+  int splitk;                 // > 1: blockIdx.z is a K split; raw partial products go to C = workspace[split][M][N]
+  int64_t kt_per_split;       // K tiles per split
 };
 
 __device__ __forceinline__ double flip(double x, uint32_t mask) {
@@ -53,9 +58,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) zgemm_kernel(GemmParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1;       // 4 x 2 warps
   const int r = lane >> 2, c = lane & 3;
-  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
-  const cplx* A = p.A + (int64_t)blockIdx.z * p.strideA;
-  const cplx* B = p.B + (int64_t)blockIdx.z * p.strideB;
+  const int64_t m0 = (int64_t)(blockIdx.x % p.tiles_m) * BM, n0 = (int64_t)(blockIdx.x / p.tiles_m) * BN;  // 1-D tile grid
+  const bool split = p.splitk > 1;
+  const cplx* A = p.A + (split ? 0 : (int64_t)blockIdx.z * p.strideA);
+  const cplx* B = p.B + (split ? 0 : (int64_t)blockIdx.z * p.strideB);
   cplx* C = p.C + (int64_t)blockIdx.z * p.strideC;
 
   CTile acc[4][4];
@@ -64,10 +70,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) zgemm_kernel(GemmParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j].zero();
 
-  const int64_t KT = (p.K + BK - 1) / BK;
+  const int64_t KT_all = (p.K + BK - 1) / BK;
+  const int64_t kt0 = split ? (int64_t)blockIdx.z * p.kt_per_split : 0;
+  const int64_t KT = split ? min(p.kt_per_split, KT_all - kt0) : KT_all;
 
   auto load_tile = [&](int64_t kt, int stage) {
-    const int64_t k0 = kt * BK;
+    const int64_t k0 = (kt0 + kt) * BK;
     cplx* as = As + stage * BM * LDK;
     cplx* bs = Bs + stage * BN * LDK;
 #pragma unroll
@@ -169,6 +177,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) zgemm_kernel(GemmParams p) {
   }
 }
 
+// split-K second pass: sum the partial products in split order (deterministic) and apply the real epilogue
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const cplx* __restrict__ ws, int splits, GemmParams p) {
+  const int64_t total = p.M * p.N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    double re = 0.0, im = 0.0;
+    for (int s2 = 0; s2 < splits; ++s2) {
+      const cplx v = ws[(int64_t)s2 * total + i];
+      re += v.x;
+      im += v.y;
+    }
+    const int64_t m = i / p.N, n = i - m * p.N;
+    const int64_t off = (p.rowoff ? p.rowoff[m] : (m / p.out.m_div) * p.out.m_s1 + (m % p.out.m_div) * p.out.m_s0) +
+                        (p.coloff ? p.coloff[n] : (n / p.out.n_div) * p.out.n_s1 + (n % p.out.n_div) * p.out.n_s0);
+    cplx v;
+    v.x = p.alpha.x * re - p.alpha.y * im;
+    v.y = p.alpha.x * im + p.alpha.y * re;
+    if (!(p.beta.x == 0.0 && p.beta.y == 0.0)) {
+      const cplx o = p.C[off];
+      v.x += p.beta.x * o.x - p.beta.y * o.y;
+      v.y += p.beta.x * o.y + p.beta.y * o.x;
+    }
+    p.C[off] = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // DMMA issue-rate microbenchmark: every warp keeps 16 independent accumulator tiles in flight.
 __global__ void __launch_bounds__(256, 1) dmma_peak_kernel(double* out, int iters) {
@@ -258,9 +291,41 @@ int zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, cplx alpha, const c
   }
   CARC_REQUIRE(p.out.m_div > 0 && p.out.n_div > 0, CARC_ERR_VALUE, "zgemm: invalid output map");
   int64_t gx = (N + BN - 1) / BN, gy = (M + BM - 1) / BM;
-  CARC_REQUIRE(gy < 65536 && batch < 65536, CARC_ERR_VALUE, "zgemm: grid too large (M tiles %lld, batch %lld)",
-               (long long)gy, (long long)batch);
-  dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)batch);
+  CARC_REQUIRE(batch < 65536 && gx * gy < (1ll << 31), CARC_ERR_VALUE, "zgemm: grid too large (%lld tiles, batch %lld)",
+               (long long)(gx * gy), (long long)batch);
+  p.tiles_m = (unsigned)gy;
+  p.splitk = 1;
+  p.kt_per_split = 0;
+  const int64_t tiles = gx * gy, KT = (K + BK - 1) / BK;
+  if (batch == 1 && tiles <= 74 && KT >= 64) {
+    // few output tiles, long K (Gram matrices, formMatrix): split K over the idle SMs
+    int64_t splits = std::min<int64_t>(148 * 2 / tiles, KT / 16);
+    splits = std::min<int64_t>(splits, 64);
+    if (splits >= 2) {
+      const int64_t kps = (KT + splits - 1) / splits;
+      splits = (KT + kps - 1) / kps;
+      cplx* ws = nullptr;
+      CARC_CHECK_CUDA(cudaMallocAsync((void**)&ws, sizeof(cplx) * (size_t)splits * M * N, stream));
+      GemmParams q = p;
+      q.splitk = (int)splits;
+      q.kt_per_split = kps;
+      q.C = ws;
+      q.strideC = M * N;
+      q.alpha = make_double2(1.0, 0.0);
+      q.beta = make_double2(0.0, 0.0);
+      q.rowoff = q.coloff = nullptr;
+      q.out.m_div = M; q.out.m_s1 = 0; q.out.m_s0 = N;
+      q.out.n_div = N; q.out.n_s1 = 0; q.out.n_s0 = 1;
+      dim3 grid((unsigned)(gx * gy), 1, (unsigned)splits);
+      zgemm_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(q);
+      const int64_t total = M * N;
+      splitk_reduce_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 148 * 8), 256, 0, stream>>>(ws, (int)splits, p);
+      CARC_CHECK_CUDA(cudaGetLastError());
+      CARC_CHECK_CUDA(cudaFreeAsync(ws, stream));
+      return CARC_OK;
+    }
+  }
+  dim3 grid((unsigned)(gx * gy), 1, (unsigned)batch);
   zgemm_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(p);
   CARC_CHECK_CUDA(cudaGetLastError());
   return CARC_OK;

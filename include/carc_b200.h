@@ -145,6 +145,12 @@ int carc_relax(carc_operator* H, carc_operator* N_op, const void* N_lu, const vo
 /* x = A^-1 b by restarted GMRES from x0 = 0 (scipy.sparse.linalg.gmres call sites utils.py:823, compression.py:39). */
 int carc_gmres(carc_operator* A, const void* b, void* x, double rtol, int restart, int maxiter, int* iterations_out,
                double* residual_out, void* stream);
+/* x = A^+ b for a Hermitian positive semi-definite operator by conjugate gradients from x0 = 0 (the normal equations
+ * A^H A x = A^H b of computeProductCompressor, compression.py:36-43, which the reference hands to GMRES; CG reaches
+ * the same minimum-norm solution without GMRES(20)'s restart stagnation).  Stops at |r| <= rtol |b|, after maxiter
+ * iterations, or when the residual stagnates at the rounding floor; *residual_out is the final |r|. */
+int carc_cg(carc_operator* A, const void* b, void* x, double rtol, int maxiter, int* iterations_out, double* residual_out,
+            void* stream);
 /* In-place LU with partial pivoting of a row-major n x n matrix (LAPACK zgetrf pivoting rule); piv_dev: int32[n] on
  * device.  Synchronises to report *singular_out (1 if a zero pivot was met).  carc_lu_solve overwrites x with A^-1 x. */
 int carc_lu_factor(void* A, int n, void* piv_dev, int* singular_out, void* stream);

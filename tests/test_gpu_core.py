@@ -47,7 +47,7 @@ def test_join_matches_reference_semantics(dd):
     assert np.array_equal(out, a.transpose(2, 0, 3, 1).reshape(8, 5, 3))
 
 
-@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (5, 7, 3), (128, 64, 16), (130, 70, 37), (64, 300, 129), (257, 33, 8)])
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (5, 7, 3), (128, 64, 16), (130, 70, 37), (64, 300, 129), (257, 33, 8), (100, 70, 4100)])
 @pytest.mark.parametrize("opA,opB", list(itertools.product(range(4), range(4))))
 def test_zgemm(dd, M, N, K, opA, opB):
     import torch
@@ -65,7 +65,7 @@ def test_zgemm(dd, M, N, K, opA, opB):
     alpha, beta = 0.7 - 0.2j, -0.3 + 0.5j
     gemm(opA, opB, M, N, K, A, a_st.shape[1], B, b_st.shape[1], Cb, alpha=alpha, beta=beta)
     ref = alpha * (a @ b) + beta * c0
-    assert relerr(Cb.cpu().numpy(), ref) < 1e-14
+    assert relerr(Cb.cpu().numpy(), ref) < (1e-14 if K < 1000 else 1e-13)
     assert _lib.lib.carc_version() >= 100
 
 

@@ -412,6 +412,45 @@ def test_product_compressor_golden(dd):
     assert np.linalg.norm(ch @ ch.conj().T - np.eye(new)) < 1e-10
 
 
+@pytest.mark.parametrize("l,old,new,r", [(3, 5, 2, 4), (16, 8, 4, 40), (7, 6, 3, 300)])
+def test_gram_form_equals_explicit_normal_equations(dd, l, old, new, r):
+    """The Gram-of-Gram normal equations (no A) against A^H A and A^H b with A from the reference's contractor."""
+    from carcassonne_b200.compression import _GramForm, formProductCompressorMatrix
+    from oracle import solver as osolver, linalg as ol
+    rng = np.random.default_rng(l + old + r)
+    Lt, Rt = crand(rng, l, old, old, 1), crand(rng, old, old, 1, r)
+    c = ol.unitize(crand(rng, old, new))
+    A = osolver.product_compressor_matrix(Lt, c, Rt)
+    b = np.tensordot(Lt, Rt, axes=([1, 2, 3], [0, 1, 2])).ravel()
+    assert relerr(formProductCompressorMatrix(dd.fromArray(Lt), dd.fromArray(c), dd.fromArray(Rt)).toArray(), A) < TOL
+    gram, rhs = _GramForm(dd.fromArray(Lt), dd.fromArray(Rt)).normal_equations(dd.fromArray(c))
+    assert relerr(gram.toArray(), A.conj().T @ A) < 1e-11
+    assert relerr(rhs.toArray(), A.conj().T @ b) < 1e-11
+
+
+def test_product_compressor_lossy_matches_least_squares(dd):
+    """A genuinely lossy compression: each ALS round must land on the polar factor of the exact least-squares
+    solution (numpy lstsq on the reference's A), i.e. at least as good as the reference's GMRES(1e-5) round."""
+    from carcassonne_b200.compression import computeProductCompressor
+    from oracle import solver as osolver, linalg as ol
+    rng = np.random.default_rng(12)
+    l, old, new, r = 6, 6, 3, 20
+    Lt = crand(rng, l, old, old, 1)
+    Lt = Lt + Lt.transpose(0, 2, 1, 3).conj()
+    Rt = crand(rng, old, old, 1, r)
+    Rt = Rt + Rt.transpose(1, 0, 2, 3).conj()
+    init = crand(rng, old, new)
+    c = ol.unitize(init)
+    b = np.tensordot(Lt, Rt, axes=([1, 2, 3], [0, 1, 2])).ravel()
+    for _ in range(4):
+        A = osolver.product_compressor_matrix(Lt, c, Rt)
+        x = np.linalg.lstsq(A, b, rcond=None)[0]
+        c = ol.unitize(x.reshape(old, new))
+    ref = np.ascontiguousarray(c.T)
+    out = computeProductCompressor(dd.fromArray(Lt), dd.fromArray(Rt), new, initial=dd.fromArray(init)).toArray()
+    assert relerr(out.conj().T @ out, ref.conj().T @ ref) < 1e-6
+
+
 def test_product_compressor_draws_like_the_reference(dd):
     """Without `initial` the random start comes from the host NumPy stream at the same point (compression.py:35)."""
     from carcassonne_b200.compression import computeProductCompressor
