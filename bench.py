@@ -187,7 +187,9 @@ def run_reference(args, rank, world):
 def workload_config(args, X):
     return {"workload": "TFIM expectation matvec, T=9 terms, D=%d, chi=%d (X=%d), d=2" % (args.D, args.chi, X),
             "D": args.D, "chi": args.chi, "terms": 9, "l2": "inputs (12 x 16*X*D^4 B) larger than L2",
-            "sharding": "X slabs over ranks + allreduce(sum) of the output vector"}
+            "sharding": "X slabs over ranks + one-shot all-reduce of the output vector (%s)" % (
+                "NVLink peer memory, fused into the stage-3 partial-sum kernel" if getattr(args, "reduce", "peer") == "peer"
+                else "NCCL")}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -222,6 +224,12 @@ def run_device(args, rank, world, local_rank):
     for a, b, o in terms:
         op.add_term(A[a], B[b], o)
     op.finalize()
+    comm = None
+    if world > 1 and args.reduce == "peer":
+        from carcassonne_b200 import distributed as cd
+        comm = cd.PeerComm(D ** 4 * d)
+        cd.shard_operator(op, comm)
+    use_nccl = world > 1 and comm is None
     n = D ** 4 * d
     v_host = torch.empty((D, D, D, D, d), dtype=torch.complex128).pin_memory()
     torch.view_as_real(v_host).normal_()
@@ -233,13 +241,13 @@ def run_device(args, rank, world, local_rank):
 
     def step():
         op.apply_raw(v, out)
-        if world > 1:
+        if use_nccl:
             dist.all_reduce(out)
 
     def step_e2e():
         v.copy_(v_host, non_blocking=True)
         op.apply_raw(v, out)
-        if world > 1:
+        if use_nccl:
             dist.all_reduce(out)
         out_host.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -273,7 +281,8 @@ def run_device(args, rank, world, local_rank):
     t1 = time.time()
     clocks = sampler.stop(t0, t1) if rank == 0 else None
 
-    # kernel-only duration of the dominant kernel (fused stage-3 + its partial-sum pass), no collective
+    # duration of the dominant kernel (fused stage-3 + its partial-sum pass; with the peer communicator attached the
+    # partial-sum pass is the cross-GPU one, so at N > 1 this includes the exchange)
     kern_ms = timed(lambda: op.apply_raw(v, out), args.steps) / args.steps
 
     for _ in range(3):
@@ -285,10 +294,15 @@ def run_device(args, rank, world, local_rank):
     ms_per_step = total_ms / args.steps
     value = flops / (ms_per_step * 1e-3) / 1e9
 
+    comm_failed = comm.timed_out() if comm is not None else False
+    if comm is not None:
+        comm.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    if comm_failed:
+        raise SystemExit("peer all-reduce timed out")
 
     tf = C.c_double()
     _lib.check(_lib.lib.carc_dmma_peak(4000, C.byref(tf), None))
@@ -326,7 +340,7 @@ def run_device(args, rank, world, local_rank):
                 "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n,
                 "what": "Stage3Operator applied to a pinned host vector: H2D of v, matvec (+allreduce), D2H of H v; "
                         "the environment stays resident as it does behind the reference's Multiplier closure"},
-        "gpu_launches": 2 * args.steps,
+        "gpu_launches": 2 * args.steps,   # stage3_kernel + (s3_reduce_kernel | xgpu_allreduce_kernel) per step
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
@@ -344,6 +358,7 @@ def main():
     ap.add_argument("--D", type=int, default=8)
     ap.add_argument("--chi", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"], help="N > 1: how partial outputs are summed")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -42,6 +42,13 @@ SIGNATURES = {
     "carc_dotc": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp]),
     "carc_sumsq": (c_int, [c_i64, c_vp, c_vp, c_vp]),
     "carc_count_nonfinite": (c_int, [c_i64, c_vp, c_vp, c_vp]),
+    "carc_comm_create": (c_int, [C.POINTER(c_vp), c_int, c_int, c_i64]),
+    "carc_comm_local_handles": (c_int, [c_vp, c_vp]),
+    "carc_comm_connect": (c_int, [c_vp, c_vp]),
+    "carc_comm_allreduce": (c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "carc_comm_status": (c_int, [c_vp, C.POINTER(c_int)]),
+    "carc_comm_destroy": (c_int, [c_vp]),
+    "carc_operator_set_comm": (c_int, [c_vp, c_vp]),
     "carc_operator_create_dense": (c_int, [C.POINTER(c_vp), c_vp, c_i64]),
     "carc_operator_dimension": (c_i64, [c_vp]),
     "carc_relax": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, C.c_double, c_int, C.c_double, c_int, c_int, c_dp, c_vp]),

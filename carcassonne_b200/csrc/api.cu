@@ -18,6 +18,11 @@ struct carc_operator {
   int64_t workspace_elems = 0;
   int force_path = 0;
   bool finalized = false;
+  carc::Comm* comm = nullptr;   // X-slab sharding: sum the output over ranks inside apply
+};
+
+struct carc_comm {
+  carc::Comm* impl = nullptr;
 };
 
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -194,7 +199,48 @@ int carc_operator_apply(carc_operator* op, const void* v, void* out, void* strea
     return carc::dense_matvec(op->matrix, op->n, op->n, op->n, (const cplx*)v, (cplx*)out, make_double2(1.0, 0.0),
                               make_double2(0.0, 0.0), S(stream));
   return carc::stage3_apply(op->terms.data(), op->terms_dev, (int)op->terms.size(), op->P, op->Q, op->R, op->S, op->d,
-                            (const cplx*)v, (cplx*)out, op->workspace, op->workspace_elems, op->force_path, S(stream));
+                            (const cplx*)v, (cplx*)out, op->workspace, op->workspace_elems, op->force_path, S(stream),
+                            op->comm);
+}
+
+// ---------------------------------------------------------------------------------------------------
+int carc_comm_create(carc_comm** comm, int rank, int world, int64_t max_elems) {
+  CARC_REQUIRE(comm != nullptr, CARC_ERR_VALUE, "comm_create: null handle pointer");
+  carc_comm* c = new carc_comm();
+  int rc = carc::comm_create(&c->impl, rank, world, max_elems);
+  if (rc) {
+    delete c;
+    return rc;
+  }
+  *comm = c;
+  return CARC_OK;
+}
+int carc_comm_local_handles(carc_comm* comm, void* out128) {
+  CARC_REQUIRE(comm, CARC_ERR_VALUE, "comm_local_handles: null communicator");
+  return carc::comm_local_handles(comm->impl, out128);
+}
+int carc_comm_connect(carc_comm* comm, const void* all_handles) {
+  CARC_REQUIRE(comm, CARC_ERR_VALUE, "comm_connect: null communicator");
+  return carc::comm_connect(comm->impl, all_handles);
+}
+int carc_comm_allreduce(carc_comm* comm, void* data, int64_t n, void* stream) {
+  CARC_REQUIRE(comm && data, CARC_ERR_VALUE, "comm_allreduce: null argument");
+  return carc::comm_allreduce(comm->impl, (const cplx*)data, 1, n, (cplx*)data, S(stream));
+}
+int carc_comm_status(carc_comm* comm, int* timed_out) {
+  CARC_REQUIRE(comm, CARC_ERR_VALUE, "comm_status: null communicator");
+  return carc::comm_status(comm->impl, timed_out);
+}
+int carc_comm_destroy(carc_comm* comm) {
+  if (!comm) return CARC_OK;
+  carc::comm_destroy(comm->impl);
+  delete comm;
+  return CARC_OK;
+}
+int carc_operator_set_comm(carc_operator* op, carc_comm* comm) {
+  CARC_REQUIRE(op && op->kind == 0, CARC_ERR_VALUE, "operator_set_comm: needs a stage-3 operator");
+  op->comm = comm ? comm->impl : nullptr;
+  return CARC_OK;
 }
 
 int carc_operator_destroy(carc_operator* op) {

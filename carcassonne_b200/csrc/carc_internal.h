@@ -39,6 +39,15 @@ int zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, cplx alpha, const c
 int index_table(int nlevels, const int64_t* extents, const int64_t* strides, int64_t* table, cudaStream_t stream);
 int dmma_peak(int iters, double* tflops_out, cudaStream_t stream);
 
+// comm.cu
+struct Comm;
+int comm_create(Comm** out, int rank, int world, int64_t max_elems);
+int comm_local_handles(Comm* c, void* out128);
+int comm_connect(Comm* c, const void* all_handles);
+int comm_allreduce(Comm* c, const cplx* src, int slots, int64_t n, cplx* out, cudaStream_t stream);
+int comm_status(Comm* c, int* timed_out);
+int comm_destroy(Comm* c);
+
 // stage3.cu
 struct Stage3Term {
   const cplx* A;   // [X, P, Q]   (pre-joined stage-2 half 0: [(x y), D0*, D1*, D0, D1])
@@ -49,7 +58,7 @@ struct Stage3Term {
 };
 int stage3_apply(const Stage3Term* terms_host, const Stage3Term* terms_dev, int nterms, int P, int Q, int R, int S,
                  int d, const cplx* v, cplx* out, cplx* workspace, int64_t workspace_elems, int force_path,
-                 cudaStream_t stream);
+                 cudaStream_t stream, Comm* comm = nullptr);
 int64_t stage3_workspace_elems(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax);
 
 // linalg.cu

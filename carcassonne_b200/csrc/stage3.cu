@@ -415,20 +415,24 @@ int64_t stage3_workspace_elems(int nterms, int P, int Q, int R, int S, int d, in
 
 int stage3_apply(const Stage3Term* terms_host, const Stage3Term* terms_dev, int nterms, int P, int Q, int R, int S,
                  int d, const cplx* v, cplx* out, cplx* workspace, int64_t workspace_elems, int force_path,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, Comm* comm) {
   CARC_REQUIRE(nterms >= 0 && P > 0 && Q > 0 && R > 0 && S > 0 && d > 0 && d <= 4, CARC_ERR_VALUE,
                "stage3: invalid dimensions");
   const int64_t n = (int64_t)P * R * d;
   if (nterms == 0) {
     CARC_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(cplx) * n, stream));
-    return CARC_OK;
+    return comm ? comm_allreduce(comm, out, 1, n, out, stream) : CARC_OK;
   }
   int64_t Xmax = 0;
   for (int t = 0; t < nterms; ++t) Xmax = std::max(Xmax, terms_host[t].X);
   S3Config k;
   const bool can_fuse = force_path != 2 && Xmax > 0 && s3_configure(nterms, P, Q, R, S, d, Xmax, &k);
   CARC_REQUIRE(!(force_path == 1 && !can_fuse), CARC_ERR_UNSUPPORTED, "stage3: fused path unavailable for this shape");
-  if (!can_fuse) return s3_unfused(terms_host, nterms, P, Q, R, S, d, v, out, workspace, workspace_elems, stream);
+  if (!can_fuse) {
+    int rc = s3_unfused(terms_host, nterms, P, Q, R, S, d, v, out, workspace, workspace_elems, stream);
+    if (rc || !comm) return rc;
+    return comm_allreduce(comm, out, 1, n, out, stream);
+  }
 
   CARC_REQUIRE(workspace_elems >= (int64_t)k.slots * n, CARC_ERR_VALUE, "stage3: workspace too small");
   S3Params p;
@@ -452,6 +456,8 @@ int stage3_apply(const Stage3Term* terms_host, const Stage3Term* terms_dev, int 
     default: rc = s3_launch<8>(p, k, stream); break;
   }
   if (rc) return rc;
+  // multi-GPU: the slot sum and the sum over ranks are one kernel reading the peers' exchange buffers over NVLink
+  if (comm) return comm_allreduce(comm, workspace, k.slots, n, out, stream);
   s3_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(workspace, out, n, k.slots, 0);
   CARC_CHECK_CUDA(cudaGetLastError());
   return CARC_OK;

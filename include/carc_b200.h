@@ -43,6 +43,7 @@ extern "C" {
 #define CARC_OP_J 3 /* conjugated, not transposed    */
 
 typedef struct carc_operator carc_operator; /* device-resident expectation / normalization operator */
+typedef struct carc_comm carc_comm;         /* one-node multi-GPU communicator over NVLink peer memory */
 
 /* ---- library ------------------------------------------------------------------------------------------- */
 int carc_version(void);
@@ -117,6 +118,23 @@ int carc_operator_destroy(carc_operator* op);
 int carc_stage3_matvec_host(int nterms, const void* const* A_host, const void* const* B_host, const int64_t* X,
                             const double* const* O_host, int P, int Q, int R, int S, int d, const void* v_host,
                             void* out_host, void* stream);
+
+/* ---- multi-GPU (no counterpart in the single-process reference) ---------------------------
+ * The matvec shards over the joined environment bond X: each rank adds the X-slab of every term it owns
+ * (carc_operator_add_term with the slab's pointers and extent) and attaches a communicator; carc_operator_apply then
+ * finishes with a one-shot all-reduce of the output vector over NVLink peer memory (the slot-sum pass of stage 3
+ * reads every peer's exchange buffer directly), so every rank returns the full, bit-identical H v.
+ * Set-up: carc_comm_create on every rank (one process per GPU); exchange the 128-byte records of
+ * carc_comm_local_handles between ranks by any host transport (torch.distributed in the Python layer) into a
+ * [world][128] array; carc_comm_connect.  max_elems bounds the vector length.  Collective calls must be issued in the
+ * same order on all ranks.  Waits are bounded; carc_comm_status reports a timed-out exchange. */
+int carc_comm_create(carc_comm** comm, int rank, int world, int64_t max_elems);
+int carc_comm_local_handles(carc_comm* comm, void* out128);
+int carc_comm_connect(carc_comm* comm, const void* all_handles);
+int carc_comm_allreduce(carc_comm* comm, void* data, int64_t n, void* stream); /* in-place sum over ranks */
+int carc_comm_status(carc_comm* comm, int* timed_out);
+int carc_comm_destroy(carc_comm* comm);
+int carc_operator_set_comm(carc_operator* op, carc_comm* comm);
 
 /* A dense operator (the `isCheaperToFormMatrix` branches of relaxOver, utils.py:814-832): matrix [n, n] row-major,
  * not copied. */
