@@ -224,6 +224,7 @@ def run_device(args, rank, world, local_rank):
     for a, b, o in terms:
         op.add_term(A[a], B[b], o)
     op.finalize()
+    A_keep.extend([A, B, op])
     comm = None
     if world > 1 and args.reduce == "peer":
         from carcassonne_b200 import distributed as cd
@@ -306,7 +307,8 @@ def run_device(args, rank, world, local_rank):
 
     tf = C.c_double()
     _lib.check(_lib.lib.carc_dmma_peak(4000, C.byref(tf), None))
-    achieved_tf = flops_local / (kern_ms * 1e-3) / 1e12
+    executed = op.executed_flops                              # DMMA flops the kernel issues (shared-B grouping)
+    achieved_tf = executed / (kern_ms * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -317,6 +319,11 @@ def run_device(args, rank, world, local_rank):
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": tf.value, "unit": "TFLOP/s",
                 "frac": achieved_tf / tf.value, "traffic": traffic,
                 "kernel": "stage3_kernel (fused A.v -> O -> B^T, DMMA.8x8x4)",
+                "executed_flops_per_launch": executed, "reference_flops_per_launch": flops_local,
+                "note": "achieved = FP64 flops the kernel issues / its duration; the kernel sums the first products of "
+                        "terms that share a half-1 tensor before one second product, so it issues %d + %d products "
+                        "per x where the reference performs %d + %d -- `value` counts the reference's flops"
+                        % (len(terms), op.num_groups, len(terms), len(terms)),
                 "peak_source": "DMMA.8x8x4 issue-rate microbenchmark run in this process (carc_dmma_peak); "
                                "MEASURED_PEAKS.json has no FP64 figure",
                 "algorithmic_bytes": 12 * 16 * Xl * D ** 4 + 32 * n,
@@ -329,6 +336,12 @@ def run_device(args, rank, world, local_rank):
         cpu = {"value": g, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "T=9 TFIM terms, D=%d, X slab of %d of %d, %.1f s, oracle.dense.stage3_multiply_joined "
                          "(NumPy tensordot -> BLAS zgemm)" % (D, xs, X, s)}
+
+    sweep = None
+    if world == 1 and not args.no_sweep:
+        op.close()
+        del A, B, op
+        sweep = sweep_section(args.no_cpu)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -343,10 +356,38 @@ def run_device(args, rank, world, local_rank):
         "gpu_launches": 2 * args.steps,   # stage3_kernel + (s3_reduce_kernel | xgpu_allreduce_kernel) per step
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "sweep": sweep,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def sweep_section(no_cpu):
+    """Second half of the BASELINE metric: seconds per sweep iteration vs bond dimension.  One iteration =
+    minimizeExpectation + contractTowards + ConstantStateCompressionPolicy(chi) on a synthetic double-layer TFIM
+    environment (scripts/sweep_bench.py); four iterations (one per direction) per size.  The CPU column is the
+    oracle's restatement of the same calls on the host cores, at the size where it finishes in tens of seconds."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import sweep_bench
+    del A_keep[:]                      # drop the matvec environment (51 GB); torch's allocator reuses the blocks
+    rows = []
+    sweep_bench.device_iterations(2, 2, False)   # warm-up
+    for D, chi in ((3, 6), (4, 8), (6, 8)):
+        r = sweep_bench.device_iterations(chi, D, False)
+        rows.append({"D": D, "chi": chi, "gpu_s_per_iteration": r["per_iteration"], "minimize_s": r["minimize"] / 4,
+                     "contract_s": r["contract"] / 4, "compress_s": r["compress"] / 4,
+                     "matvecs_per_minimize": r["mults"]})
+    out = {"unit": "s per sweep iteration (minimize + contract + 8 corner compressions)", "sizes": rows}
+    if not no_cpu:
+        c = sweep_bench.cpu_iterations(6, 3)
+        out["cpu"] = {"D": 3, "chi": 6, "cpu_s_per_iteration": c["per_iteration"], "kind": "port (oracle.system.System)",
+                      "speedup_at_same_size": c["per_iteration"] / rows[0]["gpu_s_per_iteration"]}
+    return out
+
+
+A_keep = []
 
 
 def main():
@@ -358,6 +399,7 @@ def main():
     ap.add_argument("--D", type=int, default=8)
     ap.add_argument("--chi", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the seconds-per-sweep-iteration section")
     ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"], help="N > 1: how partial outputs are summed")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

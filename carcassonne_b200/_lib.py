@@ -42,6 +42,8 @@ SIGNATURES = {
     "carc_dotc": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp]),
     "carc_sumsq": (c_int, [c_i64, c_vp, c_vp, c_vp]),
     "carc_count_nonfinite": (c_int, [c_i64, c_vp, c_vp, c_vp]),
+    "carc_operator_num_groups": (c_int, [c_vp]),
+    "carc_operator_executed_flops": (C.c_double, [c_vp]),
     "carc_comm_create": (c_int, [C.POINTER(c_vp), c_int, c_int, c_i64]),
     "carc_comm_local_handles": (c_int, [c_vp, c_vp]),
     "carc_comm_connect": (c_int, [c_vp, c_vp]),

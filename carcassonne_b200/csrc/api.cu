@@ -13,7 +13,7 @@ struct carc_operator {
   int64_t n = 0;
   int P, Q, R, S, d;
   std::vector<carc::Stage3Term> terms;
-  carc::Stage3Term* terms_dev = nullptr;
+  carc::Stage3Plan* plan = nullptr;
   cplx* workspace = nullptr;
   int64_t workspace_elems = 0;
   int force_path = 0;
@@ -27,6 +27,20 @@ struct carc_comm {
 
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline cplx C2(const double z[2]) { return make_double2(z[0], z[1]); }
+
+// cudaMallocAsync returns freed memory to the OS at the next synchronisation unless the pool is told to keep it;
+// every solver call allocates its workspace from the pool, so keep it.
+static void keep_pool_memory() {
+  static bool done[16] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev >= 16 || done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long threshold = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+  }
+  done[dev] = true;
+}
 
 extern "C" {
 
@@ -98,6 +112,7 @@ int carc_zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, const double a
   if (k_map) {
     km.a_kdiv = k_map[0]; km.a_ks1 = k_map[1]; km.b_kdiv = k_map[2]; km.b_ks1 = k_map[3];
   }
+  keep_pool_memory();
   return carc::zgemm(opA, opB, M, N, K, C2(alpha), (const cplx*)A, lda, (const cplx*)B, ldb, C2(beta), (cplx*)C,
                      out_map ? &om : nullptr, k_map ? &km : nullptr, batch, strideA, strideB, strideC, S(stream));
 }
@@ -110,6 +125,7 @@ int carc_zgemm_tab(int opA, int opB, int64_t M, int64_t N, int64_t K, const doub
                    const void* B, int64_t ldb, const double beta[2], void* C, const void* rowoff_dev,
                    const void* coloff_dev, int64_t batch, int64_t strideA, int64_t strideB, int64_t strideC,
                    void* stream) {
+  keep_pool_memory();
   return carc::zgemm(opA, opB, M, N, K, C2(alpha), (const cplx*)A, lda, (const cplx*)B, ldb, C2(beta), (cplx*)C, nullptr,
                      nullptr, batch, strideA, strideB, strideC, S(stream), (const int64_t*)rowoff_dev,
                      (const int64_t*)coloff_dev);
@@ -120,6 +136,7 @@ int carc_operator_create(carc_operator** op, int P, int Q, int R, int Sd, int d)
   CARC_REQUIRE(op != nullptr, CARC_ERR_VALUE, "operator_create: null handle pointer");
   CARC_REQUIRE(P > 0 && Q > 0 && R > 0 && Sd > 0 && d > 0 && d <= 4, CARC_ERR_VALUE,
                "operator_create: invalid dimensions P=%d Q=%d R=%d S=%d d=%d", P, Q, R, Sd, d);
+  keep_pool_memory();
   carc_operator* o = new carc_operator();
   o->P = P; o->Q = Q; o->R = R; o->S = Sd; o->d = d;
   o->n = (int64_t)P * R * d;
@@ -149,10 +166,8 @@ int carc_operator_finalize(carc_operator* op) {
   const int nt = (int)op->terms.size();
   int64_t Xmax = 1;
   for (auto& t : op->terms) Xmax = t.X > Xmax ? t.X : Xmax;
-  if (nt > 0) {
-    CARC_CHECK_CUDA(cudaMalloc(&op->terms_dev, sizeof(carc::Stage3Term) * nt));
-    CARC_CHECK_CUDA(cudaMemcpy(op->terms_dev, op->terms.data(), sizeof(carc::Stage3Term) * nt, cudaMemcpyHostToDevice));
-  }
+  int prc = carc::stage3_plan_create(op->terms.data(), nt, &op->plan);
+  if (prc) return prc;
   op->workspace_elems = carc::stage3_workspace_elems(nt, op->P, op->Q, op->R, op->S, op->d, Xmax);
   CARC_CHECK_CUDA(cudaMalloc(&op->workspace, sizeof(cplx) * (op->workspace_elems > 0 ? op->workspace_elems : 1)));
   op->finalized = true;
@@ -181,6 +196,7 @@ int64_t carc_operator_cost_of_multiply(const carc_operator* op) {
 
 int carc_operator_create_dense(carc_operator** op, const void* matrix_dev, int64_t n) {
   CARC_REQUIRE(op != nullptr && matrix_dev != nullptr && n > 0, CARC_ERR_VALUE, "operator_create_dense: invalid argument");
+  keep_pool_memory();
   carc_operator* o = new carc_operator();
   o->kind = 1;
   o->matrix = (const cplx*)matrix_dev;
@@ -193,14 +209,19 @@ int carc_operator_create_dense(carc_operator** op, const void* matrix_dev, int64
 
 int64_t carc_operator_dimension(const carc_operator* op) { return op ? op->n : -1; }
 
+double carc_operator_executed_flops(const carc_operator* op) {
+  if (!op || op->kind != 0 || !op->plan) return -1.0;
+  return carc::stage3_executed_flops(op->plan, op->P, op->Q, op->R, op->S, op->d);
+}
+int carc_operator_num_groups(const carc_operator* op) { return (op && op->plan) ? (int)op->plan->groups.size() : -1; }
+
 int carc_operator_apply(carc_operator* op, const void* v, void* out, void* stream) {
   CARC_REQUIRE(op && op->finalized, CARC_ERR_VALUE, "operator_apply: operator not finalized");
   if (op->kind == 1)
     return carc::dense_matvec(op->matrix, op->n, op->n, op->n, (const cplx*)v, (cplx*)out, make_double2(1.0, 0.0),
                               make_double2(0.0, 0.0), S(stream));
-  return carc::stage3_apply(op->terms.data(), op->terms_dev, (int)op->terms.size(), op->P, op->Q, op->R, op->S, op->d,
-                            (const cplx*)v, (cplx*)out, op->workspace, op->workspace_elems, op->force_path, S(stream),
-                            op->comm);
+  return carc::stage3_apply(op->plan, op->P, op->Q, op->R, op->S, op->d, (const cplx*)v, (cplx*)out, op->workspace,
+                            op->workspace_elems, op->force_path, S(stream), op->comm);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -245,7 +266,7 @@ int carc_operator_set_comm(carc_operator* op, carc_comm* comm) {
 
 int carc_operator_destroy(carc_operator* op) {
   if (!op) return CARC_OK;
-  if (op->terms_dev) cudaFree(op->terms_dev);
+  carc::stage3_plan_destroy(op->plan);
   if (op->workspace) cudaFree(op->workspace);
   delete op;
   return CARC_OK;
@@ -309,6 +330,7 @@ int carc_stage3_matvec_host(int nterms, const void* const* A_host, const void* c
 // ---------------------------------------------------------------------------------------------------
 int carc_lu_factor(void* A, int n, void* piv_dev, int* singular_out, void* stream) {
   CARC_REQUIRE(A && piv_dev && n > 0, CARC_ERR_VALUE, "lu_factor: invalid argument");
+  keep_pool_memory();
   cudaStream_t st = S(stream);
   void* scratch = nullptr;
   CARC_CHECK_CUDA(cudaMallocAsync(&scratch, 64, st));

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <functional>
+#include <vector>
 
 #define CARC_MAX_RANK 12
 
@@ -56,9 +57,22 @@ struct Stage3Term {
   int has_op;      // 0: identity on the physical leg
   cplx op[16];     // row-major d x d site operator O[s', s]
 };
-int stage3_apply(const Stage3Term* terms_host, const Stage3Term* terms_dev, int nterms, int P, int Q, int R, int S,
-                 int d, const cplx* v, cplx* out, cplx* workspace, int64_t workspace_elems, int force_path,
-                 cudaStream_t stream, Comm* comm = nullptr);
+struct Stage3Group {
+  const cplx* B;   // the half-1 tensor every term of the group shares
+  int64_t X;
+  int first, count;   // terms [first, first + count) of the sorted term table
+};
+struct Stage3Plan {
+  std::vector<Stage3Term> terms;     // sorted by group
+  std::vector<Stage3Group> groups;
+  Stage3Term* terms_dev;
+  Stage3Group* groups_dev;
+};
+int stage3_plan_create(const Stage3Term* terms, int nterms, Stage3Plan** out);
+void stage3_plan_destroy(Stage3Plan* plan);
+double stage3_executed_flops(const Stage3Plan* plan, int P, int Q, int R, int S, int d);
+int stage3_apply(const Stage3Plan* plan, int P, int Q, int R, int S, int d, const cplx* v, cplx* out, cplx* workspace,
+                 int64_t workspace_elems, int force_path, cudaStream_t stream, Comm* comm = nullptr);
 int64_t stage3_workspace_elems(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax);
 
 // linalg.cu

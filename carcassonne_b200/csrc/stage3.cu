@@ -18,10 +18,14 @@
 // (cp.async.bulk -> UBLKCP) into a multi-stage ring guarded by mbarriers.  There is no dedicated producer warp:
 // the register file is split per SM sub-partition (16K registers each), so a 9th warp would cap every thread at
 // 170 registers; instead warp 0 of each consumer group runs a second cursor one item ahead and issues the copies.
+// Terms that share the same B tensor (e.g. every term whose half-1 tag is Identity) are grouped: their first
+// products are summed in registers, T = sum_t O_t (A_t,x v), and ONE second product with B_x follows (linearity),
+// which removes a third of the DMMA work of the transverse-Ising operator (9 + 9 -> 9 + 6 products per x).
 // Work decomposition: CTA = (S block of 16 columns, slab of x); inside a CTA, G independent consumer groups of
 // ceil(P/8) warps take interleaved x.  Every (CTA, group) writes one partial result; a second kernel sums the
 // partials in a fixed order, so the result is deterministic.
 #include <algorithm>
+#include <vector>
 
 #include "carc_internal.h"
 #include "common.cuh"
@@ -35,11 +39,12 @@ constexpr int BSTR = SBW + 1;  // row stride of the staged B block (odd -> confl
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct S3Params {
-  const Stage3Term* terms;  // device copy
-  int nterms;
+  const Stage3Term* terms;  // device copy, sorted by group
+  const Stage3Group* groups;
+  int nterms, ngroups;
   int P, Q, R, S;
   int Q8, NPT, G, NSB, NSL, nstA, nstB;
-  uint32_t slotA_bytes, slotB_bytes, ops_off, vt_off, ring_off, smem_total;
+  uint32_t slotA_bytes, slotB_bytes, ops_off, hasop_off, tab_off, vt_off, ring_off, smem_total;
   const cplx* v;
   cplx* partial;
 };
@@ -88,7 +93,24 @@ __global__ void __launch_bounds__(s3_max_threads(NRT), 1) stage3_kernel(const S3
   const int sb = blockIdx.x % p.NSB, sl = blockIdx.x / p.NSB;
   const int S0 = sb * SBW;
   const int SBv = min(SBW, p.S - S0);
+  int* hasop = reinterpret_cast<int*>(smem + p.hasop_off);
+  // small per-launch tables in shared memory: they sit on the critical path of every item
+  const cplx** termA = reinterpret_cast<const cplx**>(smem + p.tab_off);
+  const cplx** groupB = termA + p.nterms;
+  int* groupX = reinterpret_cast<int*>(groupB + p.ngroups);
+  int* groupFirst = groupX + p.ngroups;
+  int* groupCount = groupFirst + p.ngroups;
   for (int i = tid; i < p.nterms * DP * DP; i += blockDim.x) ops[i] = p.terms[i / (DP * DP)].op[i % (DP * DP)];
+  for (int i = tid; i < p.nterms; i += blockDim.x) {
+    hasop[i] = p.terms[i].has_op;
+    termA[i] = p.terms[i].A;
+  }
+  for (int i = tid; i < p.ngroups; i += blockDim.x) {
+    groupB[i] = p.groups[i].B;
+    groupX[i] = (int)p.groups[i].X;
+    groupFirst[i] = p.groups[i].first;
+    groupCount[i] = p.groups[i].count;
+  }
   for (int i = tid; i < p.Q * SBv * DP; i += blockDim.x) {
     const int sp = i % DP, sc = (i / DP) % SBv, q = i / (DP * SBv);
     Vt[(sp * SBW + sc) * QS + q] = p.v[((int64_t)q * p.S + S0 + sc) * DP + sp];
@@ -113,68 +135,149 @@ __global__ void __launch_bounds__(s3_max_threads(NRT), 1) stage3_kernel(const S3
     const uint32_t v_base = smem_u32(Vt) + (uint32_t)((r * QS + 2 * c) * 16);
     const uint32_t b_lane_off = (uint32_t)((r * BSTR + 2 * c) * 16);
 
-    // item cursors: (term, x) pairs of this (CTA slab, group); the producer cursor runs ahead of the consumer
+    // Op cursors.  The work of this (CTA slab, consumer group) is the flattened sequence, over term groups gi and
+    // environment indices x, of [A-op for each term of the group ..., B-op of the group].  The producer cursor
+    // runs ahead of the consumer cursor by as many ops as the two rings have room for.
     struct Cursor {
-      int t;
-      int64_t x, x_hi;
+      int gi, j, x, x_hi;   // group, op within the group (producer only), environment index and its slab end
     };
-    auto next = [&](Cursor& cu) -> bool {
+    auto next_item = [&](Cursor& cu) -> bool {
       cu.x += p.G;
-      while (cu.x >= cu.x_hi) {
-        if (++cu.t >= p.nterms) return false;
-        const int64_t X = p.terms[cu.t].X;
-        cu.x = X * sl / p.NSL + g;
-        cu.x_hi = X * (sl + 1) / p.NSL;
+      while (cu.gi < 0 || cu.x >= cu.x_hi) {
+        if (++cu.gi >= p.ngroups) return false;
+        const int64_t X = groupX[cu.gi];
+        cu.x = (int)(X * sl / p.NSL) + g;
+        cu.x_hi = (int)(X * (sl + 1) / p.NSL);
       }
       return true;
     };
+    auto advance = [&](Cursor& cu) -> bool {   // producer: next op of the flattened sequence
+      if (cu.gi >= 0 && cu.j < groupCount[cu.gi]) {
+        ++cu.j;
+        return true;
+      }
+      cu.j = 0;
+      return next_item(cu);
+    };
     const uint32_t a_bytes = (uint32_t)(p.P * p.Q * 16);
     const uint32_t b_row_bytes = (uint32_t)(SBv * 16);
-    auto issue = [&](const Cursor& cu, uint32_t it) {
-      const cplx* A = p.terms[cu.t].A;
-      const cplx* B = p.terms[cu.t].B;
-      const int sa = it % p.nstA, sbq = it % p.nstB;
-      const uint32_t fullA = b + (2 * sa) * 8, fullB = b + (2 * p.nstA + 2 * sbq) * 8;
+    auto issueA = [&](const Cursor& cu, uint32_t it) {
+      const cplx* A = termA[groupFirst[cu.gi] + cu.j];
+      const int sa = it % p.nstA;
+      const uint32_t fullA = b + (2 * sa) * 8;
       if (lane == 0) {
         mbar_wait(fullA + 8, ((it / p.nstA) & 1) ^ 1);
         mbar_arrive_expect_tx(fullA, a_bytes);
-        bulk_g2s(ring + sa * p.slotA_bytes, A + cu.x * (int64_t)p.P * p.Q, a_bytes, fullA);
+        bulk_g2s(ring + sa * p.slotA_bytes, A + (int64_t)cu.x * p.P * p.Q, a_bytes, fullA);
+      }
+      __syncwarp();
+    };
+    auto issueB = [&](const Cursor& cu, uint32_t it) {
+      const cplx* B = groupB[cu.gi];
+      const int sbq = it % p.nstB;
+      const uint32_t fullB = b + (2 * p.nstA + 2 * sbq) * 8;
+      if (lane == 0) {
         mbar_wait(fullB + 8, ((it / p.nstB) & 1) ^ 1);
         mbar_arrive_expect_tx(fullB, b_row_bytes * p.R);
       }
       __syncwarp();
       const uint32_t dst = ring + p.nstA * p.slotA_bytes + sbq * p.slotB_bytes;
-      const cplx* src = B + (cu.x * p.R) * (int64_t)p.S + S0;
+      const cplx* src = B + ((int64_t)cu.x * p.R) * p.S + S0;
       for (int rr = lane; rr < p.R; rr += 32) bulk_g2s(dst + rr * BSTR * 16, src + (int64_t)rr * p.S, b_row_bytes, fullB);
     };
 
-    Cursor cc = {-1, 0, 0}, pc = {-1, 0, 0};
-    uint32_t issued = 0;
-    bool more = true;
-    if (wg == 0) {
-      for (int k = 0; k < p.nstA - 1 && more; ++k) {
-        more = next(pc);
-        if (more) issue(pc, issued++);
+    Cursor cc = {-1, 0, 0, 0}, pc = {-1, 0, 0, 0};
+    uint32_t issuedA = 0, issuedB = 0, itA = 0, itB = 0;
+    bool more = true, pending = false;
+    auto run_ahead = [&]() {
+      while (more) {
+        if (!pending) {
+          more = advance(pc);
+          pending = more;
+          if (!more) break;
+        }
+        if (pc.j < groupCount[pc.gi]) {
+          if (issuedA - itA >= (uint32_t)p.nstA) break;
+          issueA(pc, issuedA++);
+        } else {
+          if (issuedB - itB >= (uint32_t)p.nstB) break;
+          issueB(pc, issuedB++);
+        }
+        pending = false;
       }
-    }
-    uint32_t it = 0;
-    int cur_t = -1;
-    bool has_op = false;
+    };
 
-    while (next(cc)) {
-      if (wg == 0 && more) {
-        more = next(pc);
-        if (more) issue(pc, issued++);
-      }
-      if (cc.t != cur_t) {
-        cur_t = cc.t;
-        has_op = p.terms[cur_t].has_op != 0;
-      }
+    // consumer: one iteration per (term group, x): the first products of the group's terms accumulate in T, the
+    // second product follows in straight-line code
+    while (next_item(cc)) {
       CTile T[2][DP];
-      // ---- first product: U = A_x v  (8 rows of P, this S block), then T = O U
+      const int first = groupFirst[cc.gi], cnt = groupCount[cc.gi];
       {
-        const int slot = it % p.nstA;
-        mbar_wait(b + (2 * slot) * 8, (it / p.nstA) & 1);
+        // ---- first term of the group: both S chunks accumulate straight into T (8 independent DMMA chains, the A
+        // fragments are loaded once for both chunks), then the site operator is applied in place
+        if (wg == 0) run_ahead();
+        const int term = first;
+        const bool has_op = hasop[term] != 0;
+        const int slot = itA % p.nstA;
+        mbar_wait(b + (2 * slot) * 8, (itA / p.nstA) & 1);
+        const uint32_t a_base = ring + slot * p.slotA_bytes + a_lane_off;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+          for (int s = 0; s < DP; ++s) T[ch][s].zero();
+#pragma unroll 2
+        for (int kp = 0; kp < p.Q8; ++kp) {
+          const cplx x0 = lds_c(a_base + kp * 128 + a_first);
+          const cplx x1 = lds_c(a_base + kp * 128 + a_second);
+          const cplx a0 = eswap ? x1 : x0;
+          const cplx a1 = eswap ? x0 : x1;
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+            for (int s = 0; s < DP; ++s) {
+              const uint32_t va = v_base + (uint32_t)((((s * SBW + ch * 8) * QS) + kp * 8) * 16);
+              const cplx b0 = lds_c(va);
+              const cplx b1 = lds_c(va + 16);
+              cmma(T[ch][s], a0.x, a0.y, -a0.y, b0.x, b0.y);
+              cmma(T[ch][s], a1.x, a1.y, -a1.y, b1.x, b1.y);
+            }
+          }
+        }
+        if (has_op) {
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            CTile U[DP];
+#pragma unroll
+            for (int s = 0; s < DP; ++s) {
+              U[s] = T[ch][s];
+              T[ch][s].zero();
+            }
+#pragma unroll
+            for (int s = 0; s < DP; ++s) {
+#pragma unroll
+              for (int s2 = 0; s2 < DP; ++s2) {
+                const cplx w = ops[term * DP * DP + s * DP + s2];
+                if (w.x != 0.0 || w.y != 0.0) {
+                  T[ch][s].re0 += w.x * U[s2].re0 - w.y * U[s2].im0;
+                  T[ch][s].im0 += w.x * U[s2].im0 + w.y * U[s2].re0;
+                  T[ch][s].re1 += w.x * U[s2].re1 - w.y * U[s2].im1;
+                  T[ch][s].im1 += w.x * U[s2].im1 + w.y * U[s2].re1;
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b + (2 * slot + 1) * 8);
+        ++itA;
+      }
+      for (int j = 1; j < cnt; ++j) {
+        if (wg == 0) run_ahead();
+        // ---- first product of a further term of the group: U = A_x v (8 rows of P, this S block); T (+)= O U
+        const int term = first + j;
+        const bool has_op = hasop[term] != 0;
+        const int slot = itA % p.nstA;
+        mbar_wait(b + (2 * slot) * 8, (itA / p.nstA) & 1);
         const uint32_t a_base = ring + slot * p.slotA_bytes + a_lane_off;
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
@@ -198,14 +301,18 @@ __global__ void __launch_bounds__(s3_max_threads(NRT), 1) stage3_kernel(const S3
           }
           if (!has_op) {
 #pragma unroll
-            for (int s = 0; s < DP; ++s) T[ch][s] = U[s];
+            for (int s = 0; s < DP; ++s) {
+              T[ch][s].re0 += U[s].re0;
+              T[ch][s].im0 += U[s].im0;
+              T[ch][s].re1 += U[s].re1;
+              T[ch][s].im1 += U[s].im1;
+            }
           } else {
 #pragma unroll
             for (int s = 0; s < DP; ++s) {
-              T[ch][s].zero();
 #pragma unroll
               for (int s2 = 0; s2 < DP; ++s2) {
-                const cplx w = ops[cur_t * DP * DP + s * DP + s2];
+                const cplx w = ops[term * DP * DP + s * DP + s2];
                 if (w.x != 0.0 || w.y != 0.0) {
                   T[ch][s].re0 += w.x * U[s2].re0 - w.y * U[s2].im0;
                   T[ch][s].im0 += w.x * U[s2].im0 + w.y * U[s2].re0;
@@ -218,11 +325,13 @@ __global__ void __launch_bounds__(s3_max_threads(NRT), 1) stage3_kernel(const S3
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(b + (2 * slot + 1) * 8);
+        ++itA;
       }
-      // ---- second product: acc += T * B_x^T ; T's C fragments are the A fragments
+      if (wg == 0) run_ahead();
+      // ---- second product of the group: acc += T * B_x^T ; T's C fragments are the A fragments
       {
-        const int slot = it % p.nstB;
-        mbar_wait(b + (2 * p.nstA + 2 * slot) * 8, (it / p.nstB) & 1);
+        const int slot = itB % p.nstB;
+        mbar_wait(b + (2 * p.nstA + 2 * slot) * 8, (itB / p.nstB) & 1);
         const uint32_t b_base = ring + p.nstA * p.slotA_bytes + slot * p.slotB_bytes + b_lane_off;
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
@@ -240,8 +349,8 @@ __global__ void __launch_bounds__(s3_max_threads(NRT), 1) stage3_kernel(const S3
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(b + (2 * p.nstA + 2 * slot + 1) * 8);
+        ++itB;
       }
-      ++it;
     }
     // ---- partial result of this (CTA, group)
     cplx* part = p.partial + ((int64_t)blockIdx.x * p.G + g) * ((int64_t)p.P * p.R * DP);
@@ -287,12 +396,13 @@ __global__ void __launch_bounds__(256) s3_reduce_kernel(const cplx* __restrict__
 
 struct S3Config {
   int NPT, NRT, Q8, NSB, NSL, G, nstA, nstB;
-  uint32_t slotA, slotB, ops_off, vt_off, ring_off, total;
+  uint32_t slotA, slotB, ops_off, hasop_off, tab_off, vt_off, ring_off, total;
   int threads, slots;
 };
 
 bool s3_configure(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, S3Config* cfg) {
   if (d != 2) return false;
+  if (Xmax >= (1ll << 31)) return false;
   if (P > 64 || R > 64 || P < 1 || R < 1) return false;
   S3Config k;
   k.NPT = (P + 7) / 8;
@@ -313,7 +423,9 @@ bool s3_configure(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, S
       for (int nstB = 4; nstB >= nstA; --nstB) {
         const uint32_t bar_bytes = (uint32_t)(((G * 2 * (nstA + nstB) * 8) + 127) / 128 * 128);
         const uint32_t ops_off = bar_bytes;
-        const uint32_t vt_off = (ops_off + obytes + 127) / 128 * 128;
+        const uint32_t hasop_off = ops_off + obytes;
+        const uint32_t tab_off = (hasop_off + (uint32_t)nterms * 4 + 15) / 16 * 16;
+        const uint32_t vt_off = (tab_off + (uint32_t)nterms * 8 + (uint32_t)nterms * 20 + 127) / 128 * 128;
         const uint32_t ring_off = (vt_off + vbytes + 127) / 128 * 128;
         const uint64_t total = (uint64_t)ring_off + (uint64_t)G * ((uint64_t)nstA * k.slotA + (uint64_t)nstB * k.slotB);
         if (total <= SMEM_LIMIT) {
@@ -321,6 +433,8 @@ bool s3_configure(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, S
           k.nstA = nstA;
           k.nstB = nstB;
           k.ops_off = ops_off;
+          k.hasop_off = hasop_off;
+          k.tab_off = tab_off;
           k.vt_off = vt_off;
           k.ring_off = ring_off;
           k.total = (uint32_t)total;
@@ -413,35 +527,96 @@ int64_t stage3_workspace_elems(int nterms, int P, int Q, int R, int S, int d, in
   return std::max(fused, unfused);
 }
 
-int stage3_apply(const Stage3Term* terms_host, const Stage3Term* terms_dev, int nterms, int P, int Q, int R, int S,
-                 int d, const cplx* v, cplx* out, cplx* workspace, int64_t workspace_elems, int force_path,
-                 cudaStream_t stream, Comm* comm) {
-  CARC_REQUIRE(nterms >= 0 && P > 0 && Q > 0 && R > 0 && S > 0 && d > 0 && d <= 4, CARC_ERR_VALUE,
-               "stage3: invalid dimensions");
+// Group the terms by their B tensor (first-appearance order) and upload both tables.
+int stage3_plan_create(const Stage3Term* terms, int nterms, Stage3Plan** out) {
+  Stage3Plan* plan = new Stage3Plan();
+  std::vector<int> group_of(nterms, -1);
+  for (int t = 0; t < nterms; ++t) {
+    int gi = -1;
+    for (int q = 0; q < (int)plan->groups.size(); ++q)
+      if (plan->groups[q].B == terms[t].B && plan->groups[q].X == terms[t].X) gi = q;
+    if (gi < 0) {
+      Stage3Group gr;
+      gr.B = terms[t].B;
+      gr.X = terms[t].X;
+      gr.first = 0;
+      gr.count = 0;
+      plan->groups.push_back(gr);
+      gi = (int)plan->groups.size() - 1;
+    }
+    group_of[t] = gi;
+    ++plan->groups[gi].count;
+  }
+  int first = 0;
+  for (auto& gr : plan->groups) {
+    gr.first = first;
+    first += gr.count;
+  }
+  plan->terms.resize(nterms);
+  std::vector<int> fill(plan->groups.size(), 0);
+  for (int t = 0; t < nterms; ++t) {
+    const int gi = group_of[t];
+    plan->terms[plan->groups[gi].first + fill[gi]++] = terms[t];
+  }
+  plan->terms_dev = nullptr;
+  plan->groups_dev = nullptr;
+  if (nterms > 0) {
+    CARC_CHECK_CUDA(cudaMalloc(&plan->terms_dev, sizeof(Stage3Term) * nterms));
+    CARC_CHECK_CUDA(cudaMemcpy(plan->terms_dev, plan->terms.data(), sizeof(Stage3Term) * nterms, cudaMemcpyHostToDevice));
+    CARC_CHECK_CUDA(cudaMalloc(&plan->groups_dev, sizeof(Stage3Group) * plan->groups.size()));
+    CARC_CHECK_CUDA(cudaMemcpy(plan->groups_dev, plan->groups.data(), sizeof(Stage3Group) * plan->groups.size(),
+                               cudaMemcpyHostToDevice));
+  }
+  *out = plan;
+  return CARC_OK;
+}
+
+void stage3_plan_destroy(Stage3Plan* plan) {
+  if (!plan) return;
+  if (plan->terms_dev) cudaFree(plan->terms_dev);
+  if (plan->groups_dev) cudaFree(plan->groups_dev);
+  delete plan;
+}
+
+// FP64 flops the fused kernel actually issues on the tensor pipe (first products: one per term; second products:
+// one per group), for the roofline; the reference-equivalent count is 8 x cost_of_multiply.
+double stage3_executed_flops(const Stage3Plan* plan, int P, int Q, int R, int S, int d) {
+  double f = 0.0;
+  for (const auto& gr : plan->groups)
+    f += 8.0 * (double)gr.X * ((double)gr.count * P * Q * S * d + (double)P * R * S * d);
+  return f;
+}
+
+int stage3_apply(const Stage3Plan* plan, int P, int Q, int R, int S, int d, const cplx* v, cplx* out, cplx* workspace,
+                 int64_t workspace_elems, int force_path, cudaStream_t stream, Comm* comm) {
+  const int nterms = (int)plan->terms.size();
+  CARC_REQUIRE(P > 0 && Q > 0 && R > 0 && S > 0 && d > 0 && d <= 4, CARC_ERR_VALUE, "stage3: invalid dimensions");
   const int64_t n = (int64_t)P * R * d;
   if (nterms == 0) {
     CARC_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(cplx) * n, stream));
     return comm ? comm_allreduce(comm, out, 1, n, out, stream) : CARC_OK;
   }
   int64_t Xmax = 0;
-  for (int t = 0; t < nterms; ++t) Xmax = std::max(Xmax, terms_host[t].X);
+  for (const auto& t : plan->terms) Xmax = std::max(Xmax, t.X);
   S3Config k;
   const bool can_fuse = force_path != 2 && Xmax > 0 && s3_configure(nterms, P, Q, R, S, d, Xmax, &k);
   CARC_REQUIRE(!(force_path == 1 && !can_fuse), CARC_ERR_UNSUPPORTED, "stage3: fused path unavailable for this shape");
   if (!can_fuse) {
-    int rc = s3_unfused(terms_host, nterms, P, Q, R, S, d, v, out, workspace, workspace_elems, stream);
+    int rc = s3_unfused(plan->terms.data(), nterms, P, Q, R, S, d, v, out, workspace, workspace_elems, stream);
     if (rc || !comm) return rc;
     return comm_allreduce(comm, out, 1, n, out, stream);
   }
 
   CARC_REQUIRE(workspace_elems >= (int64_t)k.slots * n, CARC_ERR_VALUE, "stage3: workspace too small");
   S3Params p;
-  p.terms = terms_dev;
+  p.terms = plan->terms_dev;
+  p.groups = plan->groups_dev;
   p.nterms = nterms;
+  p.ngroups = (int)plan->groups.size();
   p.P = P; p.Q = Q; p.R = R; p.S = S;
   p.Q8 = k.Q8; p.NPT = k.NPT; p.G = k.G; p.NSB = k.NSB; p.NSL = k.NSL; p.nstA = k.nstA; p.nstB = k.nstB;
   p.slotA_bytes = k.slotA; p.slotB_bytes = k.slotB;
-  p.ops_off = k.ops_off; p.vt_off = k.vt_off; p.ring_off = k.ring_off; p.smem_total = k.total;
+  p.ops_off = k.ops_off; p.hasop_off = k.hasop_off; p.tab_off = k.tab_off; p.vt_off = k.vt_off; p.ring_off = k.ring_off; p.smem_total = k.total;
   p.v = v;
   p.partial = workspace;
   int rc;

@@ -70,6 +70,15 @@ class Stage3Operator:
     def cost_of_multiply(self):
         return int(lib.carc_operator_cost_of_multiply(self._handle))
 
+    @property
+    def num_groups(self):
+        return lib.carc_operator_num_groups(self._handle)
+
+    @property
+    def executed_flops(self):
+        """FP64 flops the fused kernel issues per apply (<= 8 * cost_of_multiply thanks to shared-B grouping)."""
+        return float(lib.carc_operator_executed_flops(self._handle))
+
     def apply_raw(self, v_t, out_t):
         """torch buffers in, torch buffer out; asynchronous on the current stream."""
         if not self._finalized:

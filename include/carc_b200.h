@@ -112,6 +112,11 @@ int carc_operator_set_path(carc_operator* op, int force_path);
 int carc_operator_num_terms(const carc_operator* op);
 /* cmac count the reference's CostTracker assigns to one apply (data/cost_tracker.py:17-21) */
 int64_t carc_operator_cost_of_multiply(const carc_operator* op);
+/* After finalize: terms sharing a B tensor are grouped (their first products are summed before ONE second product).
+ * num_groups = distinct B tensors; executed_flops = FP64 flops the fused kernel issues per apply (for the roofline:
+ * 8 X S d (count P Q + P R) per group), <= 8 x cost_of_multiply. */
+int carc_operator_num_groups(const carc_operator* op);
+double carc_operator_executed_flops(const carc_operator* op);
 int carc_operator_destroy(carc_operator* op);
 /* End-to-end convenience with HOST buffers (terms, v and out on the host; copies inside the call):
  * A_host[t], B_host[t] are host pointers to [X[t],P,Q] / [X[t],R,S]; O_host[t] NULL or d*d complex. */

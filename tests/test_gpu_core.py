@@ -180,6 +180,35 @@ def test_stage3_ragged_shapes(dd, dims, d):
     assert relerr(out, ref) < MATVEC_TOL
 
 
+@pytest.mark.parametrize("chi2,D", [(3, 2), (4, 4), (5, 8), (2, 6), (4, 3)])
+@pytest.mark.parametrize("path", [0, 2])
+def test_stage3_shared_tensors(dd, chi2, D, path):
+    """The TFIM term structure of bench.py: 9 terms over 6 + 6 tensors, several sharing the same half-1 tensor (their
+    first products are summed before one second product) and the same half-0 tensor."""
+    from carcassonne_b200.operator import Stage3Operator, prejoin_halves
+    from oracle import dense
+    rng = np.random.default_rng(chi2 * 10 + D)
+    s2_0 = [crand(rng, chi2, chi2, D, D, D, D) for _ in range(6)]
+    s2_1 = [crand(rng, chi2, chi2, D, D, D, D) for _ in range(6)]
+    Z = np.diag([1.0, -1.0]).astype(complex)
+    X = np.array([[0, 1], [1, 0]], dtype=complex)
+    G = crand(rng, 2, 2)
+    terms = [(1, 0, None), (0, 1, None), (0, 0, -Z), (4, 0, X), (5, 0, -0.7 * X), (0, 4, -0.7 * X), (0, 5, G),
+             (3, 2, None), (2, 3, None)]
+    v = crand(rng, D, D, D, D, 2)
+    ref = sum(dense.stage3_multiply(s2_0[a], s2_1[b], v, o) for a, b, o in terms)
+    halves_0 = [dd.fromArray(x).join((0, 1), 4, 5, 2, 3) for x in s2_0]
+    halves_1 = [dd.fromArray(x).join((1, 0), 4, 5, 2, 3) for x in s2_1]
+    op = Stage3Operator(v.shape)
+    for a, b, o in terms:
+        op.add_term(halves_0[a], halves_1[b], o)
+    op.finalize().set_path(path)
+    assert op.num_terms == 9 and op.num_groups == 6
+    assert op.executed_flops < 8 * op.cost_of_multiply
+    out = op(dd.fromArray(v)).toArray()
+    assert relerr(out, ref) < MATVEC_TOL
+
+
 def test_stage3_golden(dd):
     """The reference's own multiplier output (tests/golden/dense_recipes.npz)."""
     from carcassonne_b200.operator import Stage3Operator, prejoin_halves
