@@ -53,11 +53,15 @@ SIGNATURES = {
     "carc_operator_set_comm": (c_int, [c_vp, c_vp]),
     "carc_operator_create_dense": (c_int, [C.POINTER(c_vp), c_vp, c_i64]),
     "carc_operator_dimension": (c_i64, [c_vp]),
-    "carc_relax": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, C.c_double, c_int, C.c_double, c_int, c_int, c_dp, c_vp]),
+    "carc_lu_inverse_blocks_elems": (c_i64, [c_int]),
+    "carc_lu_invert_diagonal_blocks": (c_int, [c_vp, c_int, c_vp, c_vp]),
+    "carc_lu_solve_blocks": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "carc_relax": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, C.c_double, c_int, C.c_double, c_int, c_int, c_dp, c_vp]),
     "carc_gmres": (c_int, [c_vp, c_vp, c_vp, C.c_double, c_int, c_int, C.POINTER(c_int), c_dp, c_vp]),
     "carc_cg": (c_int, [c_vp, c_vp, c_vp, C.c_double, c_int, C.POINTER(c_int), c_dp, c_vp]),
     "carc_lu_factor": (c_int, [c_vp, c_int, c_vp, C.POINTER(c_int), c_vp]),
     "carc_lu_solve": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp]),
+    "carc_zgemm_hermitian": (c_int, [c_int, c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "carc_index_table": (c_int, [c_int, c_i64p, c_i64p, c_vp, c_vp]),
     "carc_zgemm_tab": (c_int, [c_int, c_int, c_i64, c_i64, c_i64, c_dp, c_vp, c_i64, c_vp, c_i64, c_dp, c_vp,
                                c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp]),

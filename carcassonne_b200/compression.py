@@ -17,7 +17,7 @@ import ctypes as C
 
 from . import _lib
 from ._lib import lib, check
-from .data import DeviceData, _empty, _ptr, _stream, gemm, gemm_scatter
+from .data import DeviceData, _empty, _ptr, _stream, gemm, gemm_hermitian, gemm_scatter
 from .utils import LUFactors, SolverDidNotConverge, _DenseOperator
 
 
@@ -100,9 +100,9 @@ class _GramForm:
         self.old = old
         o2 = old * old
         LL0 = _empty((o2, o2))
-        gemm(_lib.OP_C, _lib.OP_N, o2, o2, l, L._t, o2, L._t, o2, LL0)             # sum_l conj(L[l,(ij)]) L[l,(i'j')]
+        gemm_hermitian(_lib.OP_C, _lib.OP_N, o2, l, L._t, o2, L._t, o2, LL0)       # sum_l conj(L[l,(ij)]) L[l,(i'j')]
         RR0 = _empty((o2, o2))
-        gemm(_lib.OP_J, _lib.OP_T, o2, o2, r, R._t, r, R._t, r, RR0)                # sum_r conj(R[(kq),r]) R[(k'q'),r]
+        gemm_hermitian(_lib.OP_J, _lib.OP_T, o2, r, R._t, r, R._t, r, RR0)         # sum_r conj(R[(kq),r]) R[(k'q'),r]
         T = _empty((o2, o2))
         gemm(_lib.OP_N, _lib.OP_T, o2, o2, o2, LL0, o2, RR0, o2, T)                 # T[(ij),(kq)]
         self.LL0 = DeviceData(LL0).split(old, old, old, old)

@@ -117,6 +117,12 @@ int carc_zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, const double a
                      out_map ? &om : nullptr, k_map ? &km : nullptr, batch, strideA, strideB, strideC, S(stream));
 }
 
+int carc_zgemm_hermitian(int opA, int opB, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb,
+                         void* C, void* stream) {
+  keep_pool_memory();
+  return carc::zgemm_hermitian(opA, opB, N, K, (const cplx*)A, lda, (const cplx*)B, ldb, (cplx*)C, S(stream));
+}
+
 int carc_index_table(int nlevels, const int64_t* extents, const int64_t* strides, void* table_dev, void* stream) {
   return carc::index_table(nlevels, extents, strides, (int64_t*)table_dev, S(stream));
 }
@@ -345,6 +351,22 @@ int carc_lu_factor(void* A, int n, void* piv_dev, int* singular_out, void* strea
   return rc;
 }
 
+int64_t carc_lu_inverse_blocks_elems(int n) { return carc::lu_inverse_blocks_elems(n); }
+int carc_lu_invert_diagonal_blocks(const void* LU, int n, void* inv_blocks, void* stream) {
+  CARC_REQUIRE(LU && inv_blocks && n > 0, CARC_ERR_VALUE, "lu_invert_diagonal_blocks: invalid argument");
+  return carc::lu_invert_diagonal_blocks((const cplx*)LU, n, (cplx*)inv_blocks, S(stream));
+}
+int carc_lu_solve_blocks(const void* LU, int n, const void* piv_dev, const void* inv_blocks, void* x, void* stream) {
+  CARC_REQUIRE(LU && piv_dev && inv_blocks && x && n > 0, CARC_ERR_VALUE, "lu_solve_blocks: invalid argument");
+  keep_pool_memory();
+  cudaStream_t st = S(stream);
+  void* tmp = nullptr;
+  CARC_CHECK_CUDA(cudaMallocAsync(&tmp, sizeof(cplx) * (size_t)n, st));
+  int rc = carc::lu_solve_fast((const cplx*)LU, n, (const int*)piv_dev, (const cplx*)inv_blocks, (cplx*)x, (cplx*)tmp, st);
+  cudaFreeAsync(tmp, st);
+  return rc;
+}
+
 int carc_lu_solve(const void* LU, int n, const void* piv_dev, void* x, void* stream) {
   CARC_REQUIRE(LU && piv_dev && x && n > 0, CARC_ERR_VALUE, "lu_solve: invalid argument");
   return carc::lu_solve((const cplx*)LU, n, (const int*)piv_dev, (cplx*)x, S(stream));
@@ -394,9 +416,9 @@ int carc_cg(carc_operator* A, const void* b, void* x, double rtol, int maxiter, 
   return rc;
 }
 
-int carc_relax(carc_operator* H, carc_operator* N_op, const void* N_lu, const void* N_piv, void* v, int max_mults,
-               double tolerance, int krylov_dim, double gmres_rtol, int gmres_restart, int gmres_maxiter,
-               double* info_out, void* stream) {
+int carc_relax(carc_operator* H, carc_operator* N_op, const void* N_lu, const void* N_piv, const void* N_inv_blocks,
+               void* v, int max_mults, double tolerance, int krylov_dim, double gmres_rtol, int gmres_restart,
+               int gmres_maxiter, double* info_out, void* stream) {
   CARC_REQUIRE(H && H->finalized && v, CARC_ERR_VALUE, "relax: invalid argument");
   CARC_REQUIRE(!N_op || N_op->n == H->n, CARC_ERR_DIMENSION_MISMATCH, "relax: H and N act on different spaces");
   cudaStream_t st = S(stream);
@@ -404,8 +426,10 @@ int carc_relax(carc_operator* H, carc_operator* N_op, const void* N_lu, const vo
   const int k = krylov_dim > 0 ? krylov_dim : 3;
   int restart = gmres_restart > 0 ? gmres_restart : 20;
   if (restart > n) restart = (int)n;
-  void *work = nullptr, *state = nullptr, *hv = nullptr, *gwork = nullptr, *gstate = nullptr;
+  keep_pool_memory();
+  void *work = nullptr, *state = nullptr, *hv = nullptr, *gwork = nullptr, *gstate = nullptr, *lutmp = nullptr;
   CARC_CHECK_CUDA(cudaMallocAsync(&work, sizeof(cplx) * (size_t)(2 * k + 2) * n, st));
+  if (N_lu && N_piv && N_inv_blocks) CARC_CHECK_CUDA(cudaMallocAsync(&lutmp, sizeof(cplx) * (size_t)n, st));
   CARC_CHECK_CUDA(cudaMallocAsync(&state, carc::relax_state_bytes(), st));
   const bool use_lu = N_lu != nullptr && N_piv != nullptr;
   const bool use_gmres = !use_lu && N_op != nullptr;
@@ -422,6 +446,9 @@ int carc_relax(carc_operator* H, carc_operator* N_op, const void* N_lu, const vo
     if (use_lu) {
       int rc = carc_operator_apply(H, in, out, (void*)s2);
       if (rc) return rc;
+      if (lutmp)
+        return carc::lu_solve_fast((const cplx*)N_lu, (int)n, (const int*)N_piv, (const cplx*)N_inv_blocks, out,
+                                   (cplx*)lutmp, s2);
       return carc::lu_solve((const cplx*)N_lu, (int)n, (const int*)N_piv, out, s2);
     }
     if (use_gmres) {
@@ -440,6 +467,7 @@ int carc_relax(carc_operator* H, carc_operator* N_op, const void* N_lu, const vo
   int rc = carc::relax(M, (cplx*)v, n, max_mults, tolerance, k, (cplx*)work, state, &info, st);
   cudaFreeAsync(work, st);
   cudaFreeAsync(state, st);
+  if (lutmp) cudaFreeAsync(lutmp, st);
   if (use_gmres) {
     cudaFreeAsync(hv, st);
     cudaFreeAsync(gwork, st);

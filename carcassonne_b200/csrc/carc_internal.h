@@ -37,6 +37,8 @@ int zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, cplx alpha, const c
           int64_t ldb, cplx beta, cplx* C, const GemmOut* out, const GemmKMap* kmap, int64_t batch, int64_t strideA,
           int64_t strideB, int64_t strideC, cudaStream_t stream, const int64_t* rowoff = nullptr,
           const int64_t* coloff = nullptr);
+int zgemm_hermitian(int opA, int opB, int64_t N, int64_t K, const cplx* A, int64_t lda, const cplx* B, int64_t ldb,
+                    cplx* C, cudaStream_t stream);
 int index_table(int nlevels, const int64_t* extents, const int64_t* strides, int64_t* table, cudaStream_t stream);
 int dmma_peak(int iters, double* tflops_out, cudaStream_t stream);
 
@@ -93,6 +95,9 @@ int dense_matvec(const cplx* M, int64_t rows, int64_t cols, int64_t ld, const cp
                  cudaStream_t stream);
 int lu_factor(cplx* A, int n, int* piv, int* singular_dev, cplx* scratch, cudaStream_t stream);
 int lu_solve(const cplx* LU, int n, const int* piv, cplx* x, cudaStream_t stream);
+int lu_invert_diagonal_blocks(const cplx* LU, int n, cplx* inv, cudaStream_t stream);
+int64_t lu_inverse_blocks_elems(int n);
+int lu_solve_fast(const cplx* LU, int n, const int* piv, const cplx* inv, cplx* x, cplx* tmp, cudaStream_t stream);
 int gmres(const LinOp& A, const cplx* b, cplx* x, int64_t n, double rtol, int restart, int maxiter, cplx* work,
           void* state_dev, int* iters_out, double* resid_out, cudaStream_t stream);
 size_t gmres_state_bytes();

@@ -204,6 +204,67 @@ __global__ void __launch_bounds__(256) tri_update_kernel(const cplx* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Fast triangular solves for many right-hand sides in sequence (every Arnoldi multiplication applies N^-1): the
+// SB x SB diagonal blocks of L and U are inverted once after the factorisation, so that each block step of the
+// substitution is one launch -- every CTA forms x_k = inv(T_kk) rhs_k redundantly (a 128 x 128 matvec out of L2) and
+// then updates its share of the remaining right-hand side with one warp per row.
+constexpr int SB = 128;
+
+// inv[blk] = inverse of the diagonal block: blocks [0, nblk) unit-lower (L), [nblk, 2 nblk) upper (U); one thread per
+// column of the inverse
+__global__ void __launch_bounds__(SB) tri_invert_kernel(const cplx* __restrict__ A, int n, int nblk,
+                                                        cplx* __restrict__ inv) {
+  const int blk = blockIdx.x % nblk, upper = blockIdx.x / nblk;
+  const int j0 = blk * SB;
+  const int nb = n - j0 < SB ? n - j0 : SB;
+  cplx* out = inv + (int64_t)blockIdx.x * SB * SB;
+  const int j = threadIdx.x;
+  for (int i = 0; i < SB; ++i) out[i * SB + j] = make_double2(0.0, 0.0);
+  if (j >= nb) return;
+  if (!upper) {
+    for (int i = j; i < nb; ++i) {
+      cplx acc = make_double2(i == j ? 1.0 : 0.0, 0.0);
+      for (int k = j; k < i; ++k) acc = csub(acc, cmul(A[(int64_t)(j0 + i) * n + j0 + k], out[k * SB + j]));
+      out[i * SB + j] = acc;
+    }
+  } else {
+    for (int i = j; i >= 0; --i) {
+      cplx acc = make_double2(i == j ? 1.0 : 0.0, 0.0);
+      for (int k = i + 1; k <= j; ++k) acc = csub(acc, cmul(A[(int64_t)(j0 + i) * n + j0 + k], out[k * SB + j]));
+      out[i * SB + j] = cdiv(acc, A[(int64_t)(j0 + i) * n + j0 + i]);
+    }
+  }
+}
+
+// one block step: solved[j0 ..] = inv_kk rhs[j0 ..]; rhs[r] -= sum_j A[r][j0 + j] solved[j0 + j] for r in [r0, r1)
+__global__ void __launch_bounds__(256) tri_step_kernel(const cplx* __restrict__ A, int n, int j0, int nb,
+                                                       const cplx* __restrict__ inv_kk, cplx* __restrict__ rhs,
+                                                       cplx* __restrict__ solved, int r0, int r1) {
+  __shared__ cplx bk[SB];
+  __shared__ cplx xk[SB];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid < SB) bk[tid] = tid < nb ? rhs[j0 + tid] : make_double2(0.0, 0.0);
+  __syncthreads();
+  for (int i = w; i < nb; i += 8) {
+    cplx acc = make_double2(0.0, 0.0);
+    for (int k = lane; k < nb; k += 32) acc = cadd(acc, cmul(inv_kk[i * SB + k], bk[k]));
+    acc.x = warp_sum(acc.x);
+    acc.y = warp_sum(acc.y);
+    if (lane == 0) xk[i] = acc;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && tid < nb) solved[j0 + tid] = xk[tid];
+  for (int r = r0 + blockIdx.x * 8 + w; r < r1; r += gridDim.x * 8) {
+    const cplx* row = A + (int64_t)r * n + j0;
+    cplx acc = make_double2(0.0, 0.0);
+    for (int k = lane; k < nb; k += 32) acc = cadd(acc, cmul(row[k], xk[k]));
+    acc.x = warp_sum(acc.x);
+    acc.y = warp_sum(acc.y);
+    if (lane == 0) rhs[r] = csub(rhs[r], acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // small dense complex eigenproblem (k <= KMAX), thread 0 only.  Eigenvalues by Hessenberg reduction + shifted QR
 // with deflation; the eigenvector of the selected eigenvalue by inverse iteration.
 __device__ void small_eig_min_real(int k, const cplx* Min /* k x k row-major */, cplx* lambda_out, cplx* vec_out) {
@@ -686,6 +747,36 @@ int lu_solve(const cplx* LU, int n, const int* piv, cplx* x, cudaStream_t stream
     const int nb = n - j0 < NB ? n - j0 : NB;
     tri_block_kernel<<<1, 64, 0, stream>>>(LU, n, j0, nb, 0, x);
     if (j0 > 0) tri_update_kernel<<<(j0 + 7) / 8, 256, 0, stream>>>(LU, n, j0, nb, 0, j0, x);
+  }
+  CARC_CHECK_CUDA(cudaGetLastError());
+  return CARC_OK;
+}
+
+
+int lu_invert_diagonal_blocks(const cplx* LU, int n, cplx* inv, cudaStream_t stream) {
+  const int nblk = (n + SB - 1) / SB;
+  tri_invert_kernel<<<2 * nblk, SB, 0, stream>>>(LU, n, nblk, inv);
+  CARC_CHECK_CUDA(cudaGetLastError());
+  return CARC_OK;
+}
+
+int64_t lu_inverse_blocks_elems(int n) { return 2ll * ((n + SB - 1) / SB) * SB * SB; }
+
+// x <- A^-1 x with the pre-inverted diagonal blocks; tmp: n complex
+int lu_solve_fast(const cplx* LU, int n, const int* piv, const cplx* inv, cplx* x, cplx* tmp, cudaStream_t stream) {
+  const int nblk = (n + SB - 1) / SB;
+  lu_permute_kernel<<<1, 32, 0, stream>>>(x, piv, n);
+  for (int k = 0; k < nblk; ++k) {   // L y = P b : running rhs in x, y into tmp
+    const int j0 = k * SB, nb = n - j0 < SB ? n - j0 : SB, r0 = j0 + nb;
+    int blocks = (n - r0 + 7) / 8;
+    blocks = blocks < 1 ? 1 : (blocks > 74 ? 74 : blocks);   // every CTA re-reads the 256 KB inverse block from L2
+    tri_step_kernel<<<blocks, 256, 0, stream>>>(LU, n, j0, nb, inv + (int64_t)k * SB * SB, x, tmp, r0, n);
+  }
+  for (int k = nblk - 1; k >= 0; --k) {   // U x = y : running rhs in tmp, x into x
+    const int j0 = k * SB, nb = n - j0 < SB ? n - j0 : SB;
+    int blocks = (j0 + 7) / 8;
+    blocks = blocks < 1 ? 1 : (blocks > 74 ? 74 : blocks);
+    tri_step_kernel<<<blocks, 256, 0, stream>>>(LU, n, j0, nb, inv + (int64_t)(nblk + k) * SB * SB, tmp, x, 0, j0);
   }
   CARC_CHECK_CUDA(cudaGetLastError());
   return CARC_OK;

@@ -49,10 +49,10 @@ struct S3Params {
   cplx* partial;
 };
 
-// threads per CTA are a multiple of 128 (one warp per sub-partition): 2 / 3 / 4 warps per sub-partition leave
-// 255 / 170 / 128 registers per thread
+// threads per CTA are a multiple of 128 (one warp per sub-partition): 2 / 3 warps per sub-partition leave
+// 255 / 170 registers per thread (4 warps would leave 128, which spills the accumulator tiles)
 __host__ __device__ constexpr int s3_max_threads(int nrt) {
-  return nrt >= 5 ? 256 : (nrt >= 3 ? 384 : 512);
+  return nrt >= 5 ? 256 : 384;
 }
 
 template <int NRT, int DP>

@@ -41,6 +41,7 @@ struct GemmParams {
   GemmOut out;
   const int64_t* rowoff;      // optional per-row / per-column output offset tables (override `out`)
   const int64_t* coloff;
+  int hermitian;              // 1: C = C^H (M == N): tiles strictly below the diagonal are skipped and mirrored
   unsigned tiles_m;           // number of M tiles (the tile grid is linearised on blockIdx.x)
   int splitk;                 // > 1: blockIdx.z is a K split; raw partial products go to C = workspace[split][M][N]
   int64_t kt_per_split;       // K tiles per split
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) zgemm_kernel(GemmParams p) {
   const int wm = warp >> 1, wn = warp & 1;       // 4 x 2 warps
   const int r = lane >> 2, c = lane & 3;
   const int64_t m0 = (int64_t)(blockIdx.x % p.tiles_m) * BM, n0 = (int64_t)(blockIdx.x / p.tiles_m) * BN;  // 1-D tile grid
+  if (p.hermitian && n0 + BN - 1 < m0) return;   // strictly lower tile: filled by the mirror of its transpose
   const bool split = p.splitk > 1;
   const cplx* A = p.A + (split ? 0 : (int64_t)blockIdx.z * p.strideA);
   const cplx* B = p.B + (split ? 0 : (int64_t)blockIdx.z * p.strideB);
@@ -159,6 +161,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) zgemm_kernel(GemmParams p) {
       for (int h = 0; h < 2; ++h) {
         const int64_t n = n0 + wn * 32 + j * 8 + 2 * c + h;
         if (n >= p.N) continue;
+        if (p.hermitian && n < m) continue;   // written (bit-identically conjugated) by the mirror of (n, m)
         const int64_t off =
             moff + (p.coloff ? p.coloff[n] : (n / p.out.n_div) * p.out.n_s1 + (n % p.out.n_div) * p.out.n_s0);
         const double re = h ? acc[i][j].re1 : acc[i][j].re0;
@@ -172,6 +175,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) zgemm_kernel(GemmParams p) {
           v.y += p.beta.x * o.y + p.beta.y * o.x;
         }
         C[off] = v;
+        if (p.hermitian && m != n) C[n * p.N + m] = make_double2(v.x, -v.y);   // plain row-major only
       }
     }
   }
@@ -254,6 +258,18 @@ int index_table(int nlevels, const int64_t* extents, const int64_t* strides, int
   return CARC_OK;
 }
 
+static thread_local bool g_hermitian = false;
+
+// C = op(A) op(B) known to be Hermitian (Gram matrices): computes the upper triangle's tiles and mirrors them.
+int zgemm_hermitian(int opA, int opB, int64_t N, int64_t K, const cplx* A, int64_t lda, const cplx* B, int64_t ldb,
+                    cplx* C, cudaStream_t stream) {
+  g_hermitian = true;
+  int rc = zgemm(opA, opB, N, N, K, make_double2(1.0, 0.0), A, lda, B, ldb, make_double2(0.0, 0.0), C, nullptr, nullptr, 1,
+                 0, 0, 0, stream);
+  g_hermitian = false;
+  return rc;
+}
+
 int zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, cplx alpha, const cplx* A, int64_t lda, const cplx* B,
           int64_t ldb, cplx beta, cplx* C, const GemmOut* out, const GemmKMap* kmap, int64_t batch, int64_t strideA,
           int64_t strideB, int64_t strideC, cudaStream_t stream, const int64_t* rowoff, const int64_t* coloff) {
@@ -277,6 +293,7 @@ int zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, cplx alpha, const c
   p.b_sign = (opB == OP_C || opB == OP_J) ? 0x80000000u : 0u;
   p.alpha = alpha; p.beta = beta;
   p.rowoff = rowoff; p.coloff = coloff;
+  p.hermitian = 0;
   p.a_kdiv = p.a_ks1 = p.b_kdiv = p.b_ks1 = 0;
   if (kmap) {
     CARC_REQUIRE((!kmap->a_kdiv || p.a_kcontig) && (!kmap->b_kdiv || p.b_kcontig), CARC_ERR_VALUE,
@@ -297,6 +314,8 @@ int zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, cplx alpha, const c
   p.splitk = 1;
   p.kt_per_split = 0;
   const int64_t tiles = gx * gy, KT = (K + BK - 1) / BK;
+  const bool herm = g_hermitian && M == N && !out && !rowoff && !coloff && batch == 1;
+  if (herm && !(tiles <= 74 && KT >= 64)) p.hermitian = 1;   // (small outputs take the split-K path instead)
   if (batch == 1 && tiles <= 74 && KT >= 64) {
     // few output tiles, long K (Gram matrices, formMatrix): split K over the idle SMs
     int64_t splits = std::min<int64_t>(148 * 2 / tiles, KT / 16);

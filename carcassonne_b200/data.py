@@ -57,6 +57,11 @@ def gemm(opA, opB, M, N, K, A, lda, B, ldb, Cbuf, alpha=1.0, beta=0.0, out_map=N
         done += nb
 
 
+def gemm_hermitian(opA, opB, N, K, A, lda, B, ldb, Cbuf):
+    """C[N, N] = op(A) op(B) for a Hermitian product (Gram matrices): upper tiles computed, lower mirrored."""
+    check(lib.carc_zgemm_hermitian(opA, opB, N, K, _ptr(A), lda, _ptr(B), ldb, _ptr(Cbuf), _stream()))
+
+
 _TABLES = {}
 
 

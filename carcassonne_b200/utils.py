@@ -180,8 +180,19 @@ class LUFactors:
         singular = C.c_int(0)
         check(lib.carc_lu_factor(_ptr(self.lu._t), n, C.c_void_p(self.piv.data_ptr()), C.byref(singular), _stream()))
         self.singular = bool(singular.value)
+        self.inv_blocks = torch.empty(int(lib.carc_lu_inverse_blocks_elems(n)), dtype=torch.complex128, device="cuda")
+        check(lib.carc_lu_invert_diagonal_blocks(_ptr(self.lu._t), n, C.c_void_p(self.inv_blocks.data_ptr()), _stream()))
 
     def solve(self, b):
+        from ._lib import lib, check
+        from .data import _ptr, _stream
+        x = b.copy()
+        check(lib.carc_lu_solve_blocks(_ptr(self.lu._t), self.n, C.c_void_p(self.piv.data_ptr()),
+                                       C.c_void_p(self.inv_blocks.data_ptr()), _ptr(x._t), _stream()))
+        return x
+
+    def solve_reference(self, b):
+        """Plain blocked substitution (carc_lu_solve), kept as the cross-check of the fast path."""
         from ._lib import lib, check
         from .data import _ptr, _stream
         x = b.copy()
@@ -230,7 +241,8 @@ def relaxOver(initial, expectation_multiplier, normalization_multiplier=None, ma
     v = initial.copy()
     info = (C.c_double * 9)()
     rc = lib.carc_relax(h_handle, n_handle, _ptr(lu.lu._t) if lu else None,
-                        C.c_void_p(lu.piv.data_ptr()) if lu else None, _ptr(v._t),
+                        C.c_void_p(lu.piv.data_ptr()) if lu else None,
+                        C.c_void_p(lu.inv_blocks.data_ptr()) if lu else None, _ptr(v._t),
                         int(maximum_number_of_multiplications or 0), float(tolerance), k, float(gmres_rtol), 20, 0,
                         info, _stream())
     if statistics is not None:

@@ -87,6 +87,11 @@ int carc_zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, const double a
                const void* B, int64_t ldb, const double beta[2], void* C, const int64_t* out_map, const int64_t* k_map,
                int64_t batch, int64_t strideA, int64_t strideB, int64_t strideC, void* stream);
 
+/* C[N,N] = op(A) op(B) for a product known to be Hermitian (the Gram matrices L^H L and R R^H of the state
+ * compression, compression.py:26-45): only the tiles on or above the diagonal are computed, the rest is mirrored. */
+int carc_zgemm_hermitian(int opA, int opB, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb,
+                         void* C, void* stream);
+
 /* Same product with arbitrary output scatter: element (m, n) goes to C[rowoff[m] + coloff[n]] (device int64 tables,
  * either may be NULL = plain row-major factor).  This is how the dense recipes (tensors/_2d/dense.py:11-112) write
  * their GEMM result straight into the layout their final `join` asks for -- up to 12 interleaved axes -- without the
@@ -152,7 +157,8 @@ int64_t carc_operator_dimension(const carc_operator* op);
  * (n = carc_operator_dimension(H) complex numbers) is normalised in place, as the reference does with the caller's
  * array (utils.py:808-809), and holds the result on return.  N^-1 is applied by
  *   - N_lu / N_piv != NULL : the LU factors of the dense normalization matrix from carc_lu_factor
- *                            (scipy.linalg.lu_factor / lu_solve, utils.py:816-818);
+ *                            (scipy.linalg.lu_factor / lu_solve, utils.py:816-818); N_inv_blocks (optional, from
+ *                            carc_lu_invert_diagonal_blocks) selects the one-launch-per-block substitution;
  *   - else N_op != NULL    : GMRES(gmres_restart) on the operator to relative residual gmres_rtol
  *                            (scipy.sparse.linalg.gmres defaults 20 / 1e-5, utils.py:819-825); failure to converge
  *                            returns CARC_ERR_NO_CONVERGENCE (the reference's `assert info == 0`);
@@ -162,9 +168,9 @@ int64_t carc_operator_dimension(const carc_operator* op);
  * CARC_ERR_RELAX_FAILED under the reference's RelaxFailed condition (utils.py:871).
  * info_out (9 doubles, host): initial <v,Mv> (re, im), final (re, im), last Ritz value (re, im), multiplications
  * counted, operator applications performed, GMRES inner iterations. */
-int carc_relax(carc_operator* H, carc_operator* N_op, const void* N_lu, const void* N_piv, void* v, int max_mults,
-               double tolerance, int krylov_dim, double gmres_rtol, int gmres_restart, int gmres_maxiter,
-               double* info_out, void* stream);
+int carc_relax(carc_operator* H, carc_operator* N_op, const void* N_lu, const void* N_piv, const void* N_inv_blocks,
+               void* v, int max_mults, double tolerance, int krylov_dim, double gmres_rtol, int gmres_restart,
+               int gmres_maxiter, double* info_out, void* stream);
 /* x = A^-1 b by restarted GMRES from x0 = 0 (scipy.sparse.linalg.gmres call sites utils.py:823, compression.py:39). */
 int carc_gmres(carc_operator* A, const void* b, void* x, double rtol, int restart, int maxiter, int* iterations_out,
                double* residual_out, void* stream);
@@ -178,6 +184,12 @@ int carc_cg(carc_operator* A, const void* b, void* x, double rtol, int maxiter, 
  * device.  Synchronises to report *singular_out (1 if a zero pivot was met).  carc_lu_solve overwrites x with A^-1 x. */
 int carc_lu_factor(void* A, int n, void* piv_dev, int* singular_out, void* stream);
 int carc_lu_solve(const void* LU, int n, const void* piv_dev, void* x, void* stream);
+/* The same solve for many right-hand sides in sequence (one per Arnoldi multiplication): invert the 128 x 128 diagonal
+ * blocks of L and U once into inv_blocks (carc_lu_inverse_blocks_elems(n) complex numbers), after which every block
+ * step of the substitution is a single launch. */
+int64_t carc_lu_inverse_blocks_elems(int n);
+int carc_lu_invert_diagonal_blocks(const void* LU, int n, void* inv_blocks, void* stream);
+int carc_lu_solve_blocks(const void* LU, int n, const void* piv_dev, const void* inv_blocks, void* x, void* stream);
 
 /* ---- small factorisations: scipy.linalg.qr / svd call sites of NDArrayData.qr, svd, unitize, normalizeAxis
  * (data/__init__.py:43-50, 263-301, 344-346; utils.py:879-881).

@@ -69,6 +69,28 @@ def test_zgemm(dd, M, N, K, opA, opB):
     assert _lib.lib.carc_version() >= 100
 
 
+@pytest.mark.parametrize("n,k", [(5, 7), (64, 100), (200, 33), (300, 1000), (130, 5000)])
+def test_zgemm_hermitian(dd, n, k):
+    """Gram matrices: only the upper tiles are computed, the lower triangle is their exact conjugate mirror."""
+    import torch
+    from carcassonne_b200 import _lib
+    from carcassonne_b200.data import gemm_hermitian
+    rng = np.random.default_rng(n + k)
+    a = crand(rng, k, n)
+    A = torch.from_numpy(a).cuda()
+    G = torch.empty(n, n, dtype=torch.complex128, device="cuda")
+    gemm_hermitian(_lib.OP_C, _lib.OP_N, n, k, A, n, A, n, G)           # a^H a
+    g = G.cpu().numpy()
+    assert relerr(g, a.conj().T @ a) < 1e-13
+    off = ~np.eye(n, dtype=bool)
+    assert np.array_equal(g[off], g.conj().T[off])      # the lower triangle is the exact mirror
+    assert np.max(np.abs(np.diag(g).imag)) < 1e-13 * np.max(np.abs(g))
+    r = crand(rng, n, k)
+    R = torch.from_numpy(r).cuda()
+    gemm_hermitian(_lib.OP_J, _lib.OP_T, n, k, R, k, R, k, G)           # conj(r) r^T
+    assert relerr(G.cpu().numpy(), r.conj() @ r.T) < 1e-13
+
+
 def test_zgemm_output_map_and_kmap(dd):
     import torch
     from carcassonne_b200 import _lib

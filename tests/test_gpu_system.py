@@ -279,7 +279,7 @@ def test_relax_over_decreases_and_converges(dd, n):
     assert np.vdot(res, h @ res).real < (np.vdot(v0, h @ v0) / np.vdot(v0, v0)).real
 
 
-@pytest.mark.parametrize("n", [1, 5, 64, 65, 200, 513])
+@pytest.mark.parametrize("n", [1, 5, 64, 65, 128, 129, 200, 513])
 def test_lu_and_gmres(dd, n):
     import ctypes as C
     from carcassonne_b200.compression import _gmres_dense
@@ -291,6 +291,7 @@ def test_lu_and_gmres(dd, n):
     assert not lu.singular
     x = lu.solve(dd.fromArray(b)).toArray()
     assert relerr(a @ x, b) < 1e-10
+    assert relerr(lu.solve_reference(dd.fromArray(b)).toArray(), x) < 1e-10
     import scipy.linalg as sla
     ref_lu, ref_piv = sla.lu_factor(a)
     assert np.array_equal(lu.piv.cpu().numpy(), ref_piv)
