@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(256) tri_update_kernel(const cplx* __restrict_
 // SB x SB diagonal blocks of L and U are inverted once after the factorisation, so that each block step of the
 // substitution is one launch -- every CTA forms x_k = inv(T_kk) rhs_k redundantly (a 128 x 128 matvec out of L2) and
 // then updates its share of the remaining right-hand side with one warp per row.
-constexpr int SB = 128;
+constexpr int SB = 64;
 
 // inv[blk] = inverse of the diagonal block: blocks [0, nblk) unit-lower (L), [nblk, 2 nblk) upper (U); one thread per
 // column of the inverse
@@ -262,6 +262,92 @@ __global__ void __launch_bounds__(256) tri_step_kernel(const cplx* __restrict__ 
     acc.y = warp_sum(acc.y);
     if (lane == 0) rhs[r] = csub(rhs[r], acc);
   }
+}
+
+// Wavefront substitution: ONE launch per triangular factor.  CTA c owns row block k (k = c for L, nblk-1-c for U),
+// folds the solved blocks x_j into its right-hand side as soon as their flags appear (in dependency order), then
+// publishes x_k.  The SB x SB matrix block of the next step is prefetched into shared memory BEFORE its flag is
+// awaited and the inverse diagonal block sits in shared memory from the start, so what remains on the critical path
+// of a step is a 64-element read, two small shared-memory products and the flag hand-off.  All CTAs are co-resident
+// (nblk <= 148 => n <= 9472); waits are bounded and raise a sticky error flag instead of hanging.
+__global__ void __launch_bounds__(256) tri_wavefront_kernel(const cplx* __restrict__ A, int n, int nblk,
+                                                            const cplx* __restrict__ inv, cplx* __restrict__ x,
+                                                            unsigned long long* __restrict__ flags,
+                                                            unsigned long long epoch, int upper) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* invk = reinterpret_cast<cplx*>(smem_raw);   // [SB][SB + 1]
+  cplx* blk = invk + SB * (SB + 1);                 // [SB][SB + 1]
+  __shared__ cplx acc[SB];
+  __shared__ cplx xj[SB];
+  __shared__ int failed;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int k = upper ? nblk - 1 - (int)blockIdx.x : (int)blockIdx.x;
+  const int j0 = k * SB;
+  const int nb = n - j0 < SB ? n - j0 : SB;
+  unsigned long long* fl = flags + (upper ? nblk : 0);
+  const cplx* inv_kk = inv + (int64_t)((upper ? nblk : 0) + k) * SB * SB;
+  for (int e = tid; e < SB * SB; e += 256) invk[(e / SB) * (SB + 1) + e % SB] = inv_kk[e];
+  if (tid < SB) acc[tid] = tid < nb ? x[j0 + tid] : make_double2(0.0, 0.0);
+  if (tid == 0) failed = 0;
+  __syncthreads();
+  const int nsteps = upper ? nblk - 1 - k : k;
+  for (int sidx = 0; sidx < nsteps; ++sidx) {
+    const int j = upper ? nblk - 1 - sidx : sidx;
+    const int c0 = j * SB;
+    const int ncol = n - c0 < SB ? n - c0 : SB;
+    // prefetch A[block k, block j] (does not depend on x_j)
+    for (int e = tid; e < SB * SB; e += 256) {
+      const int r = e / SB, c = e % SB;
+      blk[r * (SB + 1) + c] = (r < nb && c < ncol) ? A[(int64_t)(j0 + r) * n + c0 + c] : make_double2(0.0, 0.0);
+    }
+    if (tid == 0) {
+      const long long t0 = clock64();
+      while (*((volatile unsigned long long*)(fl + j)) != epoch) {
+        if (clock64() - t0 > 4000000000ll) {
+          failed = 1;
+          break;
+        }
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    if (failed) break;
+    if (tid < SB) xj[tid] = tid < ncol ? __ldcg(x + c0 + tid) : make_double2(0.0, 0.0);
+    __syncthreads();
+    // acc[r] -= sum_c blk[r][c] xj[c]: four threads per row
+    {
+      const int r = tid >> 2, q = tid & 3;
+      cplx s2 = make_double2(0.0, 0.0);
+#pragma unroll 4
+      for (int c = q; c < SB; c += 4) s2 = cadd(s2, cmul(blk[r * (SB + 1) + c], xj[c]));
+      s2.x += __shfl_xor_sync(0xffffffffu, s2.x, 1);
+      s2.y += __shfl_xor_sync(0xffffffffu, s2.y, 1);
+      s2.x += __shfl_xor_sync(0xffffffffu, s2.x, 2);
+      s2.y += __shfl_xor_sync(0xffffffffu, s2.y, 2);
+      if (q == 0) acc[r] = csub(acc[r], s2);
+    }
+    __syncthreads();
+  }
+  if (failed) {
+    if (tid == 0) flags[2 * nblk] = 1ull;
+    return;
+  }
+  {
+    const int r = tid >> 2, q = tid & 3;
+    cplx s2 = make_double2(0.0, 0.0);
+#pragma unroll 4
+    for (int c = q; c < SB; c += 4) s2 = cadd(s2, cmul(invk[r * (SB + 1) + c], acc[c]));
+    s2.x += __shfl_xor_sync(0xffffffffu, s2.x, 1);
+    s2.y += __shfl_xor_sync(0xffffffffu, s2.y, 1);
+    s2.x += __shfl_xor_sync(0xffffffffu, s2.x, 2);
+    s2.y += __shfl_xor_sync(0xffffffffu, s2.y, 2);
+    if (q == 0 && r < nb) x[j0 + r] = s2;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) *((volatile unsigned long long*)(fl + k)) = epoch;
+  (void)lane;
+  (void)w;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -756,16 +842,38 @@ int lu_solve(const cplx* LU, int n, const int* piv, cplx* x, cudaStream_t stream
 int lu_invert_diagonal_blocks(const cplx* LU, int n, cplx* inv, cudaStream_t stream) {
   const int nblk = (n + SB - 1) / SB;
   tri_invert_kernel<<<2 * nblk, SB, 0, stream>>>(LU, n, nblk, inv);
+  CARC_CHECK_CUDA(cudaMemsetAsync(inv + 2ll * nblk * SB * SB, 0, sizeof(cplx) * (2 * nblk + 2), stream));
   CARC_CHECK_CUDA(cudaGetLastError());
   return CARC_OK;
 }
 
-int64_t lu_inverse_blocks_elems(int n) { return 2ll * ((n + SB - 1) / SB) * SB * SB; }
+// inverse blocks followed by 2 nblk + 1 flag words (as complex slots: 16 bytes each, more than enough)
+int64_t lu_inverse_blocks_elems(int n) {
+  const int64_t nblk = (n + SB - 1) / SB;
+  return 2 * nblk * SB * SB + 2 * nblk + 2;
+}
 
 // x <- A^-1 x with the pre-inverted diagonal blocks; tmp: n complex
 int lu_solve_fast(const cplx* LU, int n, const int* piv, const cplx* inv, cplx* x, cplx* tmp, cudaStream_t stream) {
   const int nblk = (n + SB - 1) / SB;
   lu_permute_kernel<<<1, 32, 0, stream>>>(x, piv, n);
+  if (nblk <= 148) {
+    static unsigned long long epoch_counter = 0;
+    unsigned long long* flags = reinterpret_cast<unsigned long long*>(const_cast<cplx*>(inv) + 2ll * nblk * SB * SB);
+    const unsigned long long epoch = ++epoch_counter;
+    const size_t smem = sizeof(cplx) * 2 * SB * (SB + 1);
+    static bool configured[16] = {false};
+    int dev = 0;
+    CARC_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 16 && !configured[dev]) {
+      CARC_CHECK_CUDA(cudaFuncSetAttribute(tri_wavefront_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured[dev] = true;
+    }
+    tri_wavefront_kernel<<<nblk, 256, smem, stream>>>(LU, n, nblk, inv, x, flags, epoch, 0);
+    tri_wavefront_kernel<<<nblk, 256, smem, stream>>>(LU, n, nblk, inv, x, flags, epoch, 1);
+    CARC_CHECK_CUDA(cudaGetLastError());
+    return CARC_OK;
+  }
   for (int k = 0; k < nblk; ++k) {   // L y = P b : running rhs in x, y into tmp
     const int j0 = k * SB, nb = n - j0 < SB ? n - j0 : SB, r0 = j0 + nb;
     int blocks = (n - r0 + 7) / 8;

@@ -104,8 +104,10 @@ class ConstantOperatorCompressionPolicy(CompressionPolicy):
     def apply(self):
         for corner_id in range(4):
             for direction in range(2):
-                self.system.compressCornerTwoSiteOperatorTowards(corner_id, direction, self.new_dimension,
-                                                                 self.normalize)
+                old_dimension = self.system.twoSiteOperatorBondDimension(corner_id, direction)
+                if old_dimension:
+                    self.system.compressCornerTwoSiteOperatorTowards(
+                        corner_id, direction, min(self.new_dimension, old_dimension), self.normalize)
 
 
 # -- contraction ----------------------------------------------------------------------------------------------------

@@ -344,6 +344,17 @@ class System(BaseSystem):
         return compressor
 
     # -- operator-bond compression (reference system/_2d.py:229-363) -------------------------------------------------------
+    def twoSiteOperatorBondDimension(self, corner_id, direction):
+        """Number of two-site halves (plus the extent of an existing compressed bond) a corner carries in one
+        direction: the `old_dimension` of compressCornerTwoSiteOperatorTowards."""
+        total = 0
+        for tag, data in self.corners[corner_id].items():
+            if isinstance(tag, TwoSiteOperator) and tag.direction == direction:
+                total += 1
+            elif isinstance(tag, TwoSiteOperatorCompressed) and tag.direction == direction:
+                total += data.shape[3 * direction + 2]
+        return total
+
     def compressCornerTwoSiteOperatorTowards(self, corner_id, direction, new_dimension, normalize=False):
         """Fold every ``TwoSiteOperator`` half of one direction on a corner (and the matching halves on the adjacent
         side) into one ``TwoSiteOperatorCompressed`` tensor with an operator bond of ``new_dimension``, keeping the

@@ -553,6 +553,79 @@ def test_increase_bandwidth_uses_host_rng_like_reference(dd):
     assert relerr(a.toArray(), q) < 1e-12
 
 
+# -- gauge normalisation of the environment (reference tests/test_system.py:276-305) --------------------------------
+def _psd_system(dd, chi=2, D=2, seed=5):
+    from carcassonne_b200 import synthetic
+    s = synthetic.device_system(chi, D, seed=seed)
+    for d in range(4):
+        s.contractTowards(d)
+    return s
+
+
+@pytest.mark.parametrize("which", ["center0", "center3", "corner00", "corner21", "side1", "all"])
+def test_normalize_family_preserves_expectation(dd, which):
+    s = _psd_system(dd)
+    e0, n0 = s.computeExpectationAndNormalization()
+    if which.startswith("center"):
+        s.normalizeCenterAndDenormalizeSide(int(which[-1]))
+    elif which.startswith("corner"):
+        s.normalizeCornerAndDenormalizeSide(int(which[-2]), int(which[-1]))
+    elif which.startswith("side"):
+        s.normalizeSideAndDenormalizeCenter(int(which[-1]))
+    else:
+        s.normalize()
+    s.assertNormalizationIsHermitian()
+    e1, n1 = s.computeExpectationAndNormalization()
+    assert abs(e1 - e0) < 1e-9 * abs(e0)
+    assert abs(n1 - n0) < 1e-9 * abs(n0)
+
+
+def test_one_site_expectation_matches_oracle(dd):
+    """computeOneSiteExpectation / computeEstimatedOneSiteExpectation / computeCenterSiteExpectation against the
+    oracle's restatement on the same synthetic system."""
+    from carcassonne_b200 import synthetic
+    from oracle import tags
+    from oracle.system import System as OSystem
+    chi, D = 2, 2
+    corners, sides, center = synthetic.double_layer_environment(chi, D, 2, 2, 3)
+    Os, UDs, LRs = synthetic.tfim_operator_arrays(0.7)
+    o = OSystem([{tags.I: c} for c in corners], [{tags.I: x} for x in sides], center,
+                tags.make_sparse_operator(Os, UDs, LRs))
+    s = synthetic.device_system(chi, D, J=0.7, seed=3)
+    for d in (0, 1, 2, 3, 1):
+        o.contract_towards(d)
+        s.contractTowards(d)
+    assert abs(s.computeExpectation() - o.expectation()) < 1e-10 * abs(o.expectation())
+    assert abs(s.computeOneSiteExpectation() - o.one_site_expectation()) < 1e-9 * abs(o.one_site_expectation())
+    est = o.estimated_one_site_expectation(1)
+    assert abs(s.computeEstimatedOneSiteExpectation(1) - est) < 1e-8 * max(1.0, abs(est))
+    assert np.isfinite(s.computeCenterSiteExpectation())
+
+
+def test_operator_compression_policy_run(dd):
+    """The run loop with every policy slot filled, including the operator-compression slot the reference leaves
+    empty: energies stay finite and the two-site halves are folded into compressed bonds."""
+    from carcassonne_b200 import policies as pol
+    from carcassonne_b200.sparse import TwoSiteOperator, TwoSiteOperatorCompressed
+    from carcassonne_b200.system import System
+    np.random.seed(2)
+    system = System.newTrivialWithSimpleSparseOperator(O=-dd.Z, OO_LR=[dd.X, -0.3 * dd.X], OO_UD=[dd.X, -0.3 * dd.X])
+    calls = []
+    system.setPolicy("state compression", pol.ConstantStateCompressionPolicy(2))
+    system.setPolicy("operator compression", pol.ConstantOperatorCompressionPolicy(2))
+    system.setPolicy("post-optimization hook", pol.HookPolicy(lambda sys_: calls.append(sys_.number_of_iterations)))
+    system.setPolicy("contraction", pol.RepeatPatternContractionPolicy(range(4)))
+    for _ in range(4):
+        system._applyPolicy("contraction")
+        system._applyPolicy("state compression")
+        system._applyPolicy("operator compression")
+    tags_seen = {type(t) for c in system.corners for t in c}
+    assert TwoSiteOperatorCompressed in tags_seen and TwoSiteOperator not in tags_seen
+    system.minimizeExpectation()
+    e = system.computeExpectation()
+    assert np.isfinite(e) and abs(e.imag) < 1e-8 * abs(e)
+
+
 # -- end-to-end runs (reference tests/test_simulator_2d_in_1d.py, test_simulator_2d_in_15d.py) -------------------------
 def _tfim_run(dd, direction):
     from carcassonne_b200 import policies as pol
