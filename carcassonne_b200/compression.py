@@ -86,13 +86,16 @@ def _solve_normal_equations(gram, rhs, regularization):
 
 class _GramForm:
     """Normal equations of the ALS without ever forming A (A is (l r) x (old new), 137 GB
-    at chi = D = 8).  With LL0 = L^H L and RR0 = R R^H over the outer legs (computed ONCE per compression, two
-    well-shaped DMMA GEMMs with K = l and K = r) and T = LL0 . RR0^T,
+    at chi = D = 8).  With LL0 = L^H L and RR0 = R R^H over the outer legs (computed ONCE per compression: two
+    Hermitian DMMA GEMMs with K = l and K = r) and T = LL0 . RR0^T,
 
-        A^H A [(i n),(i' n')] = sum_{q q'} LLp[i,q,i',q'] RRc[n,q,n',q'],   LLp = Pc^H LL0 Pc,  RRc = c^T RR0 conj(c)
-        A^H b [(i n)]         = sum_{j q k} conj(Pc[j,q]) c[k,n] T[i,j,k,q],   Pc = conj(c) c^T
+        A^H A [(i n),(i' n')] = sum_{j j'} LL0[i,j,i',j'] W[j,j',n,n'],   W = sum_{q q'} conj(Pc[j,q]) Pc[j',q'] RRc[n,q,n',q']
+        A^H b [(i n)]         = sum_{j q k} conj(Pc[j,q]) c[k,n] T[i,j,k,q]
+        RRc = c^T RR0 conj(c),   Pc = conj(c) c^T
 
-    so every ALS round costs O(old^5) instead of O(l r old^2 new^2).  Operator bond 1 only (Identity tensors)."""
+    so an ALS round touches only old^4-sized objects through a handful of small GEMMs (the big factor LL0 enters one
+    (old^2 x old^2) x (old^2 x new^2) product) instead of O(l r old^2 new^2) work.  Operator bond 1 (Identity
+    tensors) only."""
 
     def __init__(self, L, R):
         l, old, _, _ = L.shape
@@ -105,7 +108,8 @@ class _GramForm:
         gemm_hermitian(_lib.OP_J, _lib.OP_T, o2, r, R._t, r, R._t, r, RR0)         # sum_r conj(R[(kq),r]) R[(k'q'),r]
         T = _empty((o2, o2))
         gemm(_lib.OP_N, _lib.OP_T, o2, o2, o2, LL0, o2, RR0, o2, T)                 # T[(ij),(kq)]
-        self.LL0 = DeviceData(LL0).split(old, old, old, old)
+        # LL0 regrouped once to [(i i'), (j j')] so that every round is a single GEMM against W
+        self.LLg = DeviceData(LL0).split(old, old, old, old).join((0, 2), (1, 3))
         self.RR0 = DeviceData(RR0).split(old, old, old, old)
         self.T = DeviceData(T).split(old, old, old, old)
 
@@ -114,9 +118,11 @@ class _GramForm:
         Pc = _empty((old, old))
         gemm(_lib.OP_J, _lib.OP_T, old, old, new, c._t, new, c._t, new, Pc)
         Pc = DeviceData(Pc)
-        LLp = self.LL0.absorbMatrixAt(1, Pc.adjoint()).absorbMatrixAt(3, Pc.transpose())       # [i, q, i', q']
         RRc = self.RR0.absorbMatrixAt(0, c.transpose()).absorbMatrixAt(2, c.adjoint())         # [n, q, n', q']
-        gram = LLp.contractWith(RRc, (1, 3), (1, 3)).join((0, 2), (1, 3))                      # [(i n), (i' n')]
+        W = RRc.absorbMatrixAt(1, Pc.conj()).absorbMatrixAt(3, Pc)                             # [n, j, n', j']
+        Wg = W.join((1, 3), (0, 2))                                                            # [(j j'), (n n')]
+        G4 = self.LLg.contractWith(Wg, (1,), (0,)).split(old, old, new, new)                   # [i, i', n, n']
+        gram = G4.join((0, 2), (1, 3))                                                         # [(i n), (i' n')]
         U = self.T.absorbMatrixAt(2, c.transpose())                                            # [i, j, n, q]
         rhs = U.contractWith(Pc.conj(), (1, 3), (0, 1)).ravel()                                # [(i n)]
         return gram, rhs

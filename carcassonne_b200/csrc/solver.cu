@@ -141,14 +141,101 @@ __global__ void __launch_bounds__(256) lu_update_kernel(cplx* __restrict__ A, in
   }
 }
 
+// Sub-panel factorisation: columns [s0, s0 + w) (w <= 8) in ONE launch of one CTA -- per column a pivot search,
+// a whole-row interchange, the scaling of the column and the rank-1 update of the rest of the sub-panel, separated
+// by __syncthreads instead of kernel boundaries.  Each thread owns the rows i = c + 1 + tid + 1024 q.
+__global__ void __launch_bounds__(1024) lu_subpanel_kernel(cplx* __restrict__ A, int n, int s0, int w,
+                                                           int* __restrict__ piv, int* __restrict__ singular) {
+  __shared__ double s_val[32];
+  __shared__ int s_idx[32];
+  __shared__ int s_p;
+  __shared__ cplx s_inv;
+  __shared__ cplx s_row[8];
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  const int c_end = s0 + w;
+  for (int c = s0; c < c_end; ++c) {
+    double best = -1.0;
+    int bi = c;
+    for (int i = c + tid; i < n; i += 1024) {
+      const cplx a = A[(int64_t)i * n + c];
+      const double m = fabs(a.x) + fabs(a.y);
+      if (m > best) { best = m; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) { s_val[wp] = best; s_idx[wp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      double b = s_val[0];
+      int p = s_idx[0];
+      for (int i = 1; i < 32; ++i)
+        if (s_val[i] > b || (s_val[i] == b && s_idx[i] < p)) { b = s_val[i]; p = s_idx[i]; }
+      s_p = p;
+      piv[c] = p;
+      if (!(b > 0.0)) *singular = 1;
+    }
+    __syncthreads();
+    const int p = s_p;
+    if (p != c) {
+      for (int cc = tid; cc < n; cc += 1024) {
+        const cplx a = A[(int64_t)c * n + cc], b = A[(int64_t)p * n + cc];
+        A[(int64_t)c * n + cc] = b;
+        A[(int64_t)p * n + cc] = a;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const cplx d = A[(int64_t)c * n + c];
+      s_inv = (d.x != 0.0 || d.y != 0.0) ? cdiv(make_double2(1.0, 0.0), d) : make_double2(0.0, 0.0);
+    }
+    if (tid < c_end - c - 1) s_row[tid] = A[(int64_t)c * n + c + 1 + tid];
+    __syncthreads();
+    const cplx inv = s_inv;
+    for (int i = c + 1 + tid; i < n; i += 1024) {
+      cplx* row = A + (int64_t)i * n;
+      const cplx l = cmul(row[c], inv);
+      row[c] = l;
+      for (int cc = c + 1; cc < c_end; ++cc) row[cc] = csub(row[cc], cmul(l, s_row[cc - c - 1]));
+    }
+    __syncthreads();
+  }
+}
+
+// rows r >= r0: A[r][c] -= sum_{t < w} A[r][s0 + t] A[s0 + t][c] for c in [c0, c_end); 32 columns x 8 rows per pass
+__global__ void __launch_bounds__(256) lu_rankw_kernel(cplx* __restrict__ A, int n, int s0, int w, int r0, int c0,
+                                                       int c_end) {
+  __shared__ cplx U[8][64];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int ncols = c_end - c0;
+  for (int e = threadIdx.x; e < w * ncols; e += 256) U[e / ncols][e % ncols] = A[(int64_t)(s0 + e / ncols) * n + c0 + e % ncols];
+  __syncthreads();
+  for (int r = r0 + blockIdx.x * 8 + ty; r < n; r += gridDim.x * 8) {
+    cplx* row = A + (int64_t)r * n;
+    cplx l[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) l[t] = t < w ? row[s0 + t] : make_double2(0.0, 0.0);
+    for (int c = tx; c < ncols; c += 32) {
+      cplx acc = row[c0 + c];
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+        if (t < w) acc = csub(acc, cmul(l[t], U[t][c]));
+      row[c0 + c] = acc;
+    }
+  }
+}
+
 // U12 = L11^-1 A12 : rows [j0, j0+nb), columns [c0, n); one thread per column, L11 (unit lower) in shared memory
-__global__ void __launch_bounds__(256) lu_trsm_kernel(cplx* __restrict__ A, int n, int j0, int nb, int c0) {
+__global__ void __launch_bounds__(256) lu_trsm_kernel(cplx* __restrict__ A, int n, int j0, int nb, int c0, int c_end) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx* L = reinterpret_cast<cplx*>(smem_raw);  // nb x nb
   for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) L[e] = A[(int64_t)(j0 + e / nb) * n + j0 + e % nb];
   __syncthreads();
   const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
+  if (c >= c_end) return;
   for (int r = 1; r < nb; ++r) {
     cplx acc = A[(int64_t)(j0 + r) * n + c];
     for (int k = 0; k < r; ++k) acc = csub(acc, cmul(L[r * nb + k], A[(int64_t)(j0 + k) * n + c]));
@@ -795,18 +882,37 @@ int lu_factor(cplx* A, int n, int* piv, int* singular_dev, cplx* scratch, cudaSt
   for (int j0 = 0; j0 < n; j0 += NB) {
     const int nb = n - j0 < NB ? n - j0 : NB;
     const int pe = j0 + nb;
-    for (int j = j0; j < pe; ++j) {
-      lu_pivot_kernel<<<1, 1024, 0, stream>>>(A, n, j, piv, scratch, singular_dev);
-      const int rows = n - j - 1;
-      if (rows > 0) {
-        int blocks = (rows + 7) / 8;
-        if (blocks > 148 * 4) blocks = 148 * 4;
-        lu_update_kernel<<<blocks, 256, 0, stream>>>(A, n, j, pe, scratch);
+    if (n <= 2048) {
+      // small matrices are launch-bound: eight columns per launch of one CTA
+      for (int s0 = j0; s0 < pe; s0 += 8) {
+        const int w = pe - s0 < 8 ? pe - s0 : 8;
+        lu_subpanel_kernel<<<1, 1024, 0, stream>>>(A, n, s0, w, piv, singular_dev);
+        const int c0 = s0 + w;
+        if (c0 < pe) {   // rest of the outer panel: U block row, then the rank-w update below it
+          lu_trsm_kernel<<<1, 256, w * w * 16, stream>>>(A, n, s0, w, c0, pe);
+          const int rows = n - c0;
+          if (rows > 0) {
+            int blocks = (rows + 7) / 8;
+            if (blocks > 148 * 4) blocks = 148 * 4;
+            lu_rankw_kernel<<<blocks, 256, 0, stream>>>(A, n, s0, w, c0, c0, pe);
+          }
+        }
+      }
+    } else {
+      // tall panels need every SM for the rank-1 updates: two launches per column
+      for (int j = j0; j < pe; ++j) {
+        lu_pivot_kernel<<<1, 1024, 0, stream>>>(A, n, j, piv, scratch, singular_dev);
+        const int rows = n - j - 1;
+        if (rows > 0) {
+          int blocks = (rows + 7) / 8;
+          if (blocks > 148 * 4) blocks = 148 * 4;
+          lu_update_kernel<<<blocks, 256, 0, stream>>>(A, n, j, pe, scratch);
+        }
       }
     }
     if (pe < n) {
       const int cols = n - pe;
-      lu_trsm_kernel<<<(cols + 255) / 256, 256, nb * nb * 16, stream>>>(A, n, j0, nb, pe);
+      lu_trsm_kernel<<<(cols + 255) / 256, 256, nb * nb * 16, stream>>>(A, n, j0, nb, pe, n);
       // A22 -= L21 U12
       GemmOut o;
       o.m_div = n; o.m_s1 = 0; o.m_s0 = n;
