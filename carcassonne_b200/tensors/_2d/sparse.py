@@ -19,6 +19,50 @@ from . import dense as _dense
 from .dense import *  # noqa: F401,F403  (the reference re-exports the dense recipes from here too)
 
 
+class _Memo:
+    """Small identity-keyed cache of environment pieces.  The convergence policies rebuild the environment of an
+    unchanged system several times per sweep iteration (``computeEstimatedOneSiteExpectation`` copies the system,
+    evaluates <H>, absorbs once and evaluates again -- 37 % of the reference's run time, SURVEY.md section 8f item 1);
+    device tensors are immutable values shared by the shallow ``System.__copy__``, so a stage-1 / stage-2 result
+    can be reused whenever exactly the same input tensors come back.  Entries keep their inputs alive (ids stay
+    valid) and are bounded in number and in bytes."""
+
+    def __init__(self, max_entries=16, max_bytes=4 << 30):
+        from collections import OrderedDict
+        self.entries = OrderedDict()
+        self.max_entries = max_entries
+        self.max_bytes = max_bytes
+        self.hits = self.misses = 0
+
+    @staticmethod
+    def _key(sparse_tensors, extra):
+        return tuple(tuple((tag, id(data)) for tag, data in t.items()) for t in sparse_tensors) + (extra,)
+
+    def get(self, sparse_tensors, extra, compute):
+        key = self._key(sparse_tensors, extra)
+        hit = self.entries.get(key)
+        if hit is not None:
+            self.entries.move_to_end(key)
+            self.hits += 1
+            return hit[1]
+        self.misses += 1
+        value = compute()
+        # what an entry pins: its value AND its inputs (which the system may otherwise have released)
+        size = sum(16 * data.size() for data in value.values()) + \
+            sum(16 * data.size() for t in sparse_tensors for data in t.values())
+        if size <= self.max_bytes // 4:
+            self.entries[key] = ([list(t.values()) for t in sparse_tensors], value, size)
+            while len(self.entries) > self.max_entries or sum(e[2] for e in self.entries.values()) > self.max_bytes:
+                self.entries.popitem(last=False)
+        return value
+
+    def clear(self):
+        self.entries.clear()
+
+
+environment_cache = _Memo()
+
+
 class Stage2Half(dict):
     """{tag: tensor} of one half-ring in the stage-3 streaming layout [(x y), D*, D*, D, D] (``half`` = 0 or 1);
     ``bonds`` keeps the two environment bond extents of the reference layout."""
@@ -59,20 +103,25 @@ def absorbSparseCenterSOSIntoSide(direction, side, state_center_data, operator_c
 
 
 def formExpectationStage1(corner, side):
-    """reference tensors/_2d/sparse.py:72-85."""
-    return contractSparseTensors(rule_stage1, lambda c, s, acc, _: _dense.formNormalizationStage1(c, s, acc),
-                                 corner, side)
+    """reference tensors/_2d/sparse.py:72-85 (memoised on the identity of the input tensors)."""
+    return environment_cache.get(
+        (corner, side), "stage1",
+        lambda: contractSparseTensors(rule_stage1, lambda c, s, acc, _: _dense.formNormalizationStage1(c, s, acc),
+                                      corner, side))
 
 
 def formExpectationStage2(right, left, half=None):
     """reference tensors/_2d/sparse.py:86-99.  ``half`` = 0 / 1 produces a ``Stage2Half`` in the stage-3 layout."""
-    result = contractSparseTensors(
-        rule_stage2, lambda r, l, acc, _: _dense.formNormalizationStage2(r, l, acc, half=half), right, left)
-    if half is None:
-        return result
-    out = Stage2Half(half, (left[Identity()].shape[0], right[Identity()].shape[1]))
-    out.update(result)
-    return out
+    def compute():
+        result = contractSparseTensors(
+            rule_stage2, lambda r, l, acc, _: _dense.formNormalizationStage2(r, l, acc, half=half), right, left)
+        if half is None:
+            return result
+        out = Stage2Half(half, (left[Identity()].shape[0], right[Identity()].shape[1]))
+        out.update(result)
+        return out
+
+    return environment_cache.get((right, left), ("stage2", half), compute)
 
 
 def _as_half(stage2, half):

@@ -199,6 +199,23 @@ def test_stage3_terms_tfim(dd):
     assert H.device_operator.num_terms == 9
 
 
+def test_environment_cache_reuses_unchanged_pieces(dd):
+    """computeEstimatedOneSiteExpectation on an unchanged system must not rebuild the environment."""
+    from carcassonne_b200.tensors._2d.sparse import environment_cache
+    s = _physical_system(dd, grow=False)
+    environment_cache.clear()
+    e0 = s.computeExpectation()
+    misses = environment_cache.misses
+    e1 = s.computeExpectation()
+    assert environment_cache.misses == misses and e1 == e0          # all six pieces came from the cache
+    before = (environment_cache.hits, environment_cache.misses)
+    s.computeEstimatedOneSiteExpectation(0)
+    hits, misses = environment_cache.hits - before[0], environment_cache.misses - before[1]
+    assert hits >= 6 + 2 and misses <= 4       # first <H>: all cached; after the absorption two stage-1 pieces survive
+    s.contractTowards(1)
+    assert abs(s.computeExpectation() - e0) > 0                     # a changed environment is never served stale
+
+
 def test_copy_is_shallow_and_safe(dd):
     from copy import copy
     g = load("walk_tfim_chi2_D2")
