@@ -29,6 +29,7 @@ SIGNATURES = {
     "carc_version": (c_int, []),
     "carc_last_error": (C.c_char_p, []),
     "carc_dmma_peak": (c_int, [c_int, c_dp, c_vp]),
+    "carc_dmma_rate": (c_int, [c_int, c_int, c_int, c_dp, c_vp]),
     "carc_malloc": (c_int, [C.POINTER(c_vp), C.c_size_t]),
     "carc_free": (c_int, [c_vp]),
     "carc_malloc_host": (c_int, [C.POINTER(c_vp), C.c_size_t]),

@@ -48,6 +48,9 @@ int carc_version(void) { return 100; }
 const char* carc_last_error(void) { return carc::get_error(); }
 
 int carc_dmma_peak(int iters, double* tflops_out, void* stream) { return carc::dmma_peak(iters, tflops_out, S(stream)); }
+int carc_dmma_rate(int iters, int warps_per_sm, int chains, double* tflops_out, void* stream) {
+  return carc::dmma_rate(iters, warps_per_sm, chains, tflops_out, S(stream));
+}
 
 int carc_malloc(void** ptr, size_t bytes) {
   CARC_CHECK_CUDA(cudaMalloc(ptr, bytes ? bytes : 16));

@@ -41,6 +41,7 @@ int zgemm_hermitian(int opA, int opB, int64_t N, int64_t K, const cplx* A, int64
                     cplx* C, cudaStream_t stream);
 int index_table(int nlevels, const int64_t* extents, const int64_t* strides, int64_t* table, cudaStream_t stream);
 int dmma_peak(int iters, double* tflops_out, cudaStream_t stream);
+int dmma_rate(int iters, int warps, int chains, double* tflops_out, cudaStream_t stream);
 
 // comm.cu
 struct Comm;

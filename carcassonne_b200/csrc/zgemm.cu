@@ -240,7 +240,80 @@ __global__ void __launch_bounds__(256) index_table_kernel(IndexLevels lv, int64_
   table[i] = off;
 }
 
+template <int CH>
+__global__ void __launch_bounds__(1024, 1) dmma_rate_kernel(double* out, int iters) {
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  double c0[CH], c1[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) c0[j] = c1[j] = 0.0;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) dmma(c0[j], c1[j], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < CH; ++j) s += c0[j] + c1[j];
+  if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// the same with distinct A / B operand registers per instruction (4 x 4 outer product of fragments, the register
+// traffic a real GEMM inner loop has), to separate issue-rate limits from operand-fetch limits
+__global__ void __launch_bounds__(256, 1) dmma_rate_distinct_kernel(double* out, int iters) {
+  double a[4], b[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    a[j] = 1.0 + (threadIdx.x + j) * 1e-9;
+    b[j] = 1.0 - (threadIdx.x + 2 * j) * 1e-9;
+  }
+  double c0[16], c1[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) c0[j] = c1[j] = 0.0;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dmma(c0[j], c1[j], a[j >> 2], b[j & 3]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {   // keep the operands changing like fragments reloaded every k-step
+      a[j] += 1e-12;
+      b[j] -= 1e-12;
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s += c0[j] + c1[j];
+  if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace
+
+// DMMA issue rate with `warps` warps per SM (one CTA per SM) and `chains` independent accumulators per warp
+int dmma_rate(int iters, int warps, int chains, double* tflops_out, cudaStream_t stream) {
+  double* buf = nullptr;
+  CARC_CHECK_CUDA(cudaMalloc(&buf, sizeof(double) * 148 * 1024));
+  cudaEvent_t e0, e1;
+  CARC_CHECK_CUDA(cudaEventCreate(&e0));
+  CARC_CHECK_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    CARC_CHECK_CUDA(cudaEventRecord(e0, stream));
+    if (chains >= 100) dmma_rate_distinct_kernel<<<148, warps * 32, 0, stream>>>(buf, iters);
+    else if (chains <= 2) dmma_rate_kernel<2><<<148, warps * 32, 0, stream>>>(buf, iters);
+    else if (chains <= 4) dmma_rate_kernel<4><<<148, warps * 32, 0, stream>>>(buf, iters);
+    else if (chains <= 8) dmma_rate_kernel<8><<<148, warps * 32, 0, stream>>>(buf, iters);
+    else dmma_rate_kernel<16><<<148, warps * 32, 0, stream>>>(buf, iters);
+    CARC_CHECK_CUDA(cudaEventRecord(e1, stream));
+    CARC_CHECK_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    CARC_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  const int ch = chains >= 100 ? 16 : chains <= 2 ? 2 : chains <= 4 ? 4 : chains <= 8 ? 8 : 16;
+  *tflops_out = 148.0 * warps * iters * (double)ch * 512.0 / (best * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  return CARC_OK;
+}
+
 
 int index_table(int nlevels, const int64_t* extents, const int64_t* strides, int64_t* table, cudaStream_t stream) {
   CARC_REQUIRE(nlevels >= 0 && nlevels <= CARC_MAX_RANK, CARC_ERR_RANK, "index_table: %d levels unsupported", nlevels);

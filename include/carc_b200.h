@@ -50,6 +50,9 @@ int carc_version(void);
 const char* carc_last_error(void);
 /* Measured issue rate of DMMA.8x8x4 on the current device in TFLOP/s (the FP64 tensor roofline). */
 int carc_dmma_peak(int iters, double* tflops_out, void* stream);
+/* The same microbenchmark with `warps_per_sm` warps (one CTA per SM) and `chains` (2, 4, 8 or 16) independent
+ * accumulator chains per warp: how the DMMA issue rate depends on occupancy and instruction-level parallelism. */
+int carc_dmma_rate(int iters, int warps_per_sm, int chains, double* tflops_out, void* stream);
 
 /* ---- device memory for callers that do not bring their own allocator ------------------------------------ */
 int carc_malloc(void** ptr, size_t bytes);
