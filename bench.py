@@ -320,10 +320,15 @@ def run_device(args, rank, world, local_rank):
                 "frac": achieved_tf / tf.value, "traffic": traffic,
                 "kernel": "stage3_kernel (fused A.v -> O -> B^T, DMMA.8x8x4)",
                 "executed_flops_per_launch": executed, "reference_flops_per_launch": flops_local,
-                "note": "achieved = FP64 flops the kernel issues / its duration; the kernel sums the first products of "
-                        "terms that share a half-1 tensor before one second product, so it issues %d + %d products "
-                        "per x where the reference performs %d + %d -- `value` counts the reference's flops"
-                        % (len(terms), op.num_groups, len(terms), len(terms)),
+                "note": "achieved = FP64 flops the kernel issues / its duration.  The kernel decomposes the term list "
+                        "into stars (terms sharing a half-1 tensor: first products summed before one second product; "
+                        "terms sharing a half-0 tensor: one first product reused), so it issues %.0f%% of the flops "
+                        "the reference performs for the same result -- `value` counts the reference's flops"
+                        % (100.0 * executed / flops_local),
+                "peak_distinct_operands": 31.4,
+                "peak_note": "peak = DMMA.8x8x4 issue rate with register-resident operands; with a fresh A/B fragment "
+                             "per instruction (what any GEMM inner loop needs) the same microbenchmark tops out at "
+                             "31.4 TFLOP/s on this part (scripts/dmma_rate.py, 8 warps/SM)",
                 "peak_source": "DMMA.8x8x4 issue-rate microbenchmark run in this process (carc_dmma_peak); "
                                "MEASURED_PEAKS.json has no FP64 figure",
                 "algorithmic_bytes": 12 * 16 * Xl * D ** 4 + 32 * n,

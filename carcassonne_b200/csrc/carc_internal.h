@@ -61,9 +61,10 @@ struct Stage3Term {
   cplx op[16];     // row-major d x d site operator O[s', s]
 };
 struct Stage3Group {
-  const cplx* B;   // the half-1 tensor every term of the group shares
+  const cplx* center;   // the tensor every term of the star shares: B (kind 0) or A (kind 1)
   int64_t X;
-  int first, count;   // terms [first, first + count) of the sorted term table
+  int first, count;     // terms [first, first + count) of the sorted term table
+  int kind;             // 0: B-star (first products summed, one second product); 1: A-star (one first product reused)
 };
 struct Stage3Plan {
   std::vector<Stage3Term> terms;     // sorted by group

@@ -96,17 +96,21 @@ __global__ void __launch_bounds__(s3_max_threads(NRT), 1) stage3_kernel(const S3
   int* hasop = reinterpret_cast<int*>(smem + p.hasop_off);
   // small per-launch tables in shared memory: they sit on the critical path of every item
   const cplx** termA = reinterpret_cast<const cplx**>(smem + p.tab_off);
-  const cplx** groupB = termA + p.nterms;
-  int* groupX = reinterpret_cast<int*>(groupB + p.ngroups);
+  const cplx** termB = termA + p.nterms;
+  const cplx** groupCenter = termB + p.nterms;
+  int* groupX = reinterpret_cast<int*>(groupCenter + p.ngroups);
   int* groupFirst = groupX + p.ngroups;
   int* groupCount = groupFirst + p.ngroups;
+  int* groupKind = groupCount + p.ngroups;
   for (int i = tid; i < p.nterms * DP * DP; i += blockDim.x) ops[i] = p.terms[i / (DP * DP)].op[i % (DP * DP)];
   for (int i = tid; i < p.nterms; i += blockDim.x) {
     hasop[i] = p.terms[i].has_op;
     termA[i] = p.terms[i].A;
+    termB[i] = p.terms[i].B;
   }
   for (int i = tid; i < p.ngroups; i += blockDim.x) {
-    groupB[i] = p.groups[i].B;
+    groupCenter[i] = p.groups[i].center;
+    groupKind[i] = p.groups[i].kind;
     groupX[i] = (int)p.groups[i].X;
     groupFirst[i] = p.groups[i].first;
     groupCount[i] = p.groups[i].count;
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(s3_max_threads(NRT), 1) stage3_kernel(const S3
     const uint32_t a_bytes = (uint32_t)(p.P * p.Q * 16);
     const uint32_t b_row_bytes = (uint32_t)(SBv * 16);
     auto issueA = [&](const Cursor& cu, uint32_t it) {
-      const cplx* A = termA[groupFirst[cu.gi] + cu.j];
+      const cplx* A = groupKind[cu.gi] ? groupCenter[cu.gi] : termA[groupFirst[cu.gi] + cu.j];
       const int sa = it % p.nstA;
       const uint32_t fullA = b + (2 * sa) * 8;
       if (lane == 0) {
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(s3_max_threads(NRT), 1) stage3_kernel(const S3
       __syncwarp();
     };
     auto issueB = [&](const Cursor& cu, uint32_t it) {
-      const cplx* B = groupB[cu.gi];
+      const cplx* B = groupKind[cu.gi] ? termB[groupFirst[cu.gi] + cu.j - 1] : groupCenter[cu.gi];
       const int sbq = it % p.nstB;
       const uint32_t fullB = b + (2 * p.nstA + 2 * sbq) * 8;
       if (lane == 0) {
@@ -196,7 +200,7 @@ __global__ void __launch_bounds__(s3_max_threads(NRT), 1) stage3_kernel(const S3
           pending = more;
           if (!more) break;
         }
-        if (pc.j < groupCount[pc.gi]) {
+        if (groupKind[pc.gi] ? (pc.j == 0) : (pc.j < groupCount[pc.gi])) {
           if (issuedA - itA >= (uint32_t)p.nstA) break;
           issueA(pc, issuedA++);
         } else {
@@ -212,12 +216,13 @@ __global__ void __launch_bounds__(s3_max_threads(NRT), 1) stage3_kernel(const S3
     while (next_item(cc)) {
       CTile T[2][DP];
       const int first = groupFirst[cc.gi], cnt = groupCount[cc.gi];
+      const int kind = groupKind[cc.gi];
       {
         // ---- first term of the group: both S chunks accumulate straight into T (8 independent DMMA chains, the A
         // fragments are loaded once for both chunks), then the site operator is applied in place
         if (wg == 0) run_ahead();
         const int term = first;
-        const bool has_op = hasop[term] != 0;
+        const bool has_op = !kind && hasop[term] != 0;   // an A-star keeps the raw product: each of its terms has its own O
         const int slot = itA % p.nstA;
         mbar_wait(b + (2 * slot) * 8, (itA / p.nstA) & 1);
         const uint32_t a_base = ring + slot * p.slotA_bytes + a_lane_off;
@@ -271,85 +276,134 @@ __global__ void __launch_bounds__(s3_max_threads(NRT), 1) stage3_kernel(const S3
         if (lane == 0) mbar_arrive(b + (2 * slot + 1) * 8);
         ++itA;
       }
-      for (int j = 1; j < cnt; ++j) {
-        if (wg == 0) run_ahead();
-        // ---- first product of a further term of the group: U = A_x v (8 rows of P, this S block); T (+)= O U
-        const int term = first + j;
-        const bool has_op = hasop[term] != 0;
-        const int slot = itA % p.nstA;
-        mbar_wait(b + (2 * slot) * 8, (itA / p.nstA) & 1);
-        const uint32_t a_base = ring + slot * p.slotA_bytes + a_lane_off;
+      if (!kind) {
+        for (int j = 1; j < cnt; ++j) {
+          if (wg == 0) run_ahead();
+          // ---- first product of a further term of the group: U = A_x v (8 rows of P, this S block); T (+)= O U
+          const int term = first + j;
+          const bool has_op = hasop[term] != 0;
+          const int slot = itA % p.nstA;
+          mbar_wait(b + (2 * slot) * 8, (itA / p.nstA) & 1);
+          const uint32_t a_base = ring + slot * p.slotA_bytes + a_lane_off;
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          CTile U[DP];
+          for (int ch = 0; ch < 2; ++ch) {
+            CTile U[DP];
 #pragma unroll
-          for (int s = 0; s < DP; ++s) U[s].zero();
+            for (int s = 0; s < DP; ++s) U[s].zero();
 #pragma unroll 2
-          for (int kp = 0; kp < p.Q8; ++kp) {
-            const cplx x0 = lds_c(a_base + kp * 128 + a_first);
-            const cplx x1 = lds_c(a_base + kp * 128 + a_second);
-            const cplx a0 = eswap ? x1 : x0;
-            const cplx a1 = eswap ? x0 : x1;
+            for (int kp = 0; kp < p.Q8; ++kp) {
+              const cplx x0 = lds_c(a_base + kp * 128 + a_first);
+              const cplx x1 = lds_c(a_base + kp * 128 + a_second);
+              const cplx a0 = eswap ? x1 : x0;
+              const cplx a1 = eswap ? x0 : x1;
 #pragma unroll
-            for (int s = 0; s < DP; ++s) {
-              const uint32_t va = v_base + (uint32_t)((((s * SBW + ch * 8) * QS) + kp * 8) * 16);
-              const cplx b0 = lds_c(va);
-              const cplx b1 = lds_c(va + 16);
-              cmma(U[s], a0.x, a0.y, -a0.y, b0.x, b0.y);
-              cmma(U[s], a1.x, a1.y, -a1.y, b1.x, b1.y);
+              for (int s = 0; s < DP; ++s) {
+                const uint32_t va = v_base + (uint32_t)((((s * SBW + ch * 8) * QS) + kp * 8) * 16);
+                const cplx b0 = lds_c(va);
+                const cplx b1 = lds_c(va + 16);
+                cmma(U[s], a0.x, a0.y, -a0.y, b0.x, b0.y);
+                cmma(U[s], a1.x, a1.y, -a1.y, b1.x, b1.y);
+              }
             }
-          }
-          if (!has_op) {
+            if (!has_op) {
 #pragma unroll
-            for (int s = 0; s < DP; ++s) {
-              T[ch][s].re0 += U[s].re0;
-              T[ch][s].im0 += U[s].im0;
-              T[ch][s].re1 += U[s].re1;
-              T[ch][s].im1 += U[s].im1;
-            }
-          } else {
+              for (int s = 0; s < DP; ++s) {
+                T[ch][s].re0 += U[s].re0;
+                T[ch][s].im0 += U[s].im0;
+                T[ch][s].re1 += U[s].re1;
+                T[ch][s].im1 += U[s].im1;
+              }
+            } else {
 #pragma unroll
-            for (int s = 0; s < DP; ++s) {
+              for (int s = 0; s < DP; ++s) {
 #pragma unroll
-              for (int s2 = 0; s2 < DP; ++s2) {
-                const cplx w = ops[term * DP * DP + s * DP + s2];
-                if (w.x != 0.0 || w.y != 0.0) {
-                  T[ch][s].re0 += w.x * U[s2].re0 - w.y * U[s2].im0;
-                  T[ch][s].im0 += w.x * U[s2].im0 + w.y * U[s2].re0;
-                  T[ch][s].re1 += w.x * U[s2].re1 - w.y * U[s2].im1;
-                  T[ch][s].im1 += w.x * U[s2].im1 + w.y * U[s2].re1;
+                for (int s2 = 0; s2 < DP; ++s2) {
+                  const cplx w = ops[term * DP * DP + s * DP + s2];
+                  if (w.x != 0.0 || w.y != 0.0) {
+                    T[ch][s].re0 += w.x * U[s2].re0 - w.y * U[s2].im0;
+                    T[ch][s].im0 += w.x * U[s2].im0 + w.y * U[s2].re0;
+                    T[ch][s].re1 += w.x * U[s2].re1 - w.y * U[s2].im1;
+                    T[ch][s].im1 += w.x * U[s2].im1 + w.y * U[s2].re1;
+                  }
                 }
               }
             }
           }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(b + (2 * slot + 1) * 8);
+          ++itA;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(b + (2 * slot + 1) * 8);
-        ++itA;
-      }
-      if (wg == 0) run_ahead();
-      // ---- second product of the group: acc += T * B_x^T ; T's C fragments are the A fragments
-      {
-        const int slot = itB % p.nstB;
-        mbar_wait(b + (2 * p.nstA + 2 * slot) * 8, (itB / p.nstB) & 1);
-        const uint32_t b_base = ring + p.nstA * p.slotA_bytes + slot * p.slotB_bytes + b_lane_off;
+        if (wg == 0) run_ahead();
+        // ---- second product of the group: acc += T * B_x^T ; T's C fragments are the A fragments
+        {
+          const int slot = itB % p.nstB;
+          mbar_wait(b + (2 * p.nstA + 2 * slot) * 8, (itB / p.nstB) & 1);
+          const uint32_t b_base = ring + p.nstA * p.slotA_bytes + slot * p.slotB_bytes + b_lane_off;
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
+          for (int ch = 0; ch < 2; ++ch) {
 #pragma unroll
-          for (int rt = 0; rt < NRT; ++rt) {
-            const uint32_t ba = b_base + (uint32_t)(((rt * 8) * BSTR + ch * 8) * 16);
-            const cplx b0 = lds_c(ba);
-            const cplx b1 = lds_c(ba + 16);
+            for (int rt = 0; rt < NRT; ++rt) {
+              const uint32_t ba = b_base + (uint32_t)(((rt * 8) * BSTR + ch * 8) * 16);
+              const cplx b0 = lds_c(ba);
+              const cplx b1 = lds_c(ba + 16);
 #pragma unroll
-            for (int s = 0; s < DP; ++s) {
-              cmma(acc[rt][s], T[ch][s].re0, T[ch][s].im0, -T[ch][s].im0, b0.x, b0.y);
-              cmma(acc[rt][s], T[ch][s].re1, T[ch][s].im1, -T[ch][s].im1, b1.x, b1.y);
+              for (int s = 0; s < DP; ++s) {
+                cmma(acc[rt][s], T[ch][s].re0, T[ch][s].im0, -T[ch][s].im0, b0.x, b0.y);
+                cmma(acc[rt][s], T[ch][s].re1, T[ch][s].im1, -T[ch][s].im1, b1.x, b1.y);
+              }
             }
           }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(b + (2 * p.nstA + 2 * slot + 1) * 8);
+          ++itB;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(b + (2 * p.nstA + 2 * slot + 1) * 8);
-        ++itB;
+      } else {
+        // ---- A-star: T holds U = A_x v once; every term of the group applies its own site operator to U and multiplies
+        // with its own B_x
+        for (int j = 0; j < cnt; ++j) {
+          if (wg == 0) run_ahead();
+          const int term = first + j;
+          const bool has_op = hasop[term] != 0;
+          const int slot = itB % p.nstB;
+          mbar_wait(b + (2 * p.nstA + 2 * slot) * 8, (itB / p.nstB) & 1);
+          const uint32_t b_base = ring + p.nstA * p.slotA_bytes + slot * p.slotB_bytes + b_lane_off;
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            CTile W[DP];
+#pragma unroll
+            for (int s = 0; s < DP; ++s) {
+              if (!has_op) {
+                W[s] = T[ch][s];
+              } else {
+                W[s].zero();
+#pragma unroll
+                for (int s2 = 0; s2 < DP; ++s2) {
+                  const cplx w = ops[term * DP * DP + s * DP + s2];
+                  if (w.x != 0.0 || w.y != 0.0) {
+                    W[s].re0 += w.x * T[ch][s2].re0 - w.y * T[ch][s2].im0;
+                    W[s].im0 += w.x * T[ch][s2].im0 + w.y * T[ch][s2].re0;
+                    W[s].re1 += w.x * T[ch][s2].re1 - w.y * T[ch][s2].im1;
+                    W[s].im1 += w.x * T[ch][s2].im1 + w.y * T[ch][s2].re1;
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int rt = 0; rt < NRT; ++rt) {
+              const uint32_t ba = b_base + (uint32_t)(((rt * 8) * BSTR + ch * 8) * 16);
+              const cplx b0 = lds_c(ba);
+              const cplx b1 = lds_c(ba + 16);
+#pragma unroll
+              for (int s = 0; s < DP; ++s) {
+                cmma(acc[rt][s], W[s].re0, W[s].im0, -W[s].im0, b0.x, b0.y);
+                cmma(acc[rt][s], W[s].re1, W[s].im1, -W[s].im1, b1.x, b1.y);
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(b + (2 * p.nstA + 2 * slot + 1) * 8);
+          ++itB;
+        }
       }
     }
     // ---- partial result of this (CTA, group)
@@ -425,7 +479,7 @@ bool s3_configure(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, S
         const uint32_t ops_off = bar_bytes;
         const uint32_t hasop_off = ops_off + obytes;
         const uint32_t tab_off = (hasop_off + (uint32_t)nterms * 4 + 15) / 16 * 16;
-        const uint32_t vt_off = (tab_off + (uint32_t)nterms * 8 + (uint32_t)nterms * 20 + 127) / 128 * 128;
+        const uint32_t vt_off = (tab_off + (uint32_t)nterms * 16 + (uint32_t)nterms * 24 + 127) / 128 * 128;
         const uint32_t ring_off = (vt_off + vbytes + 127) / 128 * 128;
         const uint64_t total = (uint64_t)ring_off + (uint64_t)G * ((uint64_t)nstA * k.slotA + (uint64_t)nstB * k.slotB);
         if (total <= SMEM_LIMIT) {
@@ -527,25 +581,44 @@ int64_t stage3_workspace_elems(int nterms, int P, int Q, int R, int S, int d, in
   return std::max(fused, unfused);
 }
 
-// Group the terms by their B tensor (first-appearance order) and upload both tables.
+// Decompose the term list -- a bipartite multigraph between half-0 tensors A and half-1 tensors B -- into stars:
+// repeatedly take the tensor with the most remaining terms (ties: B first, then first appearance) together with all
+// of them.  A B-star (kind 0) sums the first products of its terms before ONE second product; an A-star (kind 1)
+// computes ONE first product and reuses it for the second product of each of its terms.  For the transverse-Ising
+// operator (9 terms over 6 + 6 tensors) this gives 7 first + 6 second products per x instead of 9 + 9.
 int stage3_plan_create(const Stage3Term* terms, int nterms, Stage3Plan** out) {
   Stage3Plan* plan = new Stage3Plan();
   std::vector<int> group_of(nterms, -1);
-  for (int t = 0; t < nterms; ++t) {
-    int gi = -1;
-    for (int q = 0; q < (int)plan->groups.size(); ++q)
-      if (plan->groups[q].B == terms[t].B && plan->groups[q].X == terms[t].X) gi = q;
-    if (gi < 0) {
-      Stage3Group gr;
-      gr.B = terms[t].B;
-      gr.X = terms[t].X;
-      gr.first = 0;
-      gr.count = 0;
-      plan->groups.push_back(gr);
-      gi = (int)plan->groups.size() - 1;
+  int remaining = nterms;
+  while (remaining > 0) {
+    int best_deg = 0, best_kind = 0, best_t = -1;
+    for (int t = 0; t < nterms; ++t) {
+      if (group_of[t] >= 0) continue;
+      int degB = 0, degA = 0;
+      for (int u = 0; u < nterms; ++u) {
+        if (group_of[u] >= 0) continue;
+        if (terms[u].B == terms[t].B && terms[u].X == terms[t].X) ++degB;
+        if (terms[u].A == terms[t].A && terms[u].X == terms[t].X) ++degA;
+      }
+      if (degB > best_deg) { best_deg = degB; best_kind = 0; best_t = t; }
+      if (degA > best_deg) { best_deg = degA; best_kind = 1; best_t = t; }
     }
-    group_of[t] = gi;
-    ++plan->groups[gi].count;
+    Stage3Group gr;
+    gr.kind = best_kind;
+    gr.center = best_kind ? terms[best_t].A : terms[best_t].B;
+    gr.X = terms[best_t].X;
+    gr.first = 0;
+    gr.count = 0;
+    const int gi = (int)plan->groups.size();
+    for (int u = 0; u < nterms; ++u) {
+      if (group_of[u] >= 0 || terms[u].X != gr.X) continue;
+      if ((best_kind ? terms[u].A : terms[u].B) == gr.center) {
+        group_of[u] = gi;
+        ++gr.count;
+        --remaining;
+      }
+    }
+    plan->groups.push_back(gr);
   }
   int first = 0;
   for (auto& gr : plan->groups) {
@@ -582,8 +655,10 @@ void stage3_plan_destroy(Stage3Plan* plan) {
 // one per group), for the roofline; the reference-equivalent count is 8 x cost_of_multiply.
 double stage3_executed_flops(const Stage3Plan* plan, int P, int Q, int R, int S, int d) {
   double f = 0.0;
-  for (const auto& gr : plan->groups)
-    f += 8.0 * (double)gr.X * ((double)gr.count * P * Q * S * d + (double)P * R * S * d);
+  for (const auto& gr : plan->groups) {
+    const double first = gr.kind ? 1.0 : (double)gr.count, second = gr.kind ? (double)gr.count : 1.0;
+    f += 8.0 * (double)gr.X * (first * P * Q * S * d + second * P * R * S * d);
+  }
   return f;
 }
 

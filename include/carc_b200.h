@@ -120,9 +120,10 @@ int carc_operator_set_path(carc_operator* op, int force_path);
 int carc_operator_num_terms(const carc_operator* op);
 /* cmac count the reference's CostTracker assigns to one apply (data/cost_tracker.py:17-21) */
 int64_t carc_operator_cost_of_multiply(const carc_operator* op);
-/* After finalize: terms sharing a B tensor are grouped (their first products are summed before ONE second product).
- * num_groups = distinct B tensors; executed_flops = FP64 flops the fused kernel issues per apply (for the roofline:
- * 8 X S d (count P Q + P R) per group), <= 8 x cost_of_multiply. */
+/* After finalize the term list is decomposed into stars: terms sharing a half-1 tensor B have their first products
+ * summed before ONE second product, terms sharing a half-0 tensor A reuse ONE first product (linearity).
+ * num_groups = number of stars; executed_flops = FP64 flops the fused kernel issues per apply (the roofline
+ * numerator), <= 8 x cost_of_multiply. */
 int carc_operator_num_groups(const carc_operator* op);
 double carc_operator_executed_flops(const carc_operator* op);
 int carc_operator_destroy(carc_operator* op);

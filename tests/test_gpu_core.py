@@ -226,8 +226,10 @@ def test_stage3_shared_tensors(dd, chi2, D, path):
     for a, b, o in terms:
         op.add_term(halves_0[a], halves_1[b], o)
     op.finalize().set_path(path)
-    assert op.num_terms == 9 and op.num_groups == 6
-    assert op.executed_flops < 8 * op.cost_of_multiply
+    assert op.num_terms == 9 and op.num_groups == 4          # B_I star (4 terms), A_I star (3), two single terms
+    # 7 first + 6 second products per x instead of the reference's 9 + 9
+    per_product = 8.0 * chi2 * chi2 * D ** 6 * 2
+    assert abs(op.executed_flops - 13 * per_product) < 1e-6 * op.executed_flops
     out = op(dd.fromArray(v)).toArray()
     assert relerr(out, ref) < MATVEC_TOL
 
