@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Headline benchmark: the center-site expectation matvec (BASELINE.json metric "center-site matvec GFLOP/s").
 
+(The term structure is read off the planner itself: see term_table_device / term_table_cpu.)
+
 A step is one application of the expectation multiplier H = sum_t B_t . (A_t . (O_t v)) that
 ``System.formExpectationMultiplier()`` builds (reference tensors/_2d/sparse.py:100-161, dense.py:115-203) for the
 2D transverse-field Ising Hamiltonian after one absorption round: T = 9 sparse terms over 6 + 6 stage-2
@@ -37,17 +39,56 @@ UNIT = "GFLOP/s"
 
 _Z = np.array([[1, 0], [0, -1]], dtype=np.complex128)
 _X = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+_Y = np.array([[0, -1j], [1j, 0]], dtype=np.complex128)
 
 
-def tfim_terms(J=1.0):
-    """Stage-3 term table of the TFIM operator (Os=[-Z], OO_LRs=[(X,-J X)], OO_UDs=[(X,-J X)]) after one
-    absorption in each direction.  Half-tensor indices: 0 Identity, 1 Complete, 2 TwoSite(0,LEFT,0),
-    3 TwoSite(0,RIGHT,0), 4 TwoSite(0,CENTER,LEFT), 5 TwoSite(0,CENTER,RIGHT).  (a, b, site operator)."""
-    return [
-        (1, 0, None), (0, 1, None), (0, 0, -_Z),
-        (4, 0, _X), (5, 0, -J * _X), (0, 4, -J * _X), (0, 5, _X),
-        (3, 2, None), (2, 3, None),
-    ]
+def _index_terms(terms, operator_of):
+    """[(tag_0, tag_1, tag_center)] -> (n_half0, n_half1, [(a, b, site operator or None)]) with tensors numbered in
+    order of first appearance."""
+    a_index, b_index, out = {}, {}, []
+    for x, y, z in terms:
+        a = a_index.setdefault(x, len(a_index))
+        b = b_index.setdefault(y, len(b_index))
+        out.append((a, b, operator_of(z)))
+    return len(a_index), len(b_index), out
+
+
+def _operator_lists(model, J):
+    if model == "tfim":      # Os=[-Z], OO_LRs=[(X,-J X)], OO_UDs=[(X,-J X)]
+        return [-_Z], [(_X, -J * _X)], [(_X, -J * _X)]
+    pairs = [(_X, _X), (_Y, _Y), (_Z, _Z)]   # nearest-neighbour Heisenberg
+    return [], list(pairs), list(pairs)
+
+
+def term_table_device(model, J=1.0):
+    """The stage-3 term structure as the product's own planner produces it: a trivial system (all bonds 1) of the
+    model is absorbed once in every direction and its expectation multiplier's term list is read off.  Only the
+    STRUCTURE (which half-0 tensor meets which half-1 tensor under which site operator) is used; the benchmark's
+    tensors are synthetic."""
+    from carcassonne_b200.data import DeviceData
+    from carcassonne_b200.sparse import Identity
+    from carcassonne_b200.system import System
+    Os, UDs, LRs = _operator_lists(model, J)
+    dev = DeviceData.fromArray
+    system = System.newTrivialWithSparseOperator([dev(o) for o in Os], [(dev(a), dev(b)) for a, b in UDs],
+                                                 [(dev(a), dev(b)) for a, b in LRs])
+    for direction in range(4):
+        system.contractTowards(direction)
+    H, _ = system.formExpectationAndNormalizationMultipliers()
+    ops = system.operator_center_tensor
+    return _index_terms(H.terms, lambda z: None if z == Identity() else ops[z].toArray())
+
+
+def term_table_cpu(model, J=1.0):
+    """The same structure from the oracle's planner (reference arm / cpu_baseline only)."""
+    from oracle import tags
+    from oracle.system import System
+    Os, UDs, LRs = _operator_lists(model, J)
+    system = System.new_trivial(tags.make_sparse_operator(Os, UDs, LRs))
+    for direction in range(4):
+        system.contract_towards(direction)
+    H, _ = system.multipliers()
+    return _index_terms(H.terms, lambda z: None if z == tags.I else system.operator_center[z])
 
 
 def cost_of_multiply(terms, X, D, d):
@@ -111,7 +152,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------
-def cpu_matvec_sample(D, d, terms, X_sample, repeats=1, seed=0):
+def cpu_matvec_sample(D, d, table, X_sample, repeats=1, seed=0):
     """Times the oracle's restatement of the reference matvec (two tensordots per term, NumPy -> BLAS zgemm)
     on an X slab of the workload.  Returns (GFLOP/s, seconds, threads)."""
     from oracle import dense
@@ -126,8 +167,9 @@ def cpu_matvec_sample(D, d, terms, X_sample, repeats=1, seed=0):
     def crand(*shape):
         return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
 
-    A = [crand(X_sample, D, D, D, D) for _ in range(6)]
-    B = [crand(X_sample, D, D, D, D) for _ in range(6)]
+    na, nb, terms = table
+    A = [crand(X_sample, D, D, D, D) for _ in range(na)]
+    B = [crand(X_sample, D, D, D, D) for _ in range(nb)]
     v = crand(D, D, D, D, d)
 
     def matvec():
@@ -146,9 +188,9 @@ def cpu_matvec_sample(D, d, terms, X_sample, repeats=1, seed=0):
     return flops / best / 1e9, best, threads
 
 
-def pick_cpu_sample(D, X):
+def pick_cpu_sample(D, X, nterms=9):
     """X slab that costs about 10-20 s of CPU work at ~10 GFLOP/s."""
-    per_x = 8.0 * 9 * 2 * (D ** 6) * 2
+    per_x = 8.0 * nterms * 2 * (D ** 6) * 2
     xs = int(max(1, min(X, 1.5e11 / per_x)))
     return xs
 
@@ -158,25 +200,26 @@ def run_reference(args, rank, world):
         return
     D, chi, d = args.D, args.chi, 2
     X = chi ** 4
-    terms = tfim_terms()
-    xs = pick_cpu_sample(D, X)
+    table = term_table_cpu(args.model)
+    terms = table[2]
+    xs = pick_cpu_sample(D, X, len(terms))
     if args.steps * 1.0 > 6:
         xs = max(1, xs * 6 // args.steps)
     for _ in range(args.warmup):
-        cpu_matvec_sample(D, d, terms, max(1, xs // 8))
+        cpu_matvec_sample(D, d, table, max(1, xs // 8))
     vals, secs = [], []
     threads = 1
     for _ in range(args.steps):
-        g, s, threads = cpu_matvec_sample(D, d, terms, xs)
+        g, s, threads = cpu_matvec_sample(D, d, table, xs)
         vals.append(g)
         secs.append(s)
     value = float(np.mean(vals))
-    sample = "T=9 TFIM terms, D=%d, X slab of %d of %d (chi=%d)" % (D, xs, X, chi)
+    sample = "T=%d %s terms, D=%d, X slab of %d of %d (chi=%d)" % (len(terms), args.model, D, xs, X, chi)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3 * (X / xs),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "complex128 (f64)",
-        "data": "synthetic", "config": workload_config(args, X),
+        "data": "synthetic", "config": workload_config(args, X, len(terms)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -184,9 +227,12 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, X):
-    return {"workload": "TFIM expectation matvec, T=9 terms, D=%d, chi=%d (X=%d), d=2" % (args.D, args.chi, X),
-            "D": args.D, "chi": args.chi, "terms": 9, "l2": "inputs (12 x 16*X*D^4 B) larger than L2",
+def workload_config(args, X, nterms):
+    name = "TFIM" if args.model == "tfim" else "Heisenberg"
+    return {"workload": "%s expectation matvec, T=%d terms, D=%d, chi=%d (X=%d), d=2" % (name, nterms, args.D,
+                                                                                          args.chi, X),
+            "D": args.D, "chi": args.chi, "terms": nterms, "model": args.model,
+            "l2": "inputs (stage-2 tensors of 16*X*D^4 B each) larger than L2",
             "sharding": "X slabs over ranks + one-shot all-reduce of the output vector (%s)" % (
                 "NVLink peer memory, fused into the stage-3 partial-sum kernel" if getattr(args, "reduce", "peer") == "peer"
                 else "NCCL")}
@@ -208,7 +254,7 @@ def run_device(args, rank, world, local_rank):
     X = chi ** 4
     x_lo, x_hi = X * rank // world, X * (rank + 1) // world
     Xl = x_hi - x_lo
-    terms = tfim_terms()
+    na, nb, terms = term_table_device(args.model)
     gen = torch.Generator(device="cuda")
     gen.manual_seed(1234 + rank)
 
@@ -218,8 +264,8 @@ def run_device(args, rank, world, local_rank):
         return t
 
     scale = 1.0 / (D * D * np.sqrt(X))
-    A = [DeviceData(rnd(Xl, D, D, D, D).mul_(scale)) for _ in range(6)]
-    B = [DeviceData(rnd(Xl, D, D, D, D).mul_(scale)) for _ in range(6)]
+    A = [DeviceData(rnd(Xl, D, D, D, D).mul_(scale)) for _ in range(na)]
+    B = [DeviceData(rnd(Xl, D, D, D, D).mul_(scale)) for _ in range(nb)]
     op = Stage3Operator((D, D, D, D, d))
     for a, b, o in terms:
         op.add_term(A[a], B[b], o)
@@ -331,16 +377,16 @@ def run_device(args, rank, world, local_rank):
                              "31.4 TFLOP/s on this part (scripts/dmma_rate.py, 8 warps/SM)",
                 "peak_source": "DMMA.8x8x4 issue-rate microbenchmark run in this process (carc_dmma_peak); "
                                "MEASURED_PEAKS.json has no FP64 figure",
-                "algorithmic_bytes": 12 * 16 * Xl * D ** 4 + 32 * n,
-                "hbm_gbs": (12 * 16 * Xl * D ** 4 + 32 * n) / (kern_ms * 1e-3) / 1e9}
+                "algorithmic_bytes": (na + nb) * 16 * Xl * D ** 4 + 32 * n,
+                "hbm_gbs": ((na + nb) * 16 * Xl * D ** 4 + 32 * n) / (kern_ms * 1e-3) / 1e9}
 
     cpu = None
     if world == 1 and not args.no_cpu:
-        xs = pick_cpu_sample(D, X)
-        g, s, threads = cpu_matvec_sample(D, d, terms, xs)
+        xs = pick_cpu_sample(D, X, len(terms))
+        g, s, threads = cpu_matvec_sample(D, d, term_table_cpu(args.model), xs)
         cpu = {"value": g, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "T=9 TFIM terms, D=%d, X slab of %d of %d, %.1f s, oracle.dense.stage3_multiply_joined "
-                         "(NumPy tensordot -> BLAS zgemm)" % (D, xs, X, s)}
+               "sample": "T=%d %s terms, D=%d, X slab of %d of %d, %.1f s, oracle.dense.stage3_multiply_joined "
+                         "(NumPy tensordot -> BLAS zgemm)" % (len(terms), args.model, D, xs, X, s)}
 
     sweep = None
     if world == 1 and not args.no_sweep:
@@ -352,7 +398,7 @@ def run_device(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "complex128 (f64)", "data": "synthetic",
-        "config": workload_config(args, X),
+        "config": workload_config(args, X, len(terms)),
         "clocks": clocks,
         "e2e": {"value": flops / (e2e_ms / args.steps * 1e-3) / 1e9, "unit": UNIT,
                 "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n,
@@ -403,6 +449,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--D", type=int, default=8)
     ap.add_argument("--chi", type=int, default=16)
+    ap.add_argument("--model", default="tfim", choices=["tfim", "heisenberg"],
+                    help="which Hamiltonian's sparse term structure to benchmark (T = 9 / 20 terms)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sweep", action="store_true", help="skip the seconds-per-sweep-iteration section")
     ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"], help="N > 1: how partial outputs are summed")
