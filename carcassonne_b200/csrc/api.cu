@@ -143,7 +143,7 @@ int carc_zgemm_tab(int opA, int opB, int64_t M, int64_t N, int64_t K, const doub
 // ---------------------------------------------------------------------------------------------------
 int carc_operator_create(carc_operator** op, int P, int Q, int R, int Sd, int d) {
   CARC_REQUIRE(op != nullptr, CARC_ERR_VALUE, "operator_create: null handle pointer");
-  CARC_REQUIRE(P > 0 && Q > 0 && R > 0 && Sd > 0 && d > 0 && d <= 4, CARC_ERR_VALUE,
+  CARC_REQUIRE(P > 0 && Q > 0 && R > 0 && Sd > 0 && d > 0 && d <= 8, CARC_ERR_VALUE,
                "operator_create: invalid dimensions P=%d Q=%d R=%d S=%d d=%d", P, Q, R, Sd, d);
   keep_pool_memory();
   carc_operator* o = new carc_operator();
@@ -161,7 +161,7 @@ int carc_operator_add_term(carc_operator* op, const void* A, const void* B, int6
   t.B = (const cplx*)B;
   t.X = X;
   t.has_op = O_host != nullptr;
-  for (int i = 0; i < 16; ++i) t.op[i] = make_double2(0.0, 0.0);
+  for (int i = 0; i < 64; ++i) t.op[i] = make_double2(0.0, 0.0);
   if (O_host)
     for (int i = 0; i < op->d * op->d; ++i) t.op[i] = make_double2(O_host[2 * i], O_host[2 * i + 1]);
   else

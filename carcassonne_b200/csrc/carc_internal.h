@@ -58,7 +58,7 @@ struct Stage3Term {
   const cplx* B;   // [X, R, S]   (pre-joined stage-2 half 1: [(y' x'), D2*, D3*, D2, D3])
   int64_t X;
   int has_op;      // 0: identity on the physical leg
-  cplx op[16];     // row-major d x d site operator O[s', s]
+  cplx op[64];     // row-major d x d site operator O[s', s], d <= 8
 };
 struct Stage3Group {
   const cplx* center;   // the tensor every term of the star shares: B (kind 0) or A (kind 1)

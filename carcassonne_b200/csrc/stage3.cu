@@ -528,16 +528,16 @@ int s3_unfused(const Stage3Term* terms, int nterms, int P, int Q, int R, int S, 
   const cplx one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0);
   const int64_t n = (int64_t)P * R * d;
   const int64_t wsize = (int64_t)Q * S * d;
-  CARC_REQUIRE(ws_elems >= wsize + (int64_t)P * S * d, CARC_ERR_VALUE, "stage3: workspace too small");
+  CARC_REQUIRE(ws_elems >= wsize + (int64_t)P * S * d + 64, CARC_ERR_VALUE, "stage3: workspace too small");
   cplx* W = ws;
   cplx* T = ws + wsize;
-  const int64_t tcap = ws_elems - wsize;
+  cplx* opdev = ws + (ws_elems - 64);   // the last 64 elements hold the d x d site operator of the current term
+  const int64_t tcap = ws_elems - 64 - wsize;
   CARC_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(cplx) * n, stream));
   for (int t = 0; t < nterms; ++t) {
     const cplx* w = v;
     if (terms[t].has_op) {
       // W[(Q S), s'] = sum_s v[(Q S), s] * O[s', s]
-      cplx* opdev = T;  // borrow the head of T for the d x d operator
       CARC_CHECK_CUDA(cudaMemcpyAsync(opdev, terms[t].op, sizeof(cplx) * d * d, cudaMemcpyHostToDevice, stream));
       int rc = zgemm(OP_N, OP_T, (int64_t)Q * S, d, d, one, v, d, opdev, d, zero, W, nullptr, nullptr, 1, 0, 0, 0, stream);
       if (rc) return rc;
@@ -578,7 +578,7 @@ int64_t stage3_workspace_elems(int nterms, int P, int Q, int R, int S, int d, in
   int64_t per_x = (int64_t)P * S * d;
   int64_t t = std::min<int64_t>(Xmax * per_x, std::max<int64_t>(per_x, (64ll << 20) / 16));
   int64_t unfused = (int64_t)Q * S * d + t;
-  return std::max(fused, unfused);
+  return std::max(fused, unfused) + 64;
 }
 
 // Decompose the term list -- a bipartite multigraph between half-0 tensors A and half-1 tensors B -- into stars:
@@ -665,7 +665,7 @@ double stage3_executed_flops(const Stage3Plan* plan, int P, int Q, int R, int S,
 int stage3_apply(const Stage3Plan* plan, int P, int Q, int R, int S, int d, const cplx* v, cplx* out, cplx* workspace,
                  int64_t workspace_elems, int force_path, cudaStream_t stream, Comm* comm) {
   const int nterms = (int)plan->terms.size();
-  CARC_REQUIRE(P > 0 && Q > 0 && R > 0 && S > 0 && d > 0 && d <= 4, CARC_ERR_VALUE, "stage3: invalid dimensions");
+  CARC_REQUIRE(P > 0 && Q > 0 && R > 0 && S > 0 && d > 0 && d <= 8, CARC_ERR_VALUE, "stage3: invalid dimensions");
   const int64_t n = (int64_t)P * R * d;
   if (nterms == 0) {
     CARC_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(cplx) * n, stream));
