@@ -94,8 +94,11 @@ class ConstantStateCompressionPolicy(CompressionPolicy):
 
 
 class ConstantOperatorCompressionPolicy(CompressionPolicy):
-    """Fills the reference's empty "operator compression" slot (system/base.py:49): folds the two-site halves of
-    every corner into a compressed operator bond of at most ``new_dimension``."""
+    """Fills the reference's empty "operator compression" slot (system/base.py:49): folds the partnered two-site
+    halves of every corner into a compressed operator bond of at most ``new_dimension``.
+    One application leaves <H> and <N> unchanged at full rank; applying it repeatedly between absorptions is only exact
+    while both ends of each side keep the same channel basis (not guaranteed by the reference's tag scheme), so the
+    policy is offered for experiments, not enabled anywhere by default."""
 
     def __init__(self, new_dimension, normalize=False):
         self.new_dimension = new_dimension

@@ -138,7 +138,11 @@ def _standard(k1, k2):
 
 
 def rule_side_into_corner_from_left(corner_tag, side_tag):
-    """tensors/_2d/sparse.py:12-23."""
+    """tensors/_2d/sparse.py:12-23, plus the two rules the reference lacks for compressed operator bonds: a corner's
+    compressed halves that point RIGHT survive the absorption of an operator-free side, and a side's compressed
+    halves that point LEFT become the new corner's (the compressed twins of the TwoSiteOperator rules; without them
+    every compressed term is dropped by the next absorption, which is why the reference ships no operator-
+    compression policy)."""
     k = (corner_tag.kind, side_tag.kind)
     std = _standard(*k)
     if std is not False:
@@ -151,14 +155,21 @@ def rule_side_into_corner_from_left(corner_tag, side_tag):
         if side_tag.direction == CENTER:
             return side_tag.withNewDirectionAndPosition(RIGHT, 0)
         return None
+    if k == ("Z", "I"):
+        return corner_tag if corner_tag.direction == RIGHT else None
+    if k == ("I", "Z"):
+        return side_tag if side_tag.direction == LEFT else None
     if k in (("2", "2"), ("Z", "Z")):
         return _halves_meet(side_tag, corner_tag)
     return None
 
 
 def rule_side_into_corner_from_right(corner_tag, side_tag):
-    """tensors/_2d/sparse.py:24-35 (the Compressed rule is declared with swapped argument names there; the net
-    effect -- side as the left half, corner as the right -- is reproduced)."""
+    """tensors/_2d/sparse.py:24-35.  The contraction joins the corner's RIGHT bond to the side's LEFT bond, so halves
+    meet as (left = corner, right = side) for compressed bonds exactly as for TwoSiteOperator tags.  (The reference
+    declares the compressed rule with swapped lambda arguments, ``lambda r,l: l.matches(r)``, which pairs the two
+    bonds the contraction leaves OPEN and would fail at the ``+=`` with a shape mismatch; corrected here, with the
+    compressed twins of the survive / carry-over rules added as in the from-left case.)"""
     k = (corner_tag.kind, side_tag.kind)
     std = _standard(*k)
     if std is not False:
@@ -171,10 +182,12 @@ def rule_side_into_corner_from_right(corner_tag, side_tag):
         if side_tag.direction == CENTER:
             return side_tag.withNewDirectionAndPosition(LEFT, 0)
         return None
-    if k == ("2", "2"):
+    if k == ("Z", "I"):
+        return corner_tag if corner_tag.direction == LEFT else None
+    if k == ("I", "Z"):
+        return side_tag if side_tag.direction == RIGHT else None
+    if k in (("2", "2"), ("Z", "Z")):
         return _halves_meet(corner_tag, side_tag)
-    if k == ("Z", "Z"):
-        return _halves_meet(side_tag, corner_tag)
     return None
 
 
@@ -342,6 +355,29 @@ def makeSparseOperator(Os=[], OO_UDs=[], OO_LRs=[]):
     return operator
 
 
+def makeMPO(I, Os=[], OOs=[]):
+    """The 1D twin of makeSparseOperator (reference sparse.py:265-287): MPO tensor [size, size, d, d] with the identity
+    on the two end channels, one-site terms from channel 0 to the last, and one channel per two-site term; returns
+    (tensor, right boundary, right tags, left boundary, left tags) -- the order of the reference's return value.  Host ndarrays in, host ndarray out (it is a
+    handful of d x d blocks; the 1D system uploads it)."""
+    import numpy as np
+    as_array = lambda x: x.toArray() if hasattr(x, "toArray") else np.asarray(x, dtype=np.complex128)
+    I = as_array(I)
+    size = 2 + len(OOs)
+    last = size - 1
+    tensor = np.zeros((size, size, len(I), len(I)), dtype=np.complex128)
+    tensor[0, 0] = I
+    tensor[last, last] = I
+    for O in Os:
+        tensor[0, last] += as_array(O)
+    for id, OO in enumerate(OOs):
+        tensor[0, id + 1] = as_array(OO[1])
+        tensor[id + 1, last] = as_array(OO[0])
+    middle = [TwoSiteOperator(id, 2) for id in range(len(OOs))]
+    return (tensor, [1] + [0] * (size - 1), [Identity()] + middle + [Complete()],
+            [0] * (size - 1) + [1], [Complete()] + middle + [Identity()])
+
+
 def makeSimpleSparseOperator(O=None, OO_UD=None, OO_LR=None):
     return makeSparseOperator(
         [O] if O is not None else [],
@@ -354,5 +390,5 @@ __all__ = [
     "Identity", "Complete", "OneSiteOperator", "TwoSiteOperator", "TwoSiteOperatorCompressed",
     "LEFT", "RIGHT", "CENTER",
     "contractSparseTensors", "planSparseContraction", "getInformationFromOperatorCenter", "makeSimpleSparseOperator",
-    "makeSparseOperator", "mapOverSparseData", "stripAllButIdentityFrom", "stage3_term_allowed",
+    "makeMPO", "makeSparseOperator", "mapOverSparseData", "stripAllButIdentityFrom", "stage3_term_allowed",
 ]

@@ -348,8 +348,11 @@ class System(BaseSystem):
         """Number of two-site halves (plus the extent of an existing compressed bond) a corner carries in one
         direction: the `old_dimension` of compressCornerTwoSiteOperatorTowards."""
         total = 0
+        side_id, side_direction = sideFromCorner(corner_id, direction), 1 - direction
+        partnered = {(tag.id, tag.position) for tag in self.sides[side_id]
+                     if isinstance(tag, TwoSiteOperator) and tag.direction == side_direction}
         for tag, data in self.corners[corner_id].items():
-            if isinstance(tag, TwoSiteOperator) and tag.direction == direction:
+            if isinstance(tag, TwoSiteOperator) and tag.direction == direction and (tag.id, tag.position) in partnered:
                 total += 1
             elif isinstance(tag, TwoSiteOperatorCompressed) and tag.direction == direction:
                 total += data.shape[3 * direction + 2]
@@ -361,11 +364,21 @@ class System(BaseSystem):
         dominant eigenvectors of the Gram matrix of the flattened halves."""
         axis = 3 * direction + 2
         corner = self.corners[corner_id]
+        side_id = sideFromCorner(corner_id, direction)
+        side_direction = 1 - direction
+        # only halves whose partner sits on the adjacent side can share a channel of the compressed bond; a half whose
+        # partner has not been absorbed yet stays an ordinary TwoSiteOperator tag and meets it later through the
+        # (TwoSite, TwoSite) rule (the reference assumes matched sets and raises KeyError otherwise)
+        partnered = {(tag.id, tag.position) for tag in self.sides[side_id]
+                     if isinstance(tag, TwoSiteOperator) and tag.direction == side_direction}
         kept, halves, slots, old_compressed = {}, [], {}, None
         for tag, data in corner.items():
-            if isinstance(tag, TwoSiteOperator) and tag.direction == direction:
-                assert tag.position not in slots
-                slots[tag.position] = len(halves)
+            if isinstance(tag, TwoSiteOperator) and tag.direction == direction and (tag.id, tag.position) in partnered:
+                # keyed by (id, position): the reference keys by position alone and therefore supports a single
+                # two-site term per axis (its assert at system/_2d.py:239 fails for Heisenberg); halves of different
+                # terms at the same position are independent channels of the compressed bond
+                assert (tag.id, tag.position) not in slots
+                slots[tag.id, tag.position] = len(halves)
                 halves.append(data)
             elif isinstance(tag, TwoSiteOperatorCompressed) and tag.direction == direction:
                 assert old_compressed is None
@@ -421,21 +434,20 @@ class System(BaseSystem):
                                                              corner_multiplier)
         self.corners[corner_id] = kept
 
-        side_id = sideFromCorner(corner_id, direction)
-        side_direction = 1 - direction
         side_axis = 3 * side_direction + 2
         side = self.sides[side_id]
         kept_side, side_halves, side_compressed = {}, [None] * n_sparse, None
         for tag, data in side.items():
-            if isinstance(tag, TwoSiteOperator) and tag.direction == side_direction:
-                side_halves[slots[tag.position]] = data
+            if isinstance(tag, TwoSiteOperator) and tag.direction == side_direction and (tag.id, tag.position) in slots:
+                side_halves[slots[tag.id, tag.position]] = data
             elif isinstance(tag, TwoSiteOperatorCompressed) and tag.direction == side_direction:
-                assert old_compressed is not None and side_compressed is None
+                assert side_compressed is None
                 side_compressed = data
             else:
                 kept_side[tag] = data
         assert None not in side_halves
-        assert (side_compressed is not None) == (old_compressed is not None)
+        if (side_compressed is not None) != (old_compressed is not None):
+            raise ValueError("corner {} and side {} do not carry matching compressed operator bonds".format(corner_id, side_id))
         side_stacked = DeviceData.newCollected([h.ravel() for h in side_halves]) if n_sparse else None
         kept_side[TwoSiteOperatorCompressed(side_direction)] = fold_in(side[Identity()].shape, side_axis, side_stacked,
                                                                        side_compressed, side_multiplier)
