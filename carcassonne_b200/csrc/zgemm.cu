@@ -258,7 +258,8 @@ __global__ void __launch_bounds__(1024, 1) dmma_rate_kernel(double* out, int ite
 
 // the same with distinct A / B operand registers per instruction (4 x 4 outer product of fragments, the register
 // traffic a real GEMM inner loop has), to separate issue-rate limits from operand-fetch limits
-__global__ void __launch_bounds__(256, 1) dmma_rate_distinct_kernel(double* out, int iters) {
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) dmma_rate_distinct_kernel(double* out, int iters) {
   double a[4], b[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -295,7 +296,8 @@ int dmma_rate(int iters, int warps, int chains, double* tflops_out, cudaStream_t
   float best = 1e30f;
   for (int rep = 0; rep < 4; ++rep) {
     CARC_CHECK_CUDA(cudaEventRecord(e0, stream));
-    if (chains >= 100) dmma_rate_distinct_kernel<<<148, warps * 32, 0, stream>>>(buf, iters);
+    if (chains >= 100 && warps <= 8) dmma_rate_distinct_kernel<256><<<148, warps * 32, 0, stream>>>(buf, iters);
+    else if (chains >= 100) dmma_rate_distinct_kernel<512><<<148, warps * 32, 0, stream>>>(buf, iters);
     else if (chains <= 2) dmma_rate_kernel<2><<<148, warps * 32, 0, stream>>>(buf, iters);
     else if (chains <= 4) dmma_rate_kernel<4><<<148, warps * 32, 0, stream>>>(buf, iters);
     else if (chains <= 8) dmma_rate_kernel<8><<<148, warps * 32, 0, stream>>>(buf, iters);

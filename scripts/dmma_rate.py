@@ -4,7 +4,7 @@ import torch
 torch.cuda.init()
 from carcassonne_b200 import _lib
 tf = C.c_double()
-for warps in (4, 8):
+for warps in (4, 8, 12, 16):
     _lib.check(_lib.lib.carc_dmma_rate(4000, warps, 100, C.byref(tf), None))
     print('warps/SM %d, 16 accumulators, 4x4 distinct operands: %.1f TFLOP/s' % (warps, tf.value))
 for warps in (8,):
