@@ -34,8 +34,9 @@ namespace carc {
 
 namespace {
 
-constexpr int SBW = 16;        // S-block width (two 8-wide chunks)
-constexpr int BSTR = SBW + 1;  // row stride of the staged B block (odd -> conflict-free paired loads)
+// S-block width = 8 * CH columns (CH = 1 or 2 chunks of 8); the staged B block has an odd row stride (SBW + 1) so that
+// the paired fragment loads are conflict-free.  CH = 1 halves the T / U register tiles, which lets shapes with 5-6 row
+// tiles (D = 6) run two consumer groups per CTA without spilling.
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct S3Params {
@@ -52,11 +53,12 @@ struct S3Params {
 // threads per CTA are a multiple of 128 (one warp per sub-partition): 2 / 3 warps per sub-partition leave
 // 255 / 170 registers per thread (4 warps would leave 128, which spills the accumulator tiles)
 __host__ __device__ constexpr int s3_max_threads(int nrt) {
-  return nrt >= 5 ? 256 : 384;
+  return nrt >= 7 ? 256 : 384;
 }
 
-template <int NRT, int DP>
+template <int NRT, int DP, int CH>
 __global__ void __launch_bounds__(s3_max_threads(NRT), 1) stage3_kernel(const S3Params p) {
+  constexpr int SBW = 8 * CH, BSTR = SBW + 1;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r = lane >> 2, c = lane & 3;
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(s3_max_threads(NRT), 1) stage3_kernel(const S3
     // consumer: one iteration per (term group, x): the first products of the group's terms accumulate in T, the
     // second product follows in straight-line code
     while (next_item(cc)) {
-      CTile T[2][DP];
+      CTile T[CH][DP];
       const int first = groupFirst[cc.gi], cnt = groupCount[cc.gi];
       const int kind = groupKind[cc.gi];
       {
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(s3_max_threads(NRT), 1) stage3_kernel(const S3
         mbar_wait(b + (2 * slot) * 8, (itA / p.nstA) & 1);
         const uint32_t a_base = ring + slot * p.slotA_bytes + a_lane_off;
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch)
+        for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
           for (int s = 0; s < DP; ++s) T[ch][s].zero();
 #pragma unroll 2
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(s3_max_threads(NRT), 1) stage3_kernel(const S3
           const cplx a0 = eswap ? x1 : x0;
           const cplx a1 = eswap ? x0 : x1;
 #pragma unroll
-          for (int ch = 0; ch < 2; ++ch) {
+          for (int ch = 0; ch < CH; ++ch) {
 #pragma unroll
             for (int s = 0; s < DP; ++s) {
               const uint32_t va = v_base + (uint32_t)((((s * SBW + ch * 8) * QS) + kp * 8) * 16);
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(s3_max_threads(NRT), 1) stage3_kernel(const S3
         }
         if (has_op) {
 #pragma unroll
-          for (int ch = 0; ch < 2; ++ch) {
+          for (int ch = 0; ch < CH; ++ch) {
             CTile U[DP];
 #pragma unroll
             for (int s = 0; s < DP; ++s) {
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(s3_max_threads(NRT), 1) stage3_kernel(const S3
           mbar_wait(b + (2 * slot) * 8, (itA / p.nstA) & 1);
           const uint32_t a_base = ring + slot * p.slotA_bytes + a_lane_off;
 #pragma unroll
-          for (int ch = 0; ch < 2; ++ch) {
+          for (int ch = 0; ch < CH; ++ch) {
             CTile U[DP];
 #pragma unroll
             for (int s = 0; s < DP; ++s) U[s].zero();
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(s3_max_threads(NRT), 1) stage3_kernel(const S3
           mbar_wait(b + (2 * p.nstA + 2 * slot) * 8, (itB / p.nstB) & 1);
           const uint32_t b_base = ring + p.nstA * p.slotA_bytes + slot * p.slotB_bytes + b_lane_off;
 #pragma unroll
-          for (int ch = 0; ch < 2; ++ch) {
+          for (int ch = 0; ch < CH; ++ch) {
 #pragma unroll
             for (int rt = 0; rt < NRT; ++rt) {
               const uint32_t ba = b_base + (uint32_t)(((rt * 8) * BSTR + ch * 8) * 16);
@@ -368,7 +370,7 @@ __global__ void __launch_bounds__(s3_max_threads(NRT), 1) stage3_kernel(const S3
           mbar_wait(b + (2 * p.nstA + 2 * slot) * 8, (itB / p.nstB) & 1);
           const uint32_t b_base = ring + p.nstA * p.slotA_bytes + slot * p.slotB_bytes + b_lane_off;
 #pragma unroll
-          for (int ch = 0; ch < 2; ++ch) {
+          for (int ch = 0; ch < CH; ++ch) {
             CTile W[DP];
 #pragma unroll
             for (int s = 0; s < DP; ++s) {
@@ -449,7 +451,7 @@ __global__ void __launch_bounds__(256) s3_reduce_kernel(const cplx* __restrict__
 }
 
 struct S3Config {
-  int NPT, NRT, Q8, NSB, NSL, G, nstA, nstB;
+  int NPT, NRT, Q8, NSB, NSL, G, nstA, nstB, CH;
   uint32_t slotA, slotB, ops_off, hasop_off, tab_off, vt_off, ring_off, total;
   int threads, slots;
 };
@@ -462,6 +464,9 @@ bool s3_configure(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, S
   k.NPT = (P + 7) / 8;
   k.NRT = (R + 7) / 8;
   k.Q8 = (Q + 7) / 8;
+  // two chunks per S block unless the shape has 5-6 row tiles (then one chunk: see the kernel's note on CH)
+  k.CH = (k.NRT == 5 || k.NRT == 6) ? 1 : 2;
+  const int SBW = 8 * k.CH, BSTR = SBW + 1;
   k.NSB = (S + SBW - 1) / SBW;
   const int maxwarps = s3_max_threads(k.NRT) / 32;
   if (k.NPT > maxwarps) return false;
@@ -506,17 +511,17 @@ bool s3_configure(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, S
   return false;
 }
 
-template <int NRT>
+template <int NRT, int CH>
 int s3_launch(const S3Params& p, const S3Config& k, cudaStream_t stream) {
   static bool configured[16] = {false};
   int dev = 0;
   CARC_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev < 16 && !configured[dev]) {
     CARC_CHECK_CUDA(
-        cudaFuncSetAttribute(stage3_kernel<NRT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        cudaFuncSetAttribute(stage3_kernel<NRT, 2, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     configured[dev] = true;
   }
-  stage3_kernel<NRT, 2><<<k.NSB * k.NSL, k.threads, k.total, stream>>>(p);
+  stage3_kernel<NRT, 2, CH><<<k.NSB * k.NSL, k.threads, k.total, stream>>>(p);
   CARC_CHECK_CUDA(cudaGetLastError());
   return CARC_OK;
 }
@@ -696,14 +701,14 @@ int stage3_apply(const Stage3Plan* plan, int P, int Q, int R, int S, int d, cons
   p.partial = workspace;
   int rc;
   switch (k.NRT) {
-    case 1: rc = s3_launch<1>(p, k, stream); break;
-    case 2: rc = s3_launch<2>(p, k, stream); break;
-    case 3: rc = s3_launch<3>(p, k, stream); break;
-    case 4: rc = s3_launch<4>(p, k, stream); break;
-    case 5: rc = s3_launch<5>(p, k, stream); break;
-    case 6: rc = s3_launch<6>(p, k, stream); break;
-    case 7: rc = s3_launch<7>(p, k, stream); break;
-    default: rc = s3_launch<8>(p, k, stream); break;
+    case 1: rc = s3_launch<1, 2>(p, k, stream); break;
+    case 2: rc = s3_launch<2, 2>(p, k, stream); break;
+    case 3: rc = s3_launch<3, 2>(p, k, stream); break;
+    case 4: rc = s3_launch<4, 2>(p, k, stream); break;
+    case 5: rc = s3_launch<5, 1>(p, k, stream); break;
+    case 6: rc = s3_launch<6, 1>(p, k, stream); break;
+    case 7: rc = s3_launch<7, 2>(p, k, stream); break;
+    default: rc = s3_launch<8, 2>(p, k, stream); break;
   }
   if (rc) return rc;
   // multi-GPU: the slot sum and the sum over ranks are one kernel reading the peers' exchange buffers over NVLink
