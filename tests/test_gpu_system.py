@@ -190,6 +190,52 @@ def test_system_walk(dd, name):
     assert abs(n - g["after_ct.normalization"]) <= 1e-10 * abs(g["after_ct.normalization"])
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_random_system_identities(dd, seed):
+    """reference tests/test_system.py:222-275 on System.newRandom (draws from `random` and the NumPy stream like the
+    reference): after a random walk the expectation / normalization multipliers equal their explicit matrices, the
+    normalization multiplier equals the submatrix (x) identity, and the consistency asserts hold."""
+    from carcassonne_b200.system import System
+    random.seed(seed)
+    np.random.seed(seed)
+    s = System.newRandom(maximum_dimension=3)
+    s.assertDimensionsAreConsistent()
+    s.assertNormalizationIsHermitian()
+    s.assertHasNoNaNs()
+    for _ in range(random.randint(0, 3)):
+        s.contractUnnormalizedTowards(random.randint(0, 3))
+    s.assertDimensionsAreConsistent()
+    H, N = s.formExpectationAndNormalizationMultipliers()
+    shape = s.state_center_data.shape
+    v = dd.newRandom(*shape)
+    hv, nv = H(v).toArray(), N(v).toArray()
+    hm, nm = H.formMatrix().toArray(), N.formMatrix().toArray()
+    assert H.shape == hm.shape == nm.shape
+    assert relerr((hm @ v.toArray().ravel()).reshape(shape), hv) < 1e-11
+    assert relerr((nm @ v.toArray().ravel()).reshape(shape), nv) < 1e-11
+    assert relerr(s.formNormalizationMultiplier()(v).toArray(), nv) < 1e-11
+    sub = s.formNormalizationSubmatrix().toArray()
+    assert relerr(np.kron(sub, np.eye(shape[4])), nm) < 1e-11
+    # the oracle on the same tensors
+    from oracle import tags
+    from oracle.system import System as OSystem
+    from carcassonne_b200.sparse import Complete, Identity, OneSiteOperator, TwoSiteOperator, TwoSiteOperatorCompressed
+
+    def back(t):
+        if isinstance(t, Identity): return tags.I
+        if isinstance(t, Complete): return tags.C
+        if isinstance(t, OneSiteOperator): return tags.ONE
+        if isinstance(t, TwoSiteOperator): return tags.two(t.id, t.direction, t.position)
+        return tags.zipd(t.direction)
+
+    host = lambda d: {back(t): x.toArray() for t, x in d.items()}
+    o = OSystem([host(c) for c in s.corners], [host(x) for x in s.sides], s.state_center_data.toArray(),
+                host(s.operator_center_tensor))
+    Ho, No = o.multipliers()
+    assert relerr(hv, Ho(v.toArray())) < 1e-11
+    assert relerr(nv, No(v.toArray())) < 1e-11
+
+
 def test_stage3_terms_tfim(dd):
     g = load("walk_tfim_chi2_D2")
     corners, sides, center = system_parts(g, "walked")
@@ -316,6 +362,9 @@ def test_lu_and_gmres(dd, n):
     spd = a.conj().T @ a + np.eye(n)
     x = _gmres_dense(dd.fromArray(spd), dd.fromArray(b), rtol=1e-10).toArray()
     assert relerr(spd @ x, b) < 1e-8
+    from carcassonne_b200.compression import _cg_dense
+    x, iterations, residual = _cg_dense(dd.fromArray(spd), dd.fromArray(b), rtol=1e-10)
+    assert relerr(spd @ x.toArray(), b) < 1e-8 and iterations >= 1 and residual <= 1e-9 * np.linalg.norm(b) + 1e-300
 
 
 def _physical_system(dd, J=0.5, grow=True):
