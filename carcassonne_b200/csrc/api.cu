@@ -342,11 +342,13 @@ int carc_lu_factor(void* A, int n, void* piv_dev, int* singular_out, void* strea
   keep_pool_memory();
   cudaStream_t st = S(stream);
   void* scratch = nullptr;
-  CARC_CHECK_CUDA(cudaMallocAsync(&scratch, 64, st));
-  int rc = carc::lu_factor((cplx*)A, n, (int*)piv_dev, (int*)((char*)scratch + 32), (cplx*)scratch, st);
+  const size_t sbytes = carc::lu_scratch_bytes() + 64;
+  CARC_CHECK_CUDA(cudaMallocAsync(&scratch, sbytes, st));
+  int* singular_dev = (int*)((char*)scratch + carc::lu_scratch_bytes());
+  int rc = carc::lu_factor((cplx*)A, n, (int*)piv_dev, singular_dev, (cplx*)scratch, st);
   int singular = 0;
   if (!rc) {
-    CARC_CHECK_CUDA(cudaMemcpyAsync(&singular, (char*)scratch + 32, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CARC_CHECK_CUDA(cudaMemcpyAsync(&singular, singular_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
     CARC_CHECK_CUDA(cudaStreamSynchronize(st));
   }
   cudaFreeAsync(scratch, st);

@@ -103,6 +103,7 @@ int lu_solve_fast(const cplx* LU, int n, const int* piv, const cplx* inv, cplx* 
 int gmres(const LinOp& A, const cplx* b, cplx* x, int64_t n, double rtol, int restart, int maxiter, cplx* work,
           void* state_dev, int* iters_out, double* resid_out, cudaStream_t stream);
 size_t gmres_state_bytes();
+size_t lu_scratch_bytes();
 int cg(const LinOp& A, const cplx* b, cplx* x, int64_t n, double rtol, int maxiter, cplx* work, void* state_dev,
        int* iters_out, double* resid_out, cudaStream_t stream);
 size_t cg_state_bytes();

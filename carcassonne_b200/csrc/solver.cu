@@ -9,6 +9,7 @@
 // long (128 KiB at D = 8) and live in L2, so these kernels are latency-bound and one CTA avoids grid-wide
 // synchronisation; the k x k non-Hermitian eigenproblem (scipy.linalg.eig -> zgeev in the reference) is solved
 // by thread 0 of the same kernel with a shifted QR iteration.
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include <vector>
@@ -77,89 +78,58 @@ __global__ void __launch_bounds__(256) zgemv_kernel(const cplx* __restrict__ M, 
   }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// LU with partial pivoting, row-major, in place.  Per column: (1) pivot search + whole-row swap + reciprocal,
-// (2) scale the column and rank-1 update of the rest of the panel; per panel: triangular solve for the U block row
-// and one DMMA GEMM for the trailing matrix.
-__global__ void __launch_bounds__(1024) lu_pivot_kernel(cplx* __restrict__ A, int n, int j, int* __restrict__ piv,
-                                                        cplx* __restrict__ inv_pivot, int* __restrict__ singular) {
+
+
+
+
+// Whole-panel factorisation in ONE cooperative launch (one CTA per SM): the column steps are separated by grid-wide
+// barriers instead of kernel boundaries (two per column; a launch pair costs ~14 us end to end on this stack, a grid
+// barrier ~2 us).  Per column j: [reduce the pivot candidates tracked during the previous update; interchange rows
+// j <-> p across the whole matrix, each CTA a slice of columns] | barrier | [scale column j, rank-1 update of the
+// rest of the current 8-column sub-panel, tracking the pivot candidates of column j + 1] | barrier.  At the end of a
+// sub-panel the remaining panel columns receive the U block row (tiny triangular solve) and one rank-8 update.
+struct LuCand {
+  double val[160];
+  int idx[160];
+};
+
+__global__ void __launch_bounds__(256, 1) lu_panel_coop_kernel(cplx* __restrict__ A, int n, int j0, int nb,
+                                                               int* __restrict__ piv, int* __restrict__ singular,
+                                                               LuCand* __restrict__ cand) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
   __shared__ double s_val[32];
   __shared__ int s_idx[32];
   __shared__ int s_p;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  double best = -1.0;
-  int bi = j;
-  for (int i = j + tid; i < n; i += blockDim.x) {
-    const cplx a = A[(int64_t)i * n + j];
-    const double m = fabs(a.x) + fabs(a.y);   // LAPACK izamax uses |re| + |im|
-    if (m > best) { best = m; bi = i; }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-  }
-  if (lane == 0) { s_val[w] = best; s_idx[w] = bi; }
-  __syncthreads();
-  if (tid == 0) {
-    double b = s_val[0];
-    int p = s_idx[0];
-    for (int i = 1; i < (int)(blockDim.x >> 5); ++i)
-      if (s_val[i] > b || (s_val[i] == b && s_idx[i] < p)) { b = s_val[i]; p = s_idx[i]; }
-    s_p = p;
-    piv[j] = p;
-    if (!(b > 0.0)) *singular = 1;
-  }
-  __syncthreads();
-  const int p = s_p;
-  if (p != j) {
-    for (int c = tid; c < n; c += blockDim.x) {
-      const cplx a = A[(int64_t)j * n + c], b = A[(int64_t)p * n + c];
-      A[(int64_t)j * n + c] = b;
-      A[(int64_t)p * n + c] = a;
-    }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    const cplx d = A[(int64_t)j * n + j];
-    *inv_pivot = (d.x != 0.0 || d.y != 0.0) ? cdiv(make_double2(1.0, 0.0), d) : make_double2(0.0, 0.0);
-  }
-}
-
-// rows i > j: l = A[i][j] * inv; A[i][j] = l; A[i][c] -= l * A[j][c] for j < c < c_end.  32 columns x 8 rows per CTA pass.
-__global__ void __launch_bounds__(256) lu_update_kernel(cplx* __restrict__ A, int n, int j, int c_end,
-                                                        const cplx* __restrict__ inv_pivot) {
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const cplx inv = *inv_pivot;
-  for (int i = j + 1 + blockIdx.x * 8 + ty; i < n; i += gridDim.x * 8) {
-    cplx* row = A + (int64_t)i * n;
-    const cplx l = cmul(row[j], inv);
-    for (int c = j + 1 + tx; c < c_end; c += 32) row[c] = csub(row[c], cmul(l, A[(int64_t)j * n + c]));
-    __syncwarp();
-    if (tx == 0) row[j] = l;
-  }
-}
-
-// Sub-panel factorisation: columns [s0, s0 + w) (w <= 8) in ONE launch of one CTA -- per column a pivot search,
-// a whole-row interchange, the scaling of the column and the rank-1 update of the rest of the sub-panel, separated
-// by __syncthreads instead of kernel boundaries.  Each thread owns the rows i = c + 1 + tid + 1024 q.
-__global__ void __launch_bounds__(1024) lu_subpanel_kernel(cplx* __restrict__ A, int n, int s0, int w,
-                                                           int* __restrict__ piv, int* __restrict__ singular) {
-  __shared__ double s_val[32];
-  __shared__ int s_idx[32];
-  __shared__ int s_p;
-  __shared__ cplx s_inv;
+  __shared__ cplx s_U[8][64];
+  __shared__ cplx s_L[8][8];
   __shared__ cplx s_row[8];
-  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
-  const int c_end = s0 + w;
-  for (int c = s0; c < c_end; ++c) {
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int pe = j0 + nb;
+  const int nctas = gridDim.x, NT = blockDim.x, NW = blockDim.x >> 5;
+
+  auto publish = [&](double best, int bi) {   // block argmax of lane-0 candidates -> cand[blockIdx]
+    if (tx == 0) { s_val[ty] = best; s_idx[ty] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      double b = s_val[0];
+      int p = s_idx[0];
+      for (int q = 1; q < NW; ++q)
+        if (s_val[q] > b || (s_val[q] == b && s_idx[q] < p)) { b = s_val[q]; p = s_idx[q]; }
+      cand->val[blockIdx.x] = b;
+      cand->idx[blockIdx.x] = p;
+    }
+    __syncthreads();
+  };
+
+  // candidates of the first column of the panel: plain scan
+  {
     double best = -1.0;
-    int bi = c;
-    for (int i = c + tid; i < n; i += 1024) {
-      const cplx a = A[(int64_t)i * n + c];
+    int bi = 0x7fffffff;
+    for (int i = j0 + blockIdx.x * NT + tid; i < n; i += nctas * NT) {
+      const cplx a = A[(int64_t)i * n + j0];
       const double m = fabs(a.x) + fabs(a.y);
-      if (m > best) { best = m; bi = i; }
+      if (m > best || (m == best && i < bi)) { best = m; bi = i; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -167,81 +137,150 @@ __global__ void __launch_bounds__(1024) lu_subpanel_kernel(cplx* __restrict__ A,
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
     }
-    if (lane == 0) { s_val[wp] = best; s_idx[wp] = bi; }
-    __syncthreads();
-    if (tid == 0) {
-      double b = s_val[0];
-      int p = s_idx[0];
-      for (int i = 1; i < 32; ++i)
-        if (s_val[i] > b || (s_val[i] == b && s_idx[i] < p)) { b = s_val[i]; p = s_idx[i]; }
-      s_p = p;
-      piv[c] = p;
-      if (!(b > 0.0)) *singular = 1;
-    }
-    __syncthreads();
-    const int p = s_p;
-    if (p != c) {
-      for (int cc = tid; cc < n; cc += 1024) {
-        const cplx a = A[(int64_t)c * n + cc], b = A[(int64_t)p * n + cc];
-        A[(int64_t)c * n + cc] = b;
-        A[(int64_t)p * n + cc] = a;
+    publish(best, bi);
+  }
+  grid.sync();
+
+  for (int s0 = j0; s0 < pe; s0 += 8) {
+    const int w = pe - s0 < 8 ? pe - s0 : 8;
+    const int c_sub = s0 + w;
+    for (int j = s0; j < c_sub; ++j) {
+      // ---- pivot of column j from the published candidates (every CTA redundantly), row interchange
+      if (tid < 32) {
+        double b = -1.0;
+        int p = 0x7fffffff;
+        for (int q = tid; q < nctas; q += 32) {
+          const double v = cand->val[q];
+          const int idx = cand->idx[q];
+          if (v > b || (v == b && idx < p)) { b = v; p = idx; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ob = __shfl_xor_sync(0xffffffffu, b, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, p, o);
+          if (ob > b || (ob == b && oi < p)) { b = ob; p = oi; }
+        }
+        if (tid == 0) {
+          if (p == 0x7fffffff) p = j;
+          s_p = p;
+          if (blockIdx.x == 0) {
+            piv[j] = p;
+            if (!(b > 0.0)) *singular = 1;
+          }
+        }
       }
+      __syncthreads();
+      const int p = s_p;
+      if (p != j) {
+        for (int c = blockIdx.x * NT + tid; c < n; c += nctas * NT) {
+          const cplx a = A[(int64_t)j * n + c], b2 = A[(int64_t)p * n + c];
+          A[(int64_t)j * n + c] = b2;
+          A[(int64_t)p * n + c] = a;
+        }
+      }
+      grid.sync();
+      // ---- scale column j, rank-1 update inside the sub-panel, candidates of column j + 1
+      const cplx d = A[(int64_t)j * n + j];
+      const cplx inv = (d.x != 0.0 || d.y != 0.0) ? cdiv(make_double2(1.0, 0.0), d) : make_double2(0.0, 0.0);
+      const bool track = j + 1 < pe;
+      double best = -1.0;
+      int bi = 0x7fffffff;
+      // one thread per row: the <= 8 sub-panel entries of a row are contiguous, all rows' loads are in flight at once
+      const int wcols = c_sub - j - 1;
+      if (tid < wcols) s_row[tid] = A[(int64_t)j * n + j + 1 + tid];
+      __syncthreads();
+      for (int i = j + 1 + blockIdx.x * NT + tid; i < n; i += nctas * NT) {
+        cplx* row = A + (int64_t)i * n + j;
+        cplx e[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (q <= wcols) e[q] = row[q];
+        const cplx l = cmul(e[0], inv);
+        row[0] = l;
+#pragma unroll
+        for (int q = 1; q < 8; ++q)
+          if (q <= wcols) {
+            const cplx v = csub(e[q], cmul(l, s_row[q - 1]));
+            row[q] = v;
+            if (q == 1) {
+              const double m = fabs(v.x) + fabs(v.y);
+              if (m > best || (m == best && i < bi)) { best = m; bi = i; }
+            }
+          }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (j + 1 == c_sub && track) {
+        // the next pivot column lies outside this sub-panel: it is finished by the rank-w update below, which tracks
+        // the candidates itself
+      } else if (track) {
+        publish(best, bi);
+      }
+      if (j + 1 < c_sub) grid.sync();
     }
-    __syncthreads();
-    if (tid == 0) {
-      const cplx d = A[(int64_t)c * n + c];
-      s_inv = (d.x != 0.0 || d.y != 0.0) ? cdiv(make_double2(1.0, 0.0), d) : make_double2(0.0, 0.0);
+    grid.sync();
+    if (c_sub < pe) {
+      // ---- U block row of the remaining panel columns (unit-lower solve with the sub-panel's L11), rank-w update
+      const int ncols = pe - c_sub;
+      for (int e = tid; e < w * w; e += NT) s_L[e / w][e % w] = A[(int64_t)(s0 + e / w) * n + s0 + e % w];
+      for (int e = tid; e < w * ncols; e += NT) s_U[e / ncols][e % ncols] = A[(int64_t)(s0 + e / ncols) * n + c_sub + e % ncols];
+      __syncthreads();
+      if (tid < ncols) {
+        for (int r = 1; r < w; ++r) {
+          cplx acc = s_U[r][tid];
+          for (int k = 0; k < r; ++k) acc = csub(acc, cmul(s_L[r][k], s_U[k][tid]));
+          s_U[r][tid] = acc;
+        }
+      }
+      __syncthreads();
+      grid.sync();   // every CTA holds the raw block row before CTA 0 overwrites it with the solved one
+      if (blockIdx.x == 0)
+        for (int e = tid; e < w * ncols; e += NT) A[(int64_t)(s0 + e / ncols) * n + c_sub + e % ncols] = s_U[e / ncols][e % ncols];
+      double best = -1.0;
+      int bi = 0x7fffffff;
+      // one warp per row, two rows in flight per warp (their loads are independent)
+      const int rstride = nctas * NW;
+      for (int i0 = c_sub + blockIdx.x * NW + ty; i0 < n; i0 += 2 * rstride) {
+        cplx l[2][8];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int i = i0 + u * rstride;
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+            l[u][t] = (i < n && t < w) ? A[(int64_t)i * n + s0 + t] : make_double2(0.0, 0.0);
+        }
+        for (int c = tx; c < ncols; c += 32) {
+          cplx acc[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int i = i0 + u * rstride;
+            acc[u] = i < n ? A[(int64_t)i * n + c_sub + c] : make_double2(0.0, 0.0);
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int i = i0 + u * rstride;
+            if (i >= n) continue;
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+              if (t < w) acc[u] = csub(acc[u], cmul(l[u][t], s_U[t][c]));
+            A[(int64_t)i * n + c_sub + c] = acc[u];
+            if (c == 0) {
+              const double m = fabs(acc[u].x) + fabs(acc[u].y);
+              if (m > best || (m == best && i < bi)) { best = m; bi = i; }
+            }
+          }
+        }
+      }
+      publish(best, bi);
+      grid.sync();
     }
-    if (tid < c_end - c - 1) s_row[tid] = A[(int64_t)c * n + c + 1 + tid];
-    __syncthreads();
-    const cplx inv = s_inv;
-    for (int i = c + 1 + tid; i < n; i += 1024) {
-      cplx* row = A + (int64_t)i * n;
-      const cplx l = cmul(row[c], inv);
-      row[c] = l;
-      for (int cc = c + 1; cc < c_end; ++cc) row[cc] = csub(row[cc], cmul(l, s_row[cc - c - 1]));
-    }
-    __syncthreads();
   }
 }
 
-// rows r >= r0: A[r][c] -= sum_{t < w} A[r][s0 + t] A[s0 + t][c] for c in [c0, c_end); 32 columns x 8 rows per pass
-__global__ void __launch_bounds__(256) lu_rankw_kernel(cplx* __restrict__ A, int n, int s0, int w, int r0, int c0,
-                                                       int c_end) {
-  __shared__ cplx U[8][64];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int ncols = c_end - c0;
-  for (int e = threadIdx.x; e < w * ncols; e += 256) U[e / ncols][e % ncols] = A[(int64_t)(s0 + e / ncols) * n + c0 + e % ncols];
-  __syncthreads();
-  for (int r = r0 + blockIdx.x * 8 + ty; r < n; r += gridDim.x * 8) {
-    cplx* row = A + (int64_t)r * n;
-    cplx l[8];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) l[t] = t < w ? row[s0 + t] : make_double2(0.0, 0.0);
-    for (int c = tx; c < ncols; c += 32) {
-      cplx acc = row[c0 + c];
-#pragma unroll
-      for (int t = 0; t < 8; ++t)
-        if (t < w) acc = csub(acc, cmul(l[t], U[t][c]));
-      row[c0 + c] = acc;
-    }
-  }
-}
-
-// U12 = L11^-1 A12 : rows [j0, j0+nb), columns [c0, n); one thread per column, L11 (unit lower) in shared memory
-__global__ void __launch_bounds__(256) lu_trsm_kernel(cplx* __restrict__ A, int n, int j0, int nb, int c0, int c_end) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx* L = reinterpret_cast<cplx*>(smem_raw);  // nb x nb
-  for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) L[e] = A[(int64_t)(j0 + e / nb) * n + j0 + e % nb];
-  __syncthreads();
-  const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= c_end) return;
-  for (int r = 1; r < nb; ++r) {
-    cplx acc = A[(int64_t)(j0 + r) * n + c];
-    for (int k = 0; k < r; ++k) acc = csub(acc, cmul(L[r * nb + k], A[(int64_t)(j0 + k) * n + c]));
-    A[(int64_t)(j0 + r) * n + c] = acc;
-  }
-}
 
 // b <- P b (apply the recorded row interchanges in order); single thread block, sequential by nature
 __global__ void lu_permute_kernel(cplx* __restrict__ b, const int* __restrict__ piv, int n) {
@@ -320,6 +359,19 @@ __global__ void __launch_bounds__(SB) tri_invert_kernel(const cplx* __restrict__
       for (int k = i + 1; k <= j; ++k) acc = csub(acc, cmul(A[(int64_t)(j0 + i) * n + j0 + k], out[k * SB + j]));
       out[i * SB + j] = cdiv(acc, A[(int64_t)(j0 + i) * n + j0 + i]);
     }
+  }
+}
+
+// inverse of the unit-lower nb x nb block at (j0, j0) into a dense [nb][nb] buffer (one thread per column)
+__global__ void __launch_bounds__(64) unit_lower_inverse_kernel(const cplx* __restrict__ A, int n, int j0, int nb,
+                                                                cplx* __restrict__ out) {
+  const int j = threadIdx.x;
+  if (j >= nb) return;
+  for (int i = 0; i < nb; ++i) out[i * nb + j] = make_double2(0.0, 0.0);
+  for (int i = j; i < nb; ++i) {
+    cplx acc = make_double2(i == j ? 1.0 : 0.0, 0.0);
+    for (int k = j; k < i; ++k) acc = csub(acc, cmul(A[(int64_t)(j0 + i) * n + j0 + k], out[k * nb + j]));
+    out[i * nb + j] = acc;
   }
 }
 
@@ -867,52 +919,52 @@ int dense_matvec(const cplx* M, int64_t rows, int64_t cols, int64_t ld, const cp
   return CARC_OK;
 }
 
+static int g_coop_ctas = 0;
+
+size_t lu_scratch_bytes() { return sizeof(LuCand); }
+
 int lu_factor(cplx* A, int n, int* piv, int* singular_dev, cplx* scratch, cudaStream_t stream) {
+  if (g_coop_ctas == 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    CARC_CHECK_CUDA(cudaGetDevice(&dev));
+    CARC_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CARC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lu_panel_coop_kernel, 256, 0));
+    g_coop_ctas = per_sm > 0 ? sms : 0;   // one CTA per SM (fewer, larger CTAs measured slower)
+    CARC_REQUIRE(g_coop_ctas > 0, CARC_ERR_UNSUPPORTED, "lu_factor: cooperative launch unavailable");
+  }
   CARC_REQUIRE(n >= 1, CARC_ERR_VALUE, "lu_factor: n must be positive");
   const int NB = 64;
   const cplx minus_one = make_double2(-1.0, 0.0), one = make_double2(1.0, 0.0);
   CARC_CHECK_CUDA(cudaMemsetAsync(singular_dev, 0, sizeof(int), stream));
-  static bool configured[16] = {false};
-  int dev = 0;
-  CARC_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev < 16 && !configured[dev]) {
-    CARC_CHECK_CUDA(cudaFuncSetAttribute(lu_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NB * NB * 16));
-    configured[dev] = true;
-  }
+  cplx* linv = nullptr;
+  CARC_CHECK_CUDA(cudaMallocAsync((void**)&linv, sizeof(cplx) * 64 * 64, stream));
   for (int j0 = 0; j0 < n; j0 += NB) {
     const int nb = n - j0 < NB ? n - j0 : NB;
     const int pe = j0 + nb;
-    if (n <= 2048) {
-      // small matrices are launch-bound: eight columns per launch of one CTA
-      for (int s0 = j0; s0 < pe; s0 += 8) {
-        const int w = pe - s0 < 8 ? pe - s0 : 8;
-        lu_subpanel_kernel<<<1, 1024, 0, stream>>>(A, n, s0, w, piv, singular_dev);
-        const int c0 = s0 + w;
-        if (c0 < pe) {   // rest of the outer panel: U block row, then the rank-w update below it
-          lu_trsm_kernel<<<1, 256, w * w * 16, stream>>>(A, n, s0, w, c0, pe);
-          const int rows = n - c0;
-          if (rows > 0) {
-            int blocks = (rows + 7) / 8;
-            if (blocks > 148 * 4) blocks = 148 * 4;
-            lu_rankw_kernel<<<blocks, 256, 0, stream>>>(A, n, s0, w, c0, c0, pe);
-          }
-        }
-      }
-    } else {
-      // tall panels need every SM for the rank-1 updates: two launches per column
-      for (int j = j0; j < pe; ++j) {
-        lu_pivot_kernel<<<1, 1024, 0, stream>>>(A, n, j, piv, scratch, singular_dev);
-        const int rows = n - j - 1;
-        if (rows > 0) {
-          int blocks = (rows + 7) / 8;
-          if (blocks > 148 * 4) blocks = 148 * 4;
-          lu_update_kernel<<<blocks, 256, 0, stream>>>(A, n, j, pe, scratch);
-        }
-      }
+    {
+      // one cooperative launch per panel (falls back to the per-column kernels if the device refuses)
+      LuCand* cand = reinterpret_cast<LuCand*>(scratch);
+      int rows = n - j0;
+      int ctas = (rows + 7) / 8;   // (the rank-w update uses one warp per row, 8 warps per CTA)
+      if (ctas > g_coop_ctas) ctas = g_coop_ctas;
+      if (ctas < 1) ctas = 1;
+      int nn = n, jj = j0, nbb = nb;
+      void* args[] = {(void*)&A, (void*)&nn, (void*)&jj, (void*)&nbb, (void*)&piv, (void*)&singular_dev, (void*)&cand};
+      CARC_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)lu_panel_coop_kernel, dim3(ctas), dim3(256), args, 0, stream));
     }
     if (pe < n) {
       const int cols = n - pe;
-      lu_trsm_kernel<<<(cols + 255) / 256, 256, nb * nb * 16, stream>>>(A, n, j0, nb, pe, n);
+      // U12 = L11^-1 A12 as a DMMA GEMM with the explicitly inverted 64 x 64 unit-lower block (in place: each CTA
+      // reads all K rows of its own columns before its epilogue writes them; M = nb <= 128 is a single row tile)
+      unit_lower_inverse_kernel<<<1, 64, 0, stream>>>(A, n, j0, nb, linv);
+      {
+        GemmOut ou;
+        ou.m_div = n; ou.m_s1 = 0; ou.m_s0 = n;
+        ou.n_div = n; ou.n_s1 = 0; ou.n_s0 = 1;
+        int rc2 = zgemm(OP_N, OP_N, nb, cols, nb, one, linv, nb, A + (int64_t)j0 * n + pe, n, make_double2(0.0, 0.0),
+                        A + (int64_t)j0 * n + pe, &ou, nullptr, 1, 0, 0, 0, stream);
+        if (rc2) return rc2;
+      }
       // A22 -= L21 U12
       GemmOut o;
       o.m_div = n; o.m_s1 = 0; o.m_s0 = n;
@@ -922,6 +974,7 @@ int lu_factor(cplx* A, int n, int* piv, int* singular_dev, cplx* scratch, cudaSt
       if (rc) return rc;
     }
   }
+  CARC_CHECK_CUDA(cudaFreeAsync(linv, stream));
   CARC_CHECK_CUDA(cudaGetLastError());
   return CARC_OK;
 }
