@@ -425,7 +425,7 @@ def sweep_section(no_cpu):
     del A_keep[:]                      # drop the matvec environment (51 GB); torch's allocator reuses the blocks
     rows = []
     sweep_bench.device_iterations(2, 2, False)   # warm-up
-    for D, chi in ((3, 6), (4, 8), (6, 8)):
+    for D, chi in ((3, 6), (4, 8), (6, 8), (8, 8)):
         r = sweep_bench.device_iterations(chi, D, False)
         rows.append({"D": D, "chi": chi, "gpu_s_per_iteration": r["per_iteration"], "minimize_s": r["minimize"] / 4,
                      "contract_s": r["contract"] / 4, "compress_s": r["compress"] / 4,
