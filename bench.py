@@ -467,4 +467,10 @@ def main():
 
 
 if __name__ == "__main__":
+    # the JSON line must be the only thing on stdout: libraries that write to fd 1 (the NCCL version banner) go to stderr
+    sys.stdout.flush()
+    _json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_json_fd, "w")
     main()
+    sys.stdout.flush()
