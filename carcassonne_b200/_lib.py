@@ -39,6 +39,7 @@ SIGNATURES = {
     "carc_stream_synchronize": (c_int, [c_vp]),
     "carc_permute": (c_int, [c_vp, c_vp, c_int, c_i64p, c_i32p, c_int, c_int, c_vp]),
     "carc_axpby": (c_int, [c_i64, c_dp, c_vp, c_dp, c_vp, c_int, c_vp]),
+    "carc_mode_product": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp]),
     "carc_mul": (c_int, [c_i64, c_vp, c_vp, c_vp]),
     "carc_dotc": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp]),
     "carc_sumsq": (c_int, [c_i64, c_vp, c_vp, c_vp]),

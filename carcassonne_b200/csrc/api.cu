@@ -90,6 +90,10 @@ int carc_axpby(int64_t n, const double alpha[2], const void* x, const double bet
                void* stream) {
   return carc::axpby(n, C2(alpha), (const cplx*)x, C2(beta), (cplx*)y, conj_x, S(stream));
 }
+int carc_mode_product(const void* matrix, const void* x, void* out, int64_t rows, int64_t k, int64_t pre, int64_t post,
+                      void* stream) {
+  return carc::mode_product((const cplx*)matrix, (const cplx*)x, (cplx*)out, rows, k, pre, post, S(stream));
+}
 int carc_mul(int64_t n, const void* x, void* y, void* stream) {
   return carc::mul_inplace(n, (const cplx*)x, (cplx*)y, S(stream));
 }

@@ -17,6 +17,8 @@ const char* get_error();
 int permute(const cplx* src, cplx* dst, int ndim, const int64_t* shape, const int32_t* perm, int conj, int accumulate,
             cudaStream_t stream);
 int axpby(int64_t n, cplx alpha, const cplx* x, cplx beta, cplx* y, int conj_x, cudaStream_t stream);
+int mode_product(const cplx* M, const cplx* x, cplx* out, int64_t j, int64_t k, int64_t pre, int64_t post,
+                 cudaStream_t stream);
 int mul_inplace(int64_t n, const cplx* x, cplx* y, cudaStream_t stream);
 int reduce(int mode, int64_t n, const cplx* x, const cplx* y, double2* out_dev, cudaStream_t stream);
 

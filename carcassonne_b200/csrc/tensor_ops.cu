@@ -360,4 +360,88 @@ int reduce(int mode, int64_t n, const cplx* x, const cplx* y, double2* out_dev, 
   return CARC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Mode product with a short matrix: out[pre][j][post] = sum_k M[j][k] * x[pre][k][post], j <= 16 rows.
+// (NDArrayData.absorbMatrixAt, data/__init__.py:148-150, when a compressor [new, old] projects an enlarged
+// environment bond: new = chi is a handful of rows while pre*post runs to 10^7..10^9.)  A DMMA GEMM would pad the
+// j rows to its 128-row tile; here every thread owns one `post` column, streams the k inputs once (coalesced
+// 16-byte loads, four in flight) and keeps the j outputs in registers -- the kernel is bound by reading x.
+template <int J>
+__global__ void __launch_bounds__(256, 2) mode_product_kernel(const cplx* __restrict__ M, const cplx* __restrict__ x,
+                                                           cplx* __restrict__ out, int j, int k, int64_t post,
+                                                           int64_t chunks) {
+  extern __shared__ __align__(16) unsigned char mp_smem[];
+  cplx* Ms = reinterpret_cast<cplx*>(mp_smem);   // [k][J], rows beyond j are zero
+  for (int i = threadIdx.x; i < k * J; i += blockDim.x) {
+    const int kk = i / J, jj = i % J;
+    Ms[i] = jj < j ? M[(int64_t)jj * k + kk] : make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+  const int64_t b = blockIdx.x;
+  const int64_t pre = b / chunks, col = (b % chunks) * blockDim.x + threadIdx.x;
+  if (col >= post) return;
+  const cplx* xp = x + (pre * k) * post + col;
+  double re[J], im[J];
+#pragma unroll
+  for (int jj = 0; jj < J; ++jj) re[jj] = im[jj] = 0.0;
+  int kk = 0;
+  for (; kk + 4 <= k; kk += 4) {
+    cplx v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(xp + (int64_t)(kk + u) * post);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int jj = 0; jj < J; ++jj) {
+        const cplx m = Ms[(kk + u) * J + jj];
+        re[jj] += m.x * v[u].x - m.y * v[u].y;
+        im[jj] += m.x * v[u].y + m.y * v[u].x;
+      }
+    }
+  }
+  for (; kk < k; ++kk) {
+    const cplx v = __ldg(xp + (int64_t)kk * post);
+#pragma unroll
+    for (int jj = 0; jj < J; ++jj) {
+      const cplx m = Ms[kk * J + jj];
+      re[jj] += m.x * v.x - m.y * v.y;
+      im[jj] += m.x * v.y + m.y * v.x;
+    }
+  }
+  cplx* op = out + (pre * j) * post + col;
+#pragma unroll
+  for (int jj = 0; jj < J; ++jj)
+    if (jj < j) op[(int64_t)jj * post] = make_double2(re[jj], im[jj]);
+}
+
+template <int J>
+static int mode_product_launch(const cplx* M, const cplx* x, cplx* out, int j, int k, int64_t pre, int64_t post,
+                               cudaStream_t stream) {
+  const size_t smem = sizeof(cplx) * (size_t)k * J;
+  static bool configured[16] = {false};
+  int dev = 0;
+  CARC_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 16 && !configured[dev]) {
+    CARC_CHECK_CUDA(cudaFuncSetAttribute(mode_product_kernel<J>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    configured[dev] = true;
+  }
+  const int64_t chunks = (post + 255) / 256;
+  const int64_t blocks = pre * chunks;
+  CARC_REQUIRE(blocks < (1ll << 31), CARC_ERR_VALUE, "mode product: tensor too large for one launch");
+  mode_product_kernel<J><<<(unsigned)blocks, 256, smem, stream>>>(M, x, out, j, k, post, chunks);
+  CARC_CHECK_CUDA(cudaGetLastError());
+  return CARC_OK;
+}
+
+int mode_product(const cplx* M, const cplx* x, cplx* out, int64_t j, int64_t k, int64_t pre, int64_t post,
+                 cudaStream_t stream) {
+  CARC_REQUIRE(j >= 1 && j <= 16, CARC_ERR_UNSUPPORTED, "mode product: 1 <= rows <= 16 required (given %lld)", (long long)j);
+  CARC_REQUIRE(k >= 1 && k * 16 * 16 <= 160 * 1024, CARC_ERR_UNSUPPORTED, "mode product: contracted extent %lld too large",
+               (long long)k);
+  if (pre <= 0 || post <= 0) return CARC_OK;
+  if (j <= 4) return mode_product_launch<4>(M, x, out, (int)j, (int)k, pre, post, stream);
+  if (j <= 8) return mode_product_launch<8>(M, x, out, (int)j, (int)k, pre, post, stream);
+  return mode_product_launch<16>(M, x, out, (int)j, (int)k, pre, post, stream);
+}
+
 }  // namespace carc

@@ -104,7 +104,9 @@ def gemm_scatter(opA, opB, M, N, K, A, lda, B, ldb, Cbuf, row_levels, col_levels
 class DeviceData:
     """complex128 tensor in device memory; API of the reference's NDArrayData."""
 
-    __slots__ = ["_t"]
+    # _factors: optional record of how this tensor was produced (set by the center -> side absorption, read by the
+    # state-bond compression to build Gram matrices from the factors); dropped by every in-place update
+    __slots__ = ["_t", "_factors"]
 
     # -- construction -----------------------------------------------------------------------------------
     def __init__(self, t):
@@ -113,6 +115,7 @@ class DeviceData:
         if t.dtype != _c128 or not t.is_cuda:
             raise TypeError("DeviceData wraps complex128 CUDA buffers")
         self._t = t if t.is_contiguous() else t.contiguous()
+        self._factors = None
 
     @classmethod
     def fromArray(cls, arr):
@@ -197,6 +200,7 @@ class DeviceData:
     # -- elementwise ------------------------------------------------------------------------------------
     def _axpby(self, alpha, x, beta, conj_x=0):
         """self = alpha * x + beta * self (in place)."""
+        self._factors = None
         check(lib.carc_axpby(self.size(), _lib.cplx2(alpha), _ptr(x._t), _lib.cplx2(beta), _ptr(self._t), conj_x,
                              _stream()))
         return self
@@ -243,6 +247,7 @@ class DeviceData:
 
     def __imul__(self, other):
         self._check_same_shape(other)
+        self._factors = None
         check(lib.carc_mul(self.size(), _ptr(other._t), _ptr(self._t), _stream()))
         return self
 
@@ -372,6 +377,7 @@ class DeviceData:
         return DeviceData(self._t[index].contiguous())
 
     def __setitem__(self, index, value):
+        self._factors = None
         self._t[index] = value._t if isinstance(value, DeviceData) else value
 
     def __str__(self):
@@ -430,7 +436,10 @@ class DeviceData:
         post = _prod(shape[axis + 1:])
         k, j = shape[axis], matrix.shape[0]
         out = _empty(shape[:axis] + (j,) + shape[axis + 1:])
-        if pre * post * j > 0:
+        if pre * post * j > 0 and j <= 16 and k <= 640 and post >= 32:
+            # a short matrix against a long tensor (compressor projections): streaming kernel, bound by reading self
+            check(lib.carc_mode_product(_ptr(matrix._t), _ptr(self._t), _ptr(out), j, k, pre, post, _stream()))
+        elif pre * post * j > 0:
             # for each leading index: out[pre][j, post] = matrix[j, k] . self[pre][k, post]
             gemm(_lib.OP_N, _lib.OP_N, j, post, k, matrix._t, k, self._t, post, out, batch=pre, strideA=0,
                  strideB=k * post, strideC=j * post)

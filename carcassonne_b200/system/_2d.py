@@ -11,7 +11,7 @@ from random import randint
 
 import numpy as np
 
-from ..compression import computeProductCompressor
+from ..compression import computeProductCompressor, factored_side_gram
 from ..data import DeviceData, _init_constants
 from ..sparse import (Identity, OneSiteOperator, TwoSiteOperator, TwoSiteOperatorCompressed, makeSimpleSparseOperator,
                       makeSparseOperator, mapOverSparseData, stripAllButIdentityFrom)
@@ -330,7 +330,8 @@ class System(BaseSystem):
         side_id = L(corner_id)
         side_joined = self.sides[side_id][Identity()].join((0, 1, 2, 6, 7), 3, 4, 5)
         corner_joined = self.corners[corner_id][Identity()].join(0, 1, 2, (3, 4, 5))
-        compressor = computeProductCompressor(side_joined, corner_joined, new_dimension, initial)
+        compressor = computeProductCompressor(side_joined, corner_joined, new_dimension, initial,
+                                              left_gram=factored_side_gram(self.sides[side_id][Identity()], 1))
         self.sides[side_id] = self._project(self.sides[side_id], 3, compressor, False)
         self.corners[corner_id] = self._project(self.corners[corner_id], 0, compressor, True)
         return compressor
@@ -338,7 +339,8 @@ class System(BaseSystem):
     def compressCornerStateTowardsRight(self, corner_id, new_dimension, initial=None):
         corner_joined = self.corners[corner_id][Identity()].join((0, 1, 2), 3, 4, 5)
         side_joined = self.sides[corner_id][Identity()].join(0, 1, 2, (3, 4, 5, 6, 7))
-        compressor = computeProductCompressor(corner_joined, side_joined, new_dimension, initial)
+        compressor = computeProductCompressor(corner_joined, side_joined, new_dimension, initial,
+                                              right_gram=factored_side_gram(self.sides[corner_id][Identity()], 0))
         self.corners[corner_id] = self._project(self.corners[corner_id], 3, compressor, False)
         self.sides[corner_id] = self._project(self.sides[corner_id], 0, compressor, True)
         return compressor

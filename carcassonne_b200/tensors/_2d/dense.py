@@ -37,6 +37,7 @@ def _target(shape, accumulate_into):
         return _empty(shape), 0.0
     if accumulate_into.shape != tuple(shape):
         raise ValueError("cannot accumulate a result of shape {} into {}".format(tuple(shape), accumulate_into.shape))
+    accumulate_into._factors = None
     return accumulate_into._t, 1.0
 
 
@@ -127,7 +128,13 @@ def _absorb_center(direction, side, E, dims, accumulate_into):
     gemm_scatter(OP_N, OP_N, prod(s[:6]), prod(dims[2:]), K, side._t, K, E, prod(dims[2:]), out,
                  ((s[0], st[0]), (s[1], st[2]), (s[2], st[4]), (s[3], st[5]), (s[4], st[7]), (s[5], st[9])),
                  ((nl, st[1]), (ml, st[3]), (nr, st[6]), (mr, st[8]), (no * mo, st[10])), beta=beta)
-    return accumulate_into if accumulate_into is not None else DeviceData(out)
+    if accumulate_into is not None:
+        return accumulate_into
+    result = DeviceData(out)
+    # side' = side (x) E over (g h): the state-bond compression that follows a contraction builds its Gram matrix
+    # from these two small factors instead of the enlarged tensor (compression.factored_side_gram)
+    result._factors = ("center_into_side", side, DeviceData(E), dims)
+    return result
 
 
 def absorbDenseCenterSSIntoSide(direction, side, center, center_conj, accumulate_into=None, _cache=None):

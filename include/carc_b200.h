@@ -71,6 +71,11 @@ int carc_permute(const void* src, void* dst, int ndim, const int64_t* shape, con
 /* ---- NDArrayData + - * += scalar*  (data/__init__.py:95-147):  y = alpha * (conj_x ? conj(x) : x) + beta * y */
 int carc_axpby(int64_t n, const double alpha[2], const void* x, const double beta[2], void* y, int conj_x,
                void* stream);
+/* ---- NDArrayData.absorbMatrixAt with a short matrix (data/__init__.py:148-150; the compressor projections of
+ * system/_2d.py:199-228):  out[pre][j][post] = sum_k matrix[j][k] * x[pre][k][post],  1 <= rows <= 16,
+ * k <= 640.  HBM-bound streaming kernel; larger matrices go through carc_zgemm (batched). */
+int carc_mode_product(const void* matrix, const void* x, void* out, int64_t rows, int64_t k, int64_t pre, int64_t post,
+                      void* stream);
 /* y *= x elementwise (NDArrayData.__imul__) */
 int carc_mul(int64_t n, const void* x, void* y, void* stream);
 

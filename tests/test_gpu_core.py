@@ -138,6 +138,30 @@ def test_absorb_matrix_at(dd):
         assert relerr(out.toArray(), g["am%d_out" % n]) < 1e-14
 
 
+@pytest.mark.parametrize("shape,axis,rows", [
+    ((37, 40), 0, 1), ((37, 40), 0, 5), ((13, 300), 0, 8), ((3, 11, 70), 1, 9), ((2, 64, 5, 33), 1, 16),
+    ((5, 4, 257), 1, 3), ((6, 2, 1000), 0, 4), ((1, 130, 32), 1, 12),
+])
+def test_absorb_short_matrix_streaming_kernel(dd, shape, axis, rows):
+    """absorbMatrixAt with <= 16 rows against a long tensor goes through carc_mode_product (the compressor projections
+    of reference system/_2d.py:199-228); ragged k (not a multiple of 4) and post (not a multiple of the block)."""
+    rng = np.random.default_rng(11)
+    t = crand(rng, *shape)
+    m = crand(rng, rows, shape[axis])
+    out = dd.fromArray(t).absorbMatrixAt(axis, dd.fromArray(m)).toArray()
+    ref = np.moveaxis(np.tensordot(m, t, (1, axis)), 0, axis)
+    assert out.shape == ref.shape
+    assert relerr(out, ref) < 1e-14
+
+
+def test_mode_product_rejects_tall_matrix():
+    import torch
+    from carcassonne_b200 import _lib
+    x = torch.zeros(64 * 64, dtype=torch.complex128, device="cuda")
+    rc = _lib.lib.carc_mode_product(x.data_ptr(), x.data_ptr(), x.data_ptr(), 17, 4, 1, 64, None)
+    assert rc == _lib.ERR_UNSUPPORTED
+
+
 def test_elementwise_and_reductions(dd):
     rng = np.random.default_rng(3)
     a, b = crand(rng, 37, 5, 3), crand(rng, 37, 5, 3)

@@ -563,6 +563,65 @@ def test_state_compression_preserves_expectation(dd):
         s.compressCornerStateTowards(0, 2, 1)
 
 
+@pytest.mark.parametrize("direction", [0, 1, 2, 3])
+def test_factored_side_gram_matches_direct_gram(dd, direction):
+    """The Gram matrices the state-bond compression needs right after a contraction are assembled from the factors
+    of the absorption (side, double-layer center) -- same numbers as summing over the enlarged side directly
+    (reference compression.py:31 b = L.R / system/_2d.py:199-228 joins), ragged bond dimensions."""
+    from carcassonne_b200.compression import factored_side_gram
+    from carcassonne_b200.tensors._2d import dense
+    rng = np.random.default_rng(20 + direction)
+    cdims = [2, 3, 2, 3]
+    cdims[direction] = 3
+    center = crand(rng, *cdims, 2)
+    g = cdims[direction]
+    side = crand(rng, 2, 3, 1, 3, 2, 1, g, g)
+    enlarged = dense.absorbDenseCenterSSIntoSide(direction, dd.fromArray(side), dd.fromArray(center),
+                                                 dd.fromArray(center.conj()))
+    big = enlarged.toArray()
+    for end, axes in ((0, (0, 1)), (1, (3, 4))):
+        gram = factored_side_gram(enlarged, end)
+        assert gram is not None
+        rest = tuple(a for a in range(8) if a not in axes)
+        m = big.transpose(axes + rest).reshape(big.shape[axes[0]] * big.shape[axes[1]], -1)
+        assert relerr(gram.toArray(), m.conj() @ m.T) < 1e-13
+    # any in-place update drops the record, and so does accumulating another product into the tensor
+    other = dense.absorbDenseCenterSSIntoSide(direction, dd.fromArray(side), dd.fromArray(center),
+                                              dd.fromArray(center.conj()))
+    dense.absorbDenseCenterSSIntoSide(direction, dd.fromArray(side), dd.fromArray(center), dd.fromArray(center.conj()),
+                                      accumulate_into=other)
+    assert factored_side_gram(other, 0) is None
+    enlarged += enlarged
+    assert factored_side_gram(enlarged, 0) is None
+    assert factored_side_gram(dd.fromArray(side), 1) is None
+
+
+def test_compression_after_contraction_uses_factors_and_matches_direct_path(dd):
+    """contractTowards followed by compressCornerStateTowards: the compressor computed with the factored Gram equals
+    the one computed from the enlarged tensors alone (same random start)."""
+    from carcassonne_b200 import synthetic
+    from carcassonne_b200.compression import computeProductCompressor, factored_side_gram
+    ident = to_tag(("I",))
+    for corner_id, direction in ((1, 1), (0, 0)):     # either end of the enlarged side 1 (the projection that follows
+        s = synthetic.device_system(2, 3, J=0.7, seed=4)   # a compression produces a new tensor without the record)
+        s.contractTowards(1)
+        side_id = corner_id if direction == 1 else (corner_id + 1) % 4
+        side = s.sides[side_id][ident]
+        end = 0 if direction == 1 else 1
+        assert factored_side_gram(side, end) is not None
+        old = side.shape[0 if direction == 1 else 3]
+        init = crand(np.random.default_rng(corner_id), old, 2)
+        if direction == 1:
+            Lj = s.corners[corner_id][ident].join((0, 1, 2), 3, 4, 5)
+            Rj = side.join(0, 1, 2, (3, 4, 5, 6, 7))
+        else:
+            Lj = side.join((0, 1, 2, 6, 7), 3, 4, 5)
+            Rj = s.corners[corner_id][ident].join(0, 1, 2, (3, 4, 5))
+        direct = computeProductCompressor(Lj, Rj, 2, initial=dd.fromArray(init)).toArray()
+        used = s.compressCornerStateTowards(corner_id, direction, 2, initial=dd.fromArray(init)).toArray()
+        assert relerr(used.conj().T @ used, direct.conj().T @ direct) < 1e-8
+
+
 def test_operator_compression_preserves_expectation(dd):
     """reference tests/test_system.py:82-178: folding all two-site halves into a full-rank compressed bond leaves the
     expectation unchanged."""
