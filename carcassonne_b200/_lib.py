@@ -62,6 +62,7 @@ SIGNATURES = {
     "carc_gmres": (c_int, [c_vp, c_vp, c_vp, C.c_double, c_int, c_int, C.POINTER(c_int), c_dp, c_vp]),
     "carc_cg": (c_int, [c_vp, c_vp, c_vp, C.c_double, c_int, C.POINTER(c_int), c_dp, c_vp]),
     "carc_lu_factor": (c_int, [c_vp, c_int, c_vp, C.POINTER(c_int), c_vp]),
+    "carc_cholesky_factor_as_lu": (c_int, [c_vp, c_int, c_vp, C.c_double, C.POINTER(c_int), c_vp]),
     "carc_lu_solve": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp]),
     "carc_zgemm_hermitian": (c_int, [c_int, c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "carc_index_table": (c_int, [c_int, c_i64p, c_i64p, c_vp, c_vp]),

@@ -376,6 +376,33 @@ int carc_lu_solve_blocks(const void* LU, int n, const void* piv_dev, const void*
   return rc;
 }
 
+int carc_cholesky_factor_as_lu(void* A, int n, void* piv_dev, double hermitian_tolerance, int* status_out, void* stream) {
+  CARC_REQUIRE(A && piv_dev && n > 0, CARC_ERR_VALUE, "cholesky_factor_as_lu: invalid argument");
+  keep_pool_memory();
+  cudaStream_t st = S(stream);
+  double* scratch = nullptr;   // [0..1] the two sums of the Hermiticity check, [2] (as int) the pivot status
+  CARC_CHECK_CUDA(cudaMallocAsync((void**)&scratch, 4 * sizeof(double), st));
+  int status = 0;
+  int rc = carc::hermitian_defect((const cplx*)A, n, scratch, st);
+  if (!rc) {
+    double sums[2] = {0.0, 0.0};
+    CARC_CHECK_CUDA(cudaMemcpyAsync(sums, scratch, sizeof(sums), cudaMemcpyDeviceToHost, st));
+    CARC_CHECK_CUDA(cudaStreamSynchronize(st));
+    // |A - A^H|_F <= tol |A|_F (NaNs fail the comparison and are rejected too)
+    if (!(sums[0] <= hermitian_tolerance * hermitian_tolerance * sums[1])) status = 2;
+  }
+  if (!rc && status == 0) {
+    int* status_dev = reinterpret_cast<int*>(scratch + 2);
+    rc = carc::cholesky_factor_as_lu((cplx*)A, n, (int*)piv_dev, status_dev, st);
+    if (!rc) {
+      CARC_CHECK_CUDA(cudaMemcpyAsync(&status, status_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CARC_CHECK_CUDA(cudaStreamSynchronize(st));
+    }
+  }
+  cudaFreeAsync(scratch, st);
+  if (status_out) *status_out = status;
+  return rc;
+}
 int carc_lu_solve(const void* LU, int n, const void* piv_dev, void* x, void* stream) {
   CARC_REQUIRE(LU && piv_dev && x && n > 0, CARC_ERR_VALUE, "lu_solve: invalid argument");
   return carc::lu_solve((const cplx*)LU, n, (const int*)piv_dev, (cplx*)x, S(stream));

@@ -41,6 +41,8 @@ int zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, cplx alpha, const c
           const int64_t* coloff = nullptr);
 int zgemm_hermitian(int opA, int opB, int64_t N, int64_t K, const cplx* A, int64_t lda, const cplx* B, int64_t ldb,
                     cplx* C, cudaStream_t stream);
+int zgemm_lower(int opA, int opB, int64_t N, int64_t K, cplx alpha, const cplx* A, int64_t lda, const cplx* B, int64_t ldb,
+                cplx beta, cplx* C, const GemmOut* out, cudaStream_t stream);
 int index_table(int nlevels, const int64_t* extents, const int64_t* strides, int64_t* table, cudaStream_t stream);
 int dmma_peak(int iters, double* tflops_out, cudaStream_t stream);
 int dmma_rate(int iters, int warps, int chains, double* tflops_out, cudaStream_t stream);
@@ -98,6 +100,8 @@ struct RelaxInfo {
 int dense_matvec(const cplx* M, int64_t rows, int64_t cols, int64_t ld, const cplx* x, cplx* y, cplx alpha, cplx beta,
                  cudaStream_t stream);
 int lu_factor(cplx* A, int n, int* piv, int* singular_dev, cplx* scratch, cudaStream_t stream);
+int cholesky_factor_as_lu(cplx* A, int n, int* piv, int* status_dev, cudaStream_t stream);
+int hermitian_defect(const cplx* A, int n, double* sums_dev, cudaStream_t stream);
 int lu_solve(const cplx* LU, int n, const int* piv, cplx* x, cudaStream_t stream);
 int lu_invert_diagonal_blocks(const cplx* LU, int n, cplx* inv, cudaStream_t stream);
 int64_t lu_inverse_blocks_elems(int n);

@@ -979,6 +979,218 @@ int lu_factor(cplx* A, int n, int* piv, int* singular_dev, cplx* scratch, cudaSt
   return CARC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Cholesky factorisation of a Hermitian positive definite matrix, delivered in LU form.
+//
+// The normalization matrix N of the center-site problem is Hermitian positive definite whenever the environment is
+// a proper (double-layer) one; the reference factorises it with the general lu_factor (utils.py:816-818).  For such N
+// the blocked right-looking Cholesky needs no pivot search (so no grid-wide barriers), half the trailing-update work,
+// and every step but a 64 x 64 diagonal block is a DMMA GEMM.  The result is rewritten as N = L' U' with L' = L D^-1
+// unit lower, U' = D L^H, identity pivots -- the format carc_lu_solve / carc_lu_solve_blocks / carc_relax consume, so
+// the solves are shared with the LU path.  A non-positive (or non-finite) pivot sets *status_dev = 1: the caller
+// falls back to carc_lu_factor on a fresh copy.
+constexpr int CB = 64;
+constexpr int CLD = CB + 1;
+
+__global__ void __launch_bounds__(256) chol_diag_kernel(cplx* __restrict__ A, int n, int j0, int nb,
+                                                        cplx* __restrict__ winv, int* __restrict__ status_dev) {
+  extern __shared__ __align__(16) unsigned char chol_smem[];
+  cplx* Ls = reinterpret_cast<cplx*>(chol_smem);   // [CB][CLD] lower triangle of the block, then its Cholesky factor
+  cplx* Wi = Ls + CB * CLD;                        // [CB][CLD] inverse of the factor
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
+    const int i = idx / nb, j = idx % nb;
+    Ls[i * CLD + j] = j <= i ? A[(int64_t)(j0 + i) * n + j0 + j] : make_double2(0.0, 0.0);
+    Wi[i * CLD + j] = make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+  bool bad = false;
+  for (int k = 0; k < nb; ++k) {
+    const double d2 = Ls[k * CLD + k].x;
+    const bool ok = d2 > 0.0 && isfinite(d2);
+    bad = bad || !ok;
+    const double d = ok ? sqrt(d2) : 1.0;
+    __syncthreads();   // every thread has read the pivot
+    if (tid == 0) Ls[k * CLD + k] = make_double2(d, 0.0);
+    const double inv = 1.0 / d;
+    for (int i = k + 1 + tid; i < nb; i += blockDim.x) Ls[i * CLD + k] = cscale(Ls[i * CLD + k], inv);
+    __syncthreads();
+    const int m = nb - k - 1;
+    for (int idx = tid; idx < m * m; idx += blockDim.x) {
+      const int ii = idx / m, jj = idx % m;
+      if (jj <= ii) {
+        const int i = k + 1 + ii, j = k + 1 + jj;
+        Ls[i * CLD + j] = csub(Ls[i * CLD + j], cmulc(Ls[j * CLD + k], Ls[i * CLD + k]));   // conj(L[j][k]) L[i][k]
+      }
+    }
+    __syncthreads();
+  }
+  if (bad && tid == 0) *status_dev = 1;
+  // Wi = L^-1: column j by four adjacent lanes (each sums a quarter of the dot product)
+  {
+    const int j = tid >> 2, part = tid & 3;
+    for (int i = 0; i < nb; ++i) {
+      cplx acc = make_double2(0.0, 0.0);
+      if (j < nb && i > j)
+        for (int k = j + part; k < i; k += 4) acc = cadd(acc, cmul(Ls[i * CLD + k], Wi[k * CLD + j]));
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 2);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 2);
+      if (j < nb && part == 0 && i >= j) {
+        const double inv = 1.0 / Ls[i * CLD + i].x;
+        Wi[i * CLD + j] = i == j ? make_double2(inv, 0.0) : make_double2(-acc.x * inv, -acc.y * inv);
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
+    const int i = idx / nb, j = idx % nb;
+    if (j <= i) A[(int64_t)(j0 + i) * n + j0 + j] = Ls[i * CLD + j];
+    winv[i * nb + j] = Wi[i * CLD + j];
+  }
+}
+
+// Rewrite the Cholesky factor (lower triangle of A) as LU factors: for i < j  U[i][j] = d_i conj(L[j][i]) and
+// L'[j][i] = L[j][i] / d_i; U[i][i] = d_i^2.  32 x 32 tiles through shared memory so both accesses are coalesced.
+__global__ void __launch_bounds__(256) chol_to_lu_kernel(cplx* __restrict__ A, int n) {
+  __shared__ cplx tile[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;   // tile (bi, bj) of the LOWER triangle: bi >= bj
+  if (bj > bi) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  // load the lower tile rows bi*32.., cols bj*32..
+  for (int rr = ty; rr < 32; rr += 8) {
+    const int i = bi * 32 + rr, j = bj * 32 + tx;
+    tile[rr][tx] = (i < n && j < n && j <= i) ? A[(int64_t)i * n + j] : make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+  // upper tile (bj, bi): U[j][i] = d_j conj(L[i][j]) with d_j = L[j][j]
+  for (int rr = ty; rr < 32; rr += 8) {
+    const int j = bj * 32 + rr, i = bi * 32 + tx;   // writing element (row j, col i), j < i
+    if (i < n && j < n && j < i) {
+      const double dj = A[(int64_t)j * n + j].x;
+      const cplx l = tile[tx][rr];
+      A[(int64_t)j * n + i] = make_double2(dj * l.x, -dj * l.y);
+    }
+  }
+}
+// second pass: scale the strictly lower part by 1 / d_column and square the diagonal (reads the diagonal of pass 1)
+__global__ void __launch_bounds__(256) chol_scale_lower_kernel(cplx* __restrict__ A, int n, const double* __restrict__ diag) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n * n) return;
+  const int i = (int)(idx / n), j = (int)(idx % n);
+  if (j < i) {
+    A[idx] = cscale(A[idx], 1.0 / diag[j]);
+  } else if (j == i) {
+    A[idx] = make_double2(diag[i] * diag[i], 0.0);
+  }
+}
+__global__ void __launch_bounds__(256) chol_diag_extract_kernel(const cplx* __restrict__ A, int n, double* __restrict__ diag,
+                                                                int* __restrict__ piv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    diag[i] = A[(int64_t)i * n + i].x;
+    piv[i] = i;
+  }
+}
+
+// sums[0] += sum |A[i][j] - conj(A[j][i])|^2 over i > j, sums[1] += sum |A[i][j]|^2 over all (i, j): tile pairs through
+// shared memory so both reads are coalesced
+__global__ void __launch_bounds__(256) hermitian_defect_kernel(const cplx* __restrict__ A, int n, double* __restrict__ sums) {
+  __shared__ cplx lo[32][33], up[32][33];
+  __shared__ double red[2][8];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj > bi) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int rr = ty; rr < 32; rr += 8) {
+    const int i = bi * 32 + rr, j = bj * 32 + tx;
+    lo[rr][tx] = (i < n && j < n) ? A[(int64_t)i * n + j] : make_double2(0.0, 0.0);
+    const int i2 = bj * 32 + rr, j2 = bi * 32 + tx;
+    up[rr][tx] = (i2 < n && j2 < n) ? A[(int64_t)i2 * n + j2] : make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+  double defect = 0.0, total = 0.0;
+  for (int rr = ty; rr < 32; rr += 8) {
+    const cplx a = lo[rr][tx], b = up[tx][rr];   // A[i][j] and A[j][i]
+    const int i = bi * 32 + rr, j = bj * 32 + tx;
+    if (bi != bj) {
+      defect += (a.x - b.x) * (a.x - b.x) + (a.y + b.y) * (a.y + b.y);
+      total += cabs2(a) + cabs2(b);
+    } else if (j <= i) {
+      if (j < i) {
+        defect += (a.x - b.x) * (a.x - b.x) + (a.y + b.y) * (a.y + b.y);
+        total += cabs2(a) + cabs2(b);
+      } else {
+        defect += a.y * a.y;
+        total += cabs2(a);
+      }
+    }
+  }
+  defect = warp_sum(defect);
+  total = warp_sum(total);
+  if (tx == 0) { red[0][ty] = defect; red[1][ty] = total; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double d = 0.0, t = 0.0;
+    for (int w = 0; w < 8; ++w) { d += red[0][w]; t += red[1][w]; }
+    atomicAdd(&sums[0], d);
+    atomicAdd(&sums[1], t);
+  }
+}
+
+int hermitian_defect(const cplx* A, int n, double* sums_dev, cudaStream_t stream) {
+  CARC_CHECK_CUDA(cudaMemsetAsync(sums_dev, 0, 2 * sizeof(double), stream));
+  const int nt = (n + 31) / 32;
+  hermitian_defect_kernel<<<dim3(nt, nt), 256, 0, stream>>>(A, n, sums_dev);
+  CARC_CHECK_CUDA(cudaGetLastError());
+  return CARC_OK;
+}
+
+int cholesky_factor_as_lu(cplx* A, int n, int* piv, int* status_dev, cudaStream_t stream) {
+  CARC_REQUIRE(n >= 1, CARC_ERR_VALUE, "cholesky: n must be positive");
+  static bool configured[16] = {false};
+  int dev = 0;
+  CARC_CHECK_CUDA(cudaGetDevice(&dev));
+  const size_t smem = sizeof(cplx) * 2 * CB * CLD;
+  if (dev < 16 && !configured[dev]) {
+    CARC_CHECK_CUDA(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[dev] = true;
+  }
+  const cplx one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0), minus_one = make_double2(-1.0, 0.0);
+  CARC_CHECK_CUDA(cudaMemsetAsync(status_dev, 0, sizeof(int), stream));
+  cplx* winv = nullptr;
+  double* diag = nullptr;
+  CARC_CHECK_CUDA(cudaMallocAsync((void**)&winv, sizeof(cplx) * CB * CB, stream));
+  CARC_CHECK_CUDA(cudaMallocAsync((void**)&diag, sizeof(double) * n, stream));
+  GemmOut o;
+  o.m_div = n; o.m_s1 = 0; o.m_s0 = n;
+  o.n_div = n; o.n_s1 = 0; o.n_s0 = 1;
+  for (int j0 = 0; j0 < n; j0 += CB) {
+    const int nb = n - j0 < CB ? n - j0 : CB;
+    const int pe = j0 + nb;
+    chol_diag_kernel<<<1, 256, smem, stream>>>(A, n, j0, nb, winv, status_dev);
+    if (pe < n) {
+      const int rows = n - pe;
+      cplx* A21 = A + (int64_t)pe * n + j0;
+      // L21 = A21 L11^-H  (in place: a CTA's 128 x 64 tile reads exactly the rows it overwrites, all K = nb columns)
+      int rc = zgemm(OP_N, OP_C, rows, nb, nb, one, A21, n, winv, nb, zero, A21, &o, nullptr, 1, 0, 0, 0, stream);
+      if (rc) return rc;
+      // A22 -= L21 L21^H on the lower triangle's tiles
+      rc = zgemm_lower(OP_N, OP_C, rows, nb, minus_one, A21, n, A21, n, one, A + (int64_t)pe * n + pe, &o, stream);
+      if (rc) return rc;
+    }
+  }
+  chol_diag_extract_kernel<<<(n + 255) / 256, 256, 0, stream>>>(A, n, diag, piv);
+  const int nt = (n + 31) / 32;
+  chol_to_lu_kernel<<<dim3(nt, nt), 256, 0, stream>>>(A, n);
+  chol_scale_lower_kernel<<<(unsigned)(((int64_t)n * n + 255) / 256), 256, 0, stream>>>(A, n, diag);
+  CARC_CHECK_CUDA(cudaGetLastError());
+  CARC_CHECK_CUDA(cudaFreeAsync(winv, stream));
+  CARC_CHECK_CUDA(cudaFreeAsync(diag, stream));
+  return CARC_OK;
+}
+
 int lu_solve(const cplx* LU, int n, const int* piv, cplx* x, cudaStream_t stream) {
   const int NB = 64;
   lu_permute_kernel<<<1, 32, 0, stream>>>(x, piv, n);

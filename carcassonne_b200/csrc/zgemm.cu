@@ -60,7 +60,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) zgemm_kernel(GemmParams p) {
   const int wm = warp >> 1, wn = warp & 1;       // 4 x 2 warps
   const int r = lane >> 2, c = lane & 3;
   const int64_t m0 = (int64_t)(blockIdx.x % p.tiles_m) * BM, n0 = (int64_t)(blockIdx.x / p.tiles_m) * BN;  // 1-D tile grid
-  if (p.hermitian && n0 + BN - 1 < m0) return;   // strictly lower tile: filled by the mirror of its transpose
+  if (p.hermitian == 1 && n0 + BN - 1 < m0) return;   // strictly lower tile: filled by the mirror of its transpose
+  if (p.hermitian == 2 && n0 > m0 + BM - 1) return;   // lower-triangle update: tiles strictly above the diagonal skipped
   const bool split = p.splitk > 1;
   const cplx* A = p.A + (split ? 0 : (int64_t)blockIdx.z * p.strideA);
   const cplx* B = p.B + (split ? 0 : (int64_t)blockIdx.z * p.strideB);
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) zgemm_kernel(GemmParams p) {
       for (int h = 0; h < 2; ++h) {
         const int64_t n = n0 + wn * 32 + j * 8 + 2 * c + h;
         if (n >= p.N) continue;
-        if (p.hermitian && n < m) continue;   // written (bit-identically conjugated) by the mirror of (n, m)
+        if (p.hermitian == 1 && n < m) continue;   // written (bit-identically conjugated) by the mirror of (n, m)
         const int64_t off =
             moff + (p.coloff ? p.coloff[n] : (n / p.out.n_div) * p.out.n_s1 + (n % p.out.n_div) * p.out.n_s0);
         const double re = h ? acc[i][j].re1 : acc[i][j].re0;
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) zgemm_kernel(GemmParams p) {
           v.y += p.beta.x * o.y + p.beta.y * o.x;
         }
         C[off] = v;
-        if (p.hermitian && m != n) C[n * p.N + m] = make_double2(v.x, -v.y);   // plain row-major only
+        if (p.hermitian == 1 && m != n) C[n * p.N + m] = make_double2(v.x, -v.y);   // plain row-major only
       }
     }
   }
@@ -334,6 +335,17 @@ int index_table(int nlevels, const int64_t* extents, const int64_t* strides, int
 }
 
 static thread_local bool g_hermitian = false;
+static thread_local bool g_lower_only = false;
+
+// C (square, any output map) = alpha op(A) op(B) + beta C on the tiles that touch the lower triangle only: the
+// Hermitian rank-k update of the blocked Cholesky factorisation (solver.cu), half the tensor work of the full update.
+int zgemm_lower(int opA, int opB, int64_t N, int64_t K, cplx alpha, const cplx* A, int64_t lda, const cplx* B, int64_t ldb,
+                cplx beta, cplx* C, const GemmOut* out, cudaStream_t stream) {
+  g_lower_only = true;
+  int rc = zgemm(opA, opB, N, N, K, alpha, A, lda, B, ldb, beta, C, out, nullptr, 1, 0, 0, 0, stream);
+  g_lower_only = false;
+  return rc;
+}
 
 // C = op(A) op(B) known to be Hermitian (Gram matrices): computes the upper triangle's tiles and mirrors them.
 int zgemm_hermitian(int opA, int opB, int64_t N, int64_t K, const cplx* A, int64_t lda, const cplx* B, int64_t ldb,
@@ -391,6 +403,7 @@ int zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, cplx alpha, const c
   const int64_t tiles = gx * gy, KT = (K + BK - 1) / BK;
   const bool herm = g_hermitian && M == N && !out && !rowoff && !coloff && batch == 1;
   if (herm && !(tiles <= 74 && KT >= 64)) p.hermitian = 1;   // (small outputs take the split-K path instead)
+  if (g_lower_only && M == N && batch == 1 && !(tiles <= 74 && KT >= 64)) p.hermitian = 2;
   if (batch == 1 && tiles <= 74 && KT >= 64) {
     // few output tiles, long K (Gram matrices, formMatrix): split K over the idle SMs
     int64_t splits = std::min<int64_t>(148 * 2 / tiles, KT / 16);

@@ -169,17 +169,33 @@ class _DenseOperator:
 class LUFactors:
     """scipy.linalg.lu_factor / lu_solve on device (carc_lu_factor / carc_lu_solve)."""
 
-    def __init__(self, matrix):
+    def __init__(self, matrix, try_cholesky=False, hermitian_tolerance=1e-11):
+        """``try_cholesky``: the caller expects a Hermitian positive definite matrix (the normalization matrix of a
+        double-layer environment).  It is then factorised by the device Cholesky (about 3x faster: no pivot search)
+        and stored in the same LU form; a matrix that is not Hermitian to ``hermitian_tolerance`` (relative,
+        Frobenius) or meets a non-positive pivot goes through the general LU as in the reference."""
         import torch
         from ._lib import lib, check
         from .data import _ptr, _stream
         n = matrix.shape[0]
         self.n = n
-        self.lu = matrix.copy()
         self.piv = torch.empty(n, dtype=torch.int32, device="cuda")
-        singular = C.c_int(0)
-        check(lib.carc_lu_factor(_ptr(self.lu._t), n, C.c_void_p(self.piv.data_ptr()), C.byref(singular), _stream()))
-        self.singular = bool(singular.value)
+        self.method = "lu"
+        self.singular = False
+        self.lu = matrix.copy()
+        if try_cholesky:
+            status = C.c_int(0)
+            check(lib.carc_cholesky_factor_as_lu(_ptr(self.lu._t), n, C.c_void_p(self.piv.data_ptr()),
+                                                 float(hermitian_tolerance), C.byref(status), _stream()))
+            if status.value == 0:
+                self.method = "cholesky"
+            elif status.value == 1:
+                self.lu = matrix.copy()        # the failed attempt overwrote its copy
+        if self.method == "lu":
+            singular = C.c_int(0)
+            check(lib.carc_lu_factor(_ptr(self.lu._t), n, C.c_void_p(self.piv.data_ptr()), C.byref(singular),
+                                     _stream()))
+            self.singular = bool(singular.value)
         self.inv_blocks = torch.empty(int(lib.carc_lu_inverse_blocks_elems(n)), dtype=torch.complex128, device="cuda")
         check(lib.carc_lu_invert_diagonal_blocks(_ptr(self.lu._t), n, C.c_void_p(self.inv_blocks.data_ptr()), _stream()))
 
@@ -233,7 +249,7 @@ def relaxOver(initial, expectation_multiplier, normalization_multiplier=None, ma
     if normalization_multiplier is not None:
         if normalization_multiplier.isCheaperToFormMatrix(10 * 2 * k) or \
                 getattr(normalization_multiplier, "device_operator", None) is None:
-            lu = LUFactors(normalization_multiplier.formMatrix())
+            lu = LUFactors(normalization_multiplier.formMatrix(), try_cholesky=True)
             keep.append(lu)
         else:
             n_handle = _operator_handle(normalization_multiplier, False, keep)
@@ -248,7 +264,8 @@ def relaxOver(initial, expectation_multiplier, normalization_multiplier=None, ma
     if statistics is not None:
         statistics.update(initial_value=complex(info[0], info[1]), final_value=complex(info[2], info[3]),
                           ritz_value=complex(info[4], info[5]), counted=int(info[6]), multiplications=int(info[7]),
-                          gmres_iterations=int(info[8]), normalization="lu" if lu else ("gmres" if n_handle else None))
+                          gmres_iterations=int(info[8]),
+                          normalization=lu.method if lu else ("gmres" if n_handle else None))
     if rc == ERR_RELAX_FAILED:
         raise RelaxFailed(complex(info[0], info[1]), complex(info[2], info[3]))
     if rc == ERR_NO_CONVERGENCE:

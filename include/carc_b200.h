@@ -192,6 +192,14 @@ int carc_cg(carc_operator* A, const void* b, void* x, double rtol, int maxiter, 
 /* In-place LU with partial pivoting of a row-major n x n matrix (LAPACK zgetrf pivoting rule); piv_dev: int32[n] on
  * device.  Synchronises to report *singular_out (1 if a zero pivot was met).  carc_lu_solve overwrites x with A^-1 x. */
 int carc_lu_factor(void* A, int n, void* piv_dev, int* singular_out, void* stream);
+/* The same factors for a Hermitian positive definite matrix (the normalization matrix of utils.py:816-818 when the
+ * environment is a proper double layer) by a blocked Cholesky factorisation -- no pivot search, half the update work,
+ * all of it DMMA GEMMs -- rewritten in place as unit-lower L' = L D^-1, upper U' = D L^H with identity pivots, so
+ * carc_lu_solve / carc_lu_solve_blocks / carc_relax consume them unchanged.  Synchronises to report *status_out:
+ *   0  factorised;
+ *   2  |A - A^H|_F > hermitian_tolerance |A|_F (or A holds NaNs): A is left untouched;
+ *   1  a pivot was <= 0 or not finite: A is garbage, factor a fresh copy with carc_lu_factor. */
+int carc_cholesky_factor_as_lu(void* A, int n, void* piv_dev, double hermitian_tolerance, int* status_out, void* stream);
 int carc_lu_solve(const void* LU, int n, const void* piv_dev, void* x, void* stream);
 /* The same solve for many right-hand sides in sequence (one per Arnoldi multiplication): invert the 128 x 128 diagonal
  * blocks of L and U once into inv_blocks (carc_lu_inverse_blocks_elems(n) complex numbers), after which every block

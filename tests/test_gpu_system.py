@@ -300,7 +300,7 @@ def test_relax_over_golden(dd):
     res = relaxOver(dd.fromArray(v0), _dense_multiplier(dd, h, False), _dense_multiplier(dd, nm, False), 100,
                     statistics=stats).toArray()
     ray = np.vdot(res, h @ res) / np.vdot(res, nm @ res)
-    assert stats["normalization"] == "lu"
+    assert stats["normalization"] in ("lu", "cholesky")     # (Cholesky when the golden N is Hermitian positive definite)
     assert abs(ray - g["lu_rayleigh"]) < 1e-10
     assert min(relerr(res, g["lu_result"]), relerr(-res, g["lu_result"])) < 1e-6 or \
         abs(abs(np.vdot(res, g["lu_result"])) - 1) < 1e-8
@@ -365,6 +365,52 @@ def test_lu_and_gmres(dd, n):
     from carcassonne_b200.compression import _cg_dense
     x, iterations, residual = _cg_dense(dd.fromArray(spd), dd.fromArray(b), rtol=1e-10)
     assert relerr(spd @ x.toArray(), b) < 1e-8 and iterations >= 1 and residual <= 1e-9 * np.linalg.norm(b) + 1e-300
+
+
+@pytest.mark.parametrize("n", [1, 5, 64, 65, 130, 300, 1000])
+def test_cholesky_factors_in_lu_form(dd, n):
+    """A Hermitian positive definite matrix (the normalization matrix of reference utils.py:816-818 in a proper
+    environment) is factorised by the device Cholesky and stored as unit-lower / upper LU factors with identity pivots:
+    L' U' reproduces the matrix and both substitution paths solve with it."""
+    from carcassonne_b200.utils import LUFactors
+    rng = np.random.default_rng(n + 100)
+    g = crand(rng, n, n + 3)
+    a = g @ g.conj().T + 0.1 * np.eye(n)
+    b = crand(rng, n)
+    lu = LUFactors(dd.fromArray(a), try_cholesky=True)
+    assert lu.method == "cholesky"
+    f = lu.lu.toArray()
+    lower, upper = np.tril(f, -1) + np.eye(n), np.triu(f)
+    assert relerr(lower @ upper, a) < 1e-13
+    assert np.array_equal(lu.piv.cpu().numpy(), np.arange(n))
+    ref = np.linalg.solve(a, b)
+    assert relerr(lu.solve(dd.fromArray(b)).toArray(), ref) < 1e-10
+    assert relerr(lu.solve_reference(dd.fromArray(b)).toArray(), ref) < 1e-10
+    # same solution as the general LU of the same matrix
+    plain = LUFactors(dd.fromArray(a))
+    assert plain.method == "lu"
+    assert relerr(plain.solve(dd.fromArray(b)).toArray(), ref) < 1e-10
+
+
+def test_cholesky_falls_back_to_lu(dd):
+    """Not Hermitian (status 2, matrix untouched) or Hermitian but indefinite (status 1): the general LU takes over,
+    as scipy.linalg.lu_factor would in the reference."""
+    from carcassonne_b200.utils import LUFactors
+    rng = np.random.default_rng(5)
+    n = 150
+    b = crand(rng, n)
+    general = crand(rng, n, n) + 4 * np.eye(n)
+    h = crand(rng, n, n)
+    indefinite = h + h.conj().T
+    slightly_off = (lambda g: g @ g.conj().T + np.eye(n))(crand(rng, n, n))
+    slightly_off[3, 7] += 1e-6
+    for a in (general, indefinite, slightly_off):
+        lu = LUFactors(dd.fromArray(a), try_cholesky=True)
+        assert lu.method == "lu"
+        assert relerr(lu.solve(dd.fromArray(b)).toArray(), np.linalg.solve(a, b)) < 1e-9
+    nan = general.copy()
+    nan[2, 2] = np.nan
+    assert LUFactors(dd.fromArray(nan), try_cholesky=True).method == "lu"
 
 
 def _physical_system(dd, J=0.5, grow=True):
