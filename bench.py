@@ -270,6 +270,11 @@ def run_device(args, rank, world, local_rank):
     for a, b, o in terms:
         op.add_term(A[a], B[b], o)
     op.finalize()
+    if args.path:
+        op.set_path(args.path)
+    kernel_name = {1: "stage3_kernel (fused A.v -> O -> B^T, DMMA.8x8x4)",
+                   3: "stage3f_kernel (fused A.v -> O -> B^T, spin index folded into the tile columns, DMMA.8x8x4)",
+                   2: "zgemm_kernel x 3 per term (unfused DMMA GEMMs)"}.get(op.path, "?")
     A_keep.extend([A, B, op])
     comm = None
     if world > 1 and args.reduce == "peer":
@@ -364,7 +369,7 @@ def run_device(args, rank, world, local_rank):
             traffic = None
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": tf.value, "unit": "TFLOP/s",
                 "frac": achieved_tf / tf.value, "traffic": traffic,
-                "kernel": "stage3_kernel (fused A.v -> O -> B^T, DMMA.8x8x4)",
+                "kernel": kernel_name,
                 "executed_flops_per_launch": executed, "reference_flops_per_launch": flops_local,
                 "note": "achieved = FP64 flops the kernel issues / its duration.  The kernel decomposes the term list "
                         "into stars (terms sharing a half-1 tensor: first products summed before one second product; "
@@ -453,6 +458,9 @@ def main():
                     help="which Hamiltonian's sparse term structure to benchmark (T = 9 / 20 terms)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sweep", action="store_true", help="skip the seconds-per-sweep-iteration section")
+    ap.add_argument("--path", type=int, default=0, choices=[0, 1, 2, 3],
+                    help="device path of the matvec: 0 automatic, 1 fused kernel, 3 fused kernel with the folded "
+                         "tiling, 2 unfused GEMMs (kernel comparisons; the default is what the library picks)")
     ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"], help="N > 1: how partial outputs are summed")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -30,6 +30,7 @@ SIGNATURES = {
     "carc_last_error": (C.c_char_p, []),
     "carc_dmma_peak": (c_int, [c_int, c_dp, c_vp]),
     "carc_dmma_rate": (c_int, [c_int, c_int, c_int, c_dp, c_vp]),
+    "carc_fp64_mix_rate": (c_int, [c_int, c_int, c_int, c_int, c_dp, c_dp, c_vp]),
     "carc_malloc": (c_int, [C.POINTER(c_vp), C.c_size_t]),
     "carc_free": (c_int, [c_vp]),
     "carc_malloc_host": (c_int, [C.POINTER(c_vp), C.c_size_t]),
@@ -75,6 +76,8 @@ SIGNATURES = {
     "carc_operator_finalize": (c_int, [c_vp]),
     "carc_operator_apply": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "carc_operator_set_path": (c_int, [c_vp, c_int]),
+    "carc_operator_path": (c_int, [c_vp]),
+    "carc_stage3f_profile_read": (c_int, [c_vp]),
     "carc_operator_num_terms": (c_int, [c_vp]),
     "carc_operator_cost_of_multiply": (c_i64, [c_vp]),
     "carc_operator_destroy": (c_int, [c_vp]),

@@ -52,6 +52,11 @@ int carc_dmma_rate(int iters, int warps_per_sm, int chains, double* tflops_out, 
   return carc::dmma_rate(iters, warps_per_sm, chains, tflops_out, S(stream));
 }
 
+int carc_fp64_mix_rate(int iters, int warps_per_sm, int ndmma, int nfma, double* tflops_dmma, double* tflops_fma,
+                       void* stream) {
+  return carc::fp64_mix_rate(iters, warps_per_sm, ndmma, nfma, tflops_dmma, tflops_fma, S(stream));
+}
+
 int carc_malloc(void** ptr, size_t bytes) {
   CARC_CHECK_CUDA(cudaMalloc(ptr, bytes ? bytes : 16));
   return CARC_OK;
@@ -188,7 +193,7 @@ int carc_operator_finalize(carc_operator* op) {
 }
 
 int carc_operator_set_path(carc_operator* op, int force_path) {
-  CARC_REQUIRE(op && force_path >= 0 && force_path <= 2, CARC_ERR_VALUE, "operator_set_path: invalid argument");
+  CARC_REQUIRE(op && force_path >= 0 && force_path <= 3, CARC_ERR_VALUE, "operator_set_path: invalid argument");
   op->force_path = force_path;
   return CARC_OK;
 }
@@ -226,6 +231,13 @@ double carc_operator_executed_flops(const carc_operator* op) {
   if (!op || op->kind != 0 || !op->plan) return -1.0;
   return carc::stage3_executed_flops(op->plan, op->P, op->Q, op->R, op->S, op->d);
 }
+int carc_operator_path(const carc_operator* op) {
+  if (!op || op->kind != 0 || !op->finalized) return -1;
+  int64_t Xmax = 0;
+  for (const auto& t : op->terms) Xmax = std::max<int64_t>(Xmax, t.X);
+  return carc::stage3_path((int)op->terms.size(), op->P, op->Q, op->R, op->S, op->d, Xmax, op->force_path);
+}
+int carc_stage3f_profile_read(unsigned long long* host) { return carc::stage3f_profile_read(host); }
 int carc_operator_num_groups(const carc_operator* op) { return (op && op->plan) ? (int)op->plan->groups.size() : -1; }
 
 int carc_operator_apply(carc_operator* op, const void* v, void* out, void* stream) {

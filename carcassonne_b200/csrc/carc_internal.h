@@ -46,6 +46,7 @@ int zgemm_lower(int opA, int opB, int64_t N, int64_t K, cplx alpha, const cplx* 
 int index_table(int nlevels, const int64_t* extents, const int64_t* strides, int64_t* table, cudaStream_t stream);
 int dmma_peak(int iters, double* tflops_out, cudaStream_t stream);
 int dmma_rate(int iters, int warps, int chains, double* tflops_out, cudaStream_t stream);
+int fp64_mix_rate(int iters, int warps, int ndmma, int nfma, double* tflops_dmma, double* tflops_fma, cudaStream_t stream);
 
 // comm.cu
 struct Comm;
@@ -82,6 +83,20 @@ double stage3_executed_flops(const Stage3Plan* plan, int P, int Q, int R, int S,
 int stage3_apply(const Stage3Plan* plan, int P, int Q, int R, int S, int d, const cplx* v, cplx* out, cplx* workspace,
                  int64_t workspace_elems, int force_path, cudaStream_t stream, Comm* comm = nullptr);
 int64_t stage3_workspace_elems(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax);
+int stage3_path(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, int force_path);
+
+// stage3f.cu: the folded tiling of the fused kernel (spin index folded into the columns of the first product)
+struct Stage3FConfig {
+  int NPT, NRT, Q4, NSB, G, nstA, nstB, QS, BSTR;
+  int sb_cta0[17], sb_tile0[17];
+  uint32_t slotA, slotB, ops_off, hasop_off, tab_off, vt_off, ring_off, total;
+  int threads, ctas, slots;
+  double padded_work;
+};
+int stage3f_profile_read(unsigned long long* host);
+bool stage3f_configure(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, Stage3FConfig* cfg);
+int stage3f_launch(const Stage3Plan* plan, const Stage3FConfig& k, int P, int Q, int R, int S, const cplx* v, cplx* partial,
+                   cudaStream_t stream);
 
 // linalg.cu
 int qr(cplx* A, int64_t m, int n, cplx* R, cplx* Q, cplx* tau, cudaStream_t stream);

@@ -573,17 +573,42 @@ int s3_unfused(const Stage3Term* terms, int nterms, int P, int Q, int R, int S, 
   return CARC_OK;
 }
 
+// Which device path runs for a shape: the original fused tiling, the folded one, or neither (unfused GEMMs).
+void s3_choose(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, int force_path, S3Config* k, Stage3FConfig* kf,
+               bool* can_fuse, bool* can_fold) {
+  *can_fuse = force_path != 2 && force_path != 3 && Xmax > 0 && s3_configure(nterms, P, Q, R, S, d, Xmax, k);
+  *can_fold = force_path != 2 && force_path != 1 && Xmax > 0 && stage3f_configure(nterms, P, Q, R, S, d, Xmax, kf);
+  if (*can_fuse && *can_fold) {
+    // both tilings fit: take the one that issues fewer DMMA steps for this shape (complex 8x8x4 steps per x and product
+    // pair; the folded tiling must win by a margin, its S blocks re-read A_x more often)
+    const double work = (double)k->NPT * k->NSB * k->CH * (4.0 * k->Q8 + 4.0 * k->NRT);
+    if (kf->padded_work < 0.97 * work) *can_fuse = false;
+    else *can_fold = false;
+  }
+}
+
 }  // namespace
 
 int64_t stage3_workspace_elems(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax) {
   S3Config k;
+  Stage3FConfig kf;
   int64_t fused = 0;
   if (s3_configure(nterms, P, Q, R, S, d, Xmax, &k)) fused = (int64_t)k.slots * P * R * d;
+  if (stage3f_configure(nterms, P, Q, R, S, d, Xmax, &kf)) fused = std::max(fused, (int64_t)kf.slots * P * R * d);
   // unfused path: W + at least 64 MiB worth of intermediate (or the whole thing if smaller)
   int64_t per_x = (int64_t)P * S * d;
   int64_t t = std::min<int64_t>(Xmax * per_x, std::max<int64_t>(per_x, (64ll << 20) / 16));
   int64_t unfused = (int64_t)Q * S * d + t;
   return std::max(fused, unfused) + 64;
+}
+
+// 1: original fused tiling, 3: folded fused tiling, 2: unfused GEMMs -- what stage3_apply runs for this shape
+int stage3_path(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, int force_path) {
+  S3Config k;
+  Stage3FConfig kf;
+  bool can_fuse = false, can_fold = false;
+  s3_choose(nterms, P, Q, R, S, d, Xmax, force_path, &k, &kf, &can_fuse, &can_fold);
+  return can_fold ? 3 : can_fuse ? 1 : 2;
 }
 
 // Decompose the term list -- a bipartite multigraph between half-0 tensors A and half-1 tensors B -- into stars:
@@ -679,8 +704,20 @@ int stage3_apply(const Stage3Plan* plan, int P, int Q, int R, int S, int d, cons
   int64_t Xmax = 0;
   for (const auto& t : plan->terms) Xmax = std::max(Xmax, t.X);
   S3Config k;
-  const bool can_fuse = force_path != 2 && Xmax > 0 && s3_configure(nterms, P, Q, R, S, d, Xmax, &k);
+  Stage3FConfig kf;
+  bool can_fuse = false, can_fold = false;
+  s3_choose(nterms, P, Q, R, S, d, Xmax, force_path, &k, &kf, &can_fuse, &can_fold);
   CARC_REQUIRE(!(force_path == 1 && !can_fuse), CARC_ERR_UNSUPPORTED, "stage3: fused path unavailable for this shape");
+  CARC_REQUIRE(!(force_path == 3 && !can_fold), CARC_ERR_UNSUPPORTED, "stage3: folded fused path unavailable for this shape");
+  if (can_fold) {
+    CARC_REQUIRE(workspace_elems >= (int64_t)kf.slots * n, CARC_ERR_VALUE, "stage3: workspace too small");
+    int rc = stage3f_launch(plan, kf, P, Q, R, S, v, workspace, stream);
+    if (rc) return rc;
+    if (comm) return comm_allreduce(comm, workspace, kf.slots, n, out, stream);
+    s3_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(workspace, out, n, kf.slots, 0);
+    CARC_CHECK_CUDA(cudaGetLastError());
+    return CARC_OK;
+  }
   if (!can_fuse) {
     int rc = s3_unfused(plan->terms.data(), nterms, P, Q, R, S, d, v, out, workspace, workspace_elems, stream);
     if (rc || !comm) return rc;

@@ -1,0 +1,567 @@
+// Fused center-site matvec, "folded" tiling (d = 2): the variant of stage3.cu for bond dimensions whose squares are
+// not multiples of 8 (D = 3, 5, 6, 7, ragged shapes).
+//
+//   out[P,R,s] = sum_t sum_x sum_S B_t[x,R,S] * ( sum_s' O_t[s,s'] * ( sum_Q A_t[x,P,Q] * v[Q,S,s'] ) )
+//
+// (reference tensors/_2d/dense.py:115-160 and tensors/_2d/sparse.py:129-133, as in stage3.cu).  Same structure as
+// stage3_kernel -- TMA rings for A_x and the S block of B_x, stars of terms, C fragment of the first product reused as
+// the A fragment of the second, partial results summed in a fixed order -- but the spin index is folded into the
+// column dimension of the first product: a tile's 8 columns are (S = 4j .. 4j+3) x (s = 0, 1), so
+//   * the first product's N extent is 2*S rounded up to 8 (72 = 9 tiles at D = 6, where stage3_kernel pads
+//     2 x 40), and its K loop takes Q in steps of 4 (one trailing single DMMA step when ceil(Q/4) is odd) instead of 8;
+//   * a lane's C fragment holds the two spins of ONE S column (slot 0 = spin 0, slot 1 = spin 1), so the site
+//     operator acts inside the lane, and the second product needs one B fragment, B_x[R = 8 rt + r, S = 4 j + c],
+//     for both spins; its K extent is S rounded up to 4 instead of 16;
+//   * S blocks hold a whole number of tiles, spread as evenly as the shape allows (D = 7: 5 + 4 + 4 tiles), and the
+//     CTAs are shared out between the S blocks in proportion to their tile counts.
+// DMMA work relative to stage3_kernel: 0.82 (D = 5), 0.86 (D = 6), 0.78 (D = 7), 0.66 (D = 3).
+#include <algorithm>
+#include <vector>
+
+#include "carc_internal.h"
+#include "common.cuh"
+
+namespace carc {
+
+namespace {
+
+constexpr int S3F_SMEM_LIMIT = 227 * 1024;
+constexpr int S3F_MAX_SB = 16;
+
+struct S3FParams {
+  const Stage3Term* terms;  // device copy, sorted by group
+  const Stage3Group* groups;
+  int nterms, ngroups;
+  int P, Q, R, S;
+  int Q4, NPT, G, NSB, nstA, nstB, QS, BSTR;
+  int sb_cta0[S3F_MAX_SB + 1];    // CTAs [sb_cta0[i], sb_cta0[i+1]) work on S block i (one X slab each)
+  int sb_tile0[S3F_MAX_SB + 1];   // S block i covers the tiles (4 S columns each) [sb_tile0[i], sb_tile0[i+1])
+  uint32_t slotA_bytes, slotB_bytes, ops_off, hasop_off, tab_off, vt_off, ring_off, smem_total;
+  const cplx* v;
+  cplx* partial;
+};
+
+// 2 / 3 warps per SM sub-partition leave 255 / 170 registers per thread (see stage3.cu)
+__host__ __device__ constexpr int s3f_max_threads(int nrt) { return nrt >= 7 ? 256 : 384; }
+// tiles per S block (register budget: 16 NRT accumulator registers + 8 per T tile + 16 for the U pair)
+__host__ __device__ constexpr int s3f_tiles(int nrt) { return nrt <= 4 ? 4 : nrt <= 6 ? 3 : nrt == 7 ? 5 : 4; }
+
+// Optional wait-time instrumentation (make EXTRA=-DS3F_PROFILE): cycles each warp spends in the three consumer-side
+// mbarrier waits and in total, read back through stage3f_profile_read().
+#ifdef S3F_PROFILE
+__device__ unsigned long long s3f_prof[148 * 12 * 4];
+#define S3F_WAIT(slot_, bar_, parity_)             \
+  do {                                             \
+    const long long t0_ = clock64();               \
+    mbar_wait(bar_, parity_);                      \
+    prof_wait[slot_] += clock64() - t0_;           \
+  } while (0)
+#else
+#define S3F_WAIT(slot_, bar_, parity_) mbar_wait(bar_, parity_)
+#endif
+
+struct S3FLane {
+  uint32_t a_pair, a_tail, v_pair, v_tail, tile_stride, a_first, a_second;
+  int npairs, ntv;
+  bool tail, eswap;
+};
+
+// T[jj] += A_x (8 rows of this warp) * Vt (tile jbase + jj), for the tiles below ntv
+template <int NJ>
+__device__ __forceinline__ void s3f_first(CTile (&T)[NJ], int jbase, const S3FLane& L, uint32_t slot) {
+  const uint32_t a_base = slot + L.a_pair;
+#pragma unroll 2
+  for (int kp = 0; kp < L.npairs; ++kp) {
+    const cplx x0 = lds_c(a_base + kp * 128 + L.a_first);
+    const cplx x1 = lds_c(a_base + kp * 128 + L.a_second);
+    const cplx a0 = L.eswap ? x1 : x0;
+    const cplx a1 = L.eswap ? x0 : x1;
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+      if (jbase + jj < L.ntv) {
+        const uint32_t va = L.v_pair + (uint32_t)(jbase + jj) * L.tile_stride + kp * 128;
+        const cplx b0 = lds_c(va);
+        const cplx b1 = lds_c(va + 16);
+        cmma(T[jj], a0.x, a0.y, -a0.y, b0.x, b0.y);
+        cmma(T[jj], a1.x, a1.y, -a1.y, b1.x, b1.y);
+      }
+    }
+  }
+  if (L.tail) {
+    const cplx a = lds_c(slot + L.a_tail);
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+      if (jbase + jj < L.ntv) {
+        const cplx b = lds_c(L.v_tail + (uint32_t)(jbase + jj) * L.tile_stride);
+        cmma(T[jj], a.x, a.y, -a.y, b.x, b.y);
+      }
+    }
+  }
+}
+
+// out (+)= O * U on the two spins a lane holds (slot 0 = spin 0, slot 1 = spin 1); w = O row-major [s][s']
+__device__ __forceinline__ void s3f_apply_op(CTile& out, const CTile& U, const cplx* w) {
+  const cplx w00 = w[0], w01 = w[1], w10 = w[2], w11 = w[3];
+  if (w00.x != 0.0 || w00.y != 0.0) {
+    out.re0 += w00.x * U.re0 - w00.y * U.im0;
+    out.im0 += w00.x * U.im0 + w00.y * U.re0;
+  }
+  if (w01.x != 0.0 || w01.y != 0.0) {
+    out.re0 += w01.x * U.re1 - w01.y * U.im1;
+    out.im0 += w01.x * U.im1 + w01.y * U.re1;
+  }
+  if (w10.x != 0.0 || w10.y != 0.0) {
+    out.re1 += w10.x * U.re0 - w10.y * U.im0;
+    out.im1 += w10.x * U.im0 + w10.y * U.re0;
+  }
+  if (w11.x != 0.0 || w11.y != 0.0) {
+    out.re1 += w11.x * U.re1 - w11.y * U.im1;
+    out.im1 += w11.x * U.im1 + w11.y * U.re1;
+  }
+}
+
+// acc[rt][s] += W (tile j, spin s) * B_x[8 rt .., 4 j ..]^T : W's C fragment is the A fragment, one B fragment per rt
+template <int NRT>
+__device__ __forceinline__ void s3f_second(CTile (&acc)[NRT][2], const CTile& W, int j, uint32_t b_base, uint32_t rt_stride) {
+  const double nim0 = -W.im0, nim1 = -W.im1;
+#pragma unroll
+  for (int rt = 0; rt < NRT; ++rt) {
+    const cplx b = lds_c(b_base + rt * rt_stride + (uint32_t)j * 64);
+    cmma(acc[rt][0], W.re0, W.im0, nim0, b.x, b.y);
+    cmma(acc[rt][1], W.re1, W.im1, nim1, b.x, b.y);
+  }
+}
+
+template <int NRT, int NT>
+__global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const S3FParams p) {
+  constexpr int DP = 2;
+  constexpr int UW = NT < 2 ? NT : 2;   // tiles per pass of a later term's first product (register budget)
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = lane >> 2, c = lane & 3;
+  const int ncw = p.G * p.NPT;
+  const int nbar_g = 2 * (p.nstA + p.nstB);
+  const uint32_t bars = smem_u32(smem);
+  cplx* ops = reinterpret_cast<cplx*>(smem + p.ops_off);
+  cplx* Vt = reinterpret_cast<cplx*>(smem + p.vt_off);
+  const int QS = p.QS, BSTR = p.BSTR;
+  const uint32_t group_bytes = p.nstA * p.slotA_bytes + p.nstB * p.slotB_bytes;
+
+  // zero everything behind the barriers: padding rows / columns must read as finite zeros forever
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem + p.ops_off);
+    const uint32_t n16 = (p.smem_total - p.ops_off) / 16;
+    for (uint32_t i = tid; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (tid == 0) {
+    for (int g = 0; g < p.G; ++g) {
+      const uint32_t b = bars + g * nbar_g * 8;
+      for (int i = 0; i < p.nstA; ++i) {
+        mbar_init(b + (2 * i) * 8, 1);           // full A
+        mbar_init(b + (2 * i + 1) * 8, p.NPT);   // empty A
+      }
+      for (int i = 0; i < p.nstB; ++i) {
+        mbar_init(b + (2 * p.nstA + 2 * i) * 8, 1);
+        mbar_init(b + (2 * p.nstA + 2 * i + 1) * 8, p.NPT);
+      }
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  int sb = 0;
+  while (sb + 1 < p.NSB && (int)blockIdx.x >= p.sb_cta0[sb + 1]) ++sb;
+  const int sl = (int)blockIdx.x - p.sb_cta0[sb], NSL = p.sb_cta0[sb + 1] - p.sb_cta0[sb];
+  const int S0 = 4 * p.sb_tile0[sb];
+  const int SBv = min(4 * (p.sb_tile0[sb + 1] - p.sb_tile0[sb]), p.S - S0);
+  int* hasop = reinterpret_cast<int*>(smem + p.hasop_off);
+  const cplx** termA = reinterpret_cast<const cplx**>(smem + p.tab_off);
+  const cplx** termB = termA + p.nterms;
+  const cplx** groupCenter = termB + p.nterms;
+  int* groupX = reinterpret_cast<int*>(groupCenter + p.ngroups);
+  int* groupFirst = groupX + p.ngroups;
+  int* groupCount = groupFirst + p.ngroups;
+  int* groupKind = groupCount + p.ngroups;
+  for (int i = tid; i < p.nterms * DP * DP; i += blockDim.x) ops[i] = p.terms[i / (DP * DP)].op[i % (DP * DP)];
+  for (int i = tid; i < p.nterms; i += blockDim.x) {
+    hasop[i] = p.terms[i].has_op;
+    termA[i] = p.terms[i].A;
+    termB[i] = p.terms[i].B;
+  }
+  for (int i = tid; i < p.ngroups; i += blockDim.x) {
+    groupCenter[i] = p.groups[i].center;
+    groupKind[i] = p.groups[i].kind;
+    groupX[i] = (int)p.groups[i].X;
+    groupFirst[i] = p.groups[i].first;
+    groupCount[i] = p.groups[i].count;
+  }
+  // Vt[f = 2 * S_local + s][q] = v[q, S0 + S_local, s]
+  for (int i = tid; i < p.Q * SBv * DP; i += blockDim.x) {
+    const int f = i % (DP * SBv), q = i / (DP * SBv);
+    Vt[f * QS + q] = p.v[((int64_t)q * p.S + S0) * DP + f];
+  }
+  fence_proxy_async();
+  __syncthreads();
+
+  if (warp >= ncw) return;
+  {
+    const int g = warp / p.NPT, wg = warp % p.NPT;
+    const uint32_t b = bars + g * nbar_g * 8;
+    const uint32_t ring = smem_u32(smem + p.ring_off) + g * group_bytes;
+    CTile acc[NRT][DP];
+#pragma unroll
+    for (int i = 0; i < NRT; ++i)
+#pragma unroll
+      for (int s = 0; s < DP; ++s) acc[i][s].zero();
+
+#ifdef S3F_PROFILE
+    long long prof_wait[3] = {0, 0, 0};
+    const long long prof_t0 = clock64();
+#endif
+    S3FLane L;
+    L.npairs = p.Q4 >> 1;
+    L.tail = (p.Q4 & 1) != 0;
+    L.ntv = (SBv + 3) >> 2;
+    L.eswap = ((p.Q & 1) == 0) && (r & 1);
+    L.a_first = L.eswap ? 16u : 0u;
+    L.a_second = 16u - L.a_first;
+    L.a_pair = (uint32_t)(((wg * 8 + r) * p.Q + 2 * c) * 16);
+    L.a_tail = (uint32_t)(((wg * 8 + r) * p.Q + 8 * L.npairs + c) * 16);
+    L.v_pair = smem_u32(Vt) + (uint32_t)((r * QS + 2 * c) * 16);
+    L.v_tail = smem_u32(Vt) + (uint32_t)((r * QS + 8 * L.npairs + c) * 16);
+    L.tile_stride = (uint32_t)(8 * QS * 16);
+    const uint32_t b_lane_off = (uint32_t)((r * BSTR + c) * 16);
+    const uint32_t rt_stride = (uint32_t)(8 * BSTR * 16);
+
+    // Op cursors: identical to stage3_kernel (flattened sequence of [A-op ..., B-op] per star and x).
+    struct Cursor {
+      int gi, j, x, x_hi;
+    };
+    auto next_item = [&](Cursor& cu) -> bool {
+      cu.x += p.G;
+      while (cu.gi < 0 || cu.x >= cu.x_hi) {
+        if (++cu.gi >= p.ngroups) return false;
+        const int64_t X = groupX[cu.gi];
+        cu.x = (int)(X * sl / NSL) + g;
+        cu.x_hi = (int)(X * (sl + 1) / NSL);
+      }
+      return true;
+    };
+    auto advance = [&](Cursor& cu) -> bool {
+      if (cu.gi >= 0 && cu.j < groupCount[cu.gi]) {
+        ++cu.j;
+        return true;
+      }
+      cu.j = 0;
+      return next_item(cu);
+    };
+    const uint32_t a_bytes = (uint32_t)(p.P * p.Q * 16);
+    const uint32_t b_row_bytes = (uint32_t)(SBv * 16);
+    auto issueA = [&](const Cursor& cu, uint32_t it) {
+      const cplx* A = groupKind[cu.gi] ? groupCenter[cu.gi] : termA[groupFirst[cu.gi] + cu.j];
+      const int sa = it % p.nstA;
+      const uint32_t fullA = b + (2 * sa) * 8;
+      if (lane == 0) {
+        mbar_wait(fullA + 8, ((it / p.nstA) & 1) ^ 1);
+        mbar_arrive_expect_tx(fullA, a_bytes);
+        bulk_g2s(ring + sa * p.slotA_bytes, A + (int64_t)cu.x * p.P * p.Q, a_bytes, fullA);
+      }
+      __syncwarp();
+    };
+    auto issueB = [&](const Cursor& cu, uint32_t it) {
+      const cplx* B = groupKind[cu.gi] ? termB[groupFirst[cu.gi] + cu.j - 1] : groupCenter[cu.gi];
+      const int sbq = it % p.nstB;
+      const uint32_t fullB = b + (2 * p.nstA + 2 * sbq) * 8;
+      if (lane == 0) {
+        mbar_wait(fullB + 8, ((it / p.nstB) & 1) ^ 1);
+        mbar_arrive_expect_tx(fullB, b_row_bytes * p.R);
+      }
+      __syncwarp();
+      const uint32_t dst = ring + p.nstA * p.slotA_bytes + sbq * p.slotB_bytes;
+      const cplx* src = B + ((int64_t)cu.x * p.R) * p.S + S0;
+      for (int rr = lane; rr < p.R; rr += 32) bulk_g2s(dst + rr * BSTR * 16, src + (int64_t)rr * p.S, b_row_bytes, fullB);
+    };
+
+    Cursor cc = {-1, 0, 0, 0}, pc = {-1, 0, 0, 0};
+    uint32_t issuedA = 0, issuedB = 0, itA = 0, itB = 0;
+    bool more = true, pending = false;
+    auto run_ahead = [&]() {
+      while (more) {
+        if (!pending) {
+          more = advance(pc);
+          pending = more;
+          if (!more) break;
+        }
+        if (groupKind[pc.gi] ? (pc.j == 0) : (pc.j < groupCount[pc.gi])) {
+          if (issuedA - itA >= (uint32_t)p.nstA) break;
+          issueA(pc, issuedA++);
+        } else {
+          if (issuedB - itB >= (uint32_t)p.nstB) break;
+          issueB(pc, issuedB++);
+        }
+        pending = false;
+      }
+    };
+
+    while (next_item(cc)) {
+      CTile T[NT];
+      const int first = groupFirst[cc.gi], cnt = groupCount[cc.gi];
+      const int kind = groupKind[cc.gi];
+      {
+        // ---- first term of the star: all tiles of the S block accumulate straight into T
+        if (wg == 0) run_ahead();
+        const bool has_op = !kind && hasop[first] != 0;   // an A-star keeps the raw product
+        const int slot = itA % p.nstA;
+        S3F_WAIT(0, b + (2 * slot) * 8, (itA / p.nstA) & 1);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) T[j].zero();
+        s3f_first<NT>(T, 0, L, ring + slot * p.slotA_bytes);
+        if (has_op) {
+#pragma unroll
+          for (int j = 0; j < NT; ++j) {
+            const CTile U = T[j];
+            T[j].zero();
+            s3f_apply_op(T[j], U, ops + first * DP * DP);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b + (2 * slot + 1) * 8);
+        ++itA;
+      }
+      if (!kind) {
+        for (int jt = 1; jt < cnt; ++jt) {
+          if (wg == 0) run_ahead();
+          // ---- a further term of a B-star: T += O (A_x v); without a site operator the DMMA chains simply continue
+          const int term = first + jt;
+          const bool has_op = hasop[term] != 0;
+          const int slot = itA % p.nstA;
+          S3F_WAIT(1, b + (2 * slot) * 8, (itA / p.nstA) & 1);
+          const uint32_t aslot = ring + slot * p.slotA_bytes;
+          if (!has_op) {
+            s3f_first<NT>(T, 0, L, aslot);
+          } else {
+#pragma unroll
+            for (int j0 = 0; j0 < NT; j0 += UW) {
+              CTile U[UW];
+#pragma unroll
+              for (int jj = 0; jj < UW; ++jj) U[jj].zero();
+              s3f_first<UW>(U, j0, L, aslot);
+#pragma unroll
+              for (int jj = 0; jj < UW; ++jj)
+                if (j0 + jj < NT) s3f_apply_op(T[j0 + jj], U[jj], ops + term * DP * DP);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(b + (2 * slot + 1) * 8);
+          ++itA;
+        }
+        if (wg == 0) run_ahead();
+        // ---- second product of the star: acc += T * B_x^T
+        {
+          const int slot = itB % p.nstB;
+          S3F_WAIT(2, b + (2 * p.nstA + 2 * slot) * 8, (itB / p.nstB) & 1);
+          const uint32_t b_base = ring + p.nstA * p.slotA_bytes + slot * p.slotB_bytes + b_lane_off;
+#pragma unroll
+          for (int j = 0; j < NT; ++j)
+            if (j < L.ntv) s3f_second<NRT>(acc, T[j], j, b_base, rt_stride);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(b + (2 * p.nstA + 2 * slot + 1) * 8);
+          ++itB;
+        }
+      } else {
+        // ---- A-star: T holds A_x v once; every term applies its own site operator and multiplies with its own B_x
+        for (int jt = 0; jt < cnt; ++jt) {
+          if (wg == 0) run_ahead();
+          const int term = first + jt;
+          const bool has_op = hasop[term] != 0;
+          const int slot = itB % p.nstB;
+          S3F_WAIT(2, b + (2 * p.nstA + 2 * slot) * 8, (itB / p.nstB) & 1);
+          const uint32_t b_base = ring + p.nstA * p.slotA_bytes + slot * p.slotB_bytes + b_lane_off;
+#pragma unroll
+          for (int j = 0; j < NT; ++j) {
+            if (j < L.ntv) {
+              CTile W;
+              if (has_op) {
+                W.zero();
+                s3f_apply_op(W, T[j], ops + term * DP * DP);
+              } else {
+                W = T[j];
+              }
+              s3f_second<NRT>(acc, W, j, b_base, rt_stride);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(b + (2 * p.nstA + 2 * slot + 1) * 8);
+          ++itB;
+        }
+      }
+    }
+#ifdef S3F_PROFILE
+    if (lane == 0 && blockIdx.x < 148 && warp < 12) {
+      unsigned long long* o = s3f_prof + ((int)blockIdx.x * 12 + warp) * 4;
+      o[0] = prof_wait[0];
+      o[1] = prof_wait[1];
+      o[2] = prof_wait[2];
+      o[3] = clock64() - prof_t0;
+    }
+#endif
+    // ---- partial result of this (CTA, group)
+    cplx* part = p.partial + ((int64_t)blockIdx.x * p.G + g) * ((int64_t)p.P * p.R * DP);
+    const int row = wg * 8 + r;
+    if (row < p.P) {
+#pragma unroll
+      for (int rt = 0; rt < NRT; ++rt) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int col = rt * 8 + 2 * c + h;
+          if (col < p.R) {
+#pragma unroll
+            for (int s = 0; s < DP; ++s) {
+              cplx val;
+              val.x = h ? acc[rt][s].re1 : acc[rt][s].re0;
+              val.y = h ? acc[rt][s].im1 : acc[rt][s].im0;
+              part[((int64_t)row * p.R + col) * DP + s] = val;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int NRT>
+int s3f_launch(const S3FParams& p, int ctas, int threads, cudaStream_t stream) {
+  static bool configured[16] = {false};
+  int dev = 0;
+  CARC_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 16 && !configured[dev]) {
+    CARC_CHECK_CUDA(cudaFuncSetAttribute(stage3f_kernel<NRT, s3f_tiles(NRT)>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         S3F_SMEM_LIMIT));
+    configured[dev] = true;
+  }
+  stage3f_kernel<NRT, s3f_tiles(NRT)><<<ctas, threads, p.smem_total, stream>>>(p);
+  CARC_CHECK_CUDA(cudaGetLastError());
+  return CARC_OK;
+}
+
+}  // namespace
+
+// Wait-time counters of the last stage3f launch: [148 CTAs][12 warps][first-term A wait, later-term A wait, B wait,
+// total] in cycles; CARC_ERR_UNSUPPORTED unless the library was built with -DS3F_PROFILE.
+int stage3f_profile_read(unsigned long long* host) {
+#ifdef S3F_PROFILE
+  CARC_CHECK_CUDA(cudaDeviceSynchronize());
+  CARC_CHECK_CUDA(cudaMemcpyFromSymbol(host, s3f_prof, sizeof(unsigned long long) * 148 * 12 * 4));
+  return CARC_OK;
+#else
+  (void)host;
+  set_error("stage3f_profile_read: library built without -DS3F_PROFILE");
+  return CARC_ERR_UNSUPPORTED;
+#endif
+}
+
+// Launch geometry of the folded kernel for one shape; false when the shape is outside its envelope.
+bool stage3f_configure(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, Stage3FConfig* cfg) {
+  if (d != 2) return false;
+  if (Xmax >= (1ll << 31) || Xmax < 1) return false;
+  if (P > 64 || R > 64 || P < 1 || R < 1 || Q < 1 || S < 1) return false;
+  Stage3FConfig k;
+  k.NPT = (P + 7) / 8;
+  k.NRT = (R + 7) / 8;
+  k.Q4 = (Q + 3) / 4;
+  const int ntt = (S + 3) / 4;
+  const int ntmax = s3f_tiles(k.NRT);
+  k.NSB = (ntt + ntmax - 1) / ntmax;
+  if (k.NSB > S3F_MAX_SB) return false;
+  const int maxwarps = s3f_max_threads(k.NRT) / 32;
+  if (k.NPT > maxwarps) return false;
+  // tiles as evenly as the shape allows
+  k.sb_tile0[0] = 0;
+  for (int i = 0; i < k.NSB; ++i) k.sb_tile0[i + 1] = k.sb_tile0[i] + ntt / k.NSB + (i < ntt % k.NSB ? 1 : 0);
+  const int nt_block = k.sb_tile0[1];   // the widest block comes first
+  k.QS = k.Q4 * 4;
+  while (k.QS % 8 != 1) ++k.QS;
+  k.BSTR = 4 * nt_block;
+  while (k.BSTR % 8 != 4) ++k.BSTR;
+  k.slotA = (uint32_t)((k.NPT * 8 * Q + 8) * 16);
+  k.slotB = (uint32_t)(k.NRT * 8 * k.BSTR * 16);
+  const uint32_t vbytes = (uint32_t)(8 * nt_block * k.QS * 16);
+  const uint32_t obytes = (uint32_t)(nterms * d * d * 16);
+  int G = std::min(8, maxwarps / k.NPT);
+  if (Xmax < G) G = (int)std::max<int64_t>(1, Xmax);
+  for (; G >= 1; --G) {
+    for (int nstA = 3; nstA >= 2; --nstA) {
+      for (int nstB = 4; nstB >= nstA; --nstB) {
+        const uint32_t bar_bytes = (uint32_t)(((G * 2 * (nstA + nstB) * 8) + 127) / 128 * 128);
+        const uint32_t ops_off = bar_bytes;
+        const uint32_t hasop_off = ops_off + obytes;
+        const uint32_t tab_off = (hasop_off + (uint32_t)nterms * 4 + 15) / 16 * 16;
+        const uint32_t vt_off = (tab_off + (uint32_t)nterms * 16 + (uint32_t)nterms * 24 + 127) / 128 * 128;
+        const uint32_t ring_off = (vt_off + vbytes + 127) / 128 * 128;
+        const uint64_t total = (uint64_t)ring_off + (uint64_t)G * ((uint64_t)nstA * k.slotA + (uint64_t)nstB * k.slotB);
+        if (total > (uint64_t)S3F_SMEM_LIMIT) continue;
+        k.G = G;
+        k.nstA = nstA;
+        k.nstB = nstB;
+        k.ops_off = ops_off;
+        k.hasop_off = hasop_off;
+        k.tab_off = tab_off;
+        k.vt_off = vt_off;
+        k.ring_off = ring_off;
+        k.total = (uint32_t)total;
+        k.threads = G * k.NPT * 32;
+        // share the CTAs (one per SM) between the S blocks in proportion to their tile counts
+        const int64_t max_slabs = std::max<int64_t>(1, Xmax / G);
+        int budget = 148, used = 0;
+        if (k.NSB > budget) budget = k.NSB;
+        k.sb_cta0[0] = 0;
+        for (int i = 0; i < k.NSB; ++i) {
+          const int tiles = k.sb_tile0[i + 1] - k.sb_tile0[i];
+          int64_t n = (int64_t)budget * tiles / ntt;
+          n = std::max<int64_t>(1, std::min<int64_t>(n, max_slabs));
+          k.sb_cta0[i + 1] = k.sb_cta0[i] + (int)n;
+          used += (int)n;
+        }
+        k.ctas = used;
+        k.slots = used * G;
+        // DMMA work per x and product pair, in complex 8x8x4 steps, for the choice between the two kernels
+        k.padded_work = (double)k.NPT * ntt * ((double)k.Q4 + 2.0 * k.NRT);
+        *cfg = k;
+        return true;
+      }
+    }
+  }
+  return false;
+}
+
+int stage3f_launch(const Stage3Plan* plan, const Stage3FConfig& k, int P, int Q, int R, int S, const cplx* v, cplx* partial,
+                   cudaStream_t stream) {
+  S3FParams p;
+  p.terms = plan->terms_dev;
+  p.groups = plan->groups_dev;
+  p.nterms = (int)plan->terms.size();
+  p.ngroups = (int)plan->groups.size();
+  p.P = P; p.Q = Q; p.R = R; p.S = S;
+  p.Q4 = k.Q4; p.NPT = k.NPT; p.G = k.G; p.NSB = k.NSB; p.nstA = k.nstA; p.nstB = k.nstB; p.QS = k.QS; p.BSTR = k.BSTR;
+  for (int i = 0; i <= S3F_MAX_SB; ++i) {
+    p.sb_cta0[i] = i <= k.NSB ? k.sb_cta0[i] : 0;
+    p.sb_tile0[i] = i <= k.NSB ? k.sb_tile0[i] : 0;
+  }
+  p.slotA_bytes = k.slotA; p.slotB_bytes = k.slotB;
+  p.ops_off = k.ops_off; p.hasop_off = k.hasop_off; p.tab_off = k.tab_off; p.vt_off = k.vt_off; p.ring_off = k.ring_off;
+  p.smem_total = k.total;
+  p.v = v;
+  p.partial = partial;
+  switch (k.NRT) {
+    case 1: return s3f_launch<1>(p, k.ctas, k.threads, stream);
+    case 2: return s3f_launch<2>(p, k.ctas, k.threads, stream);
+    case 3: return s3f_launch<3>(p, k.ctas, k.threads, stream);
+    case 4: return s3f_launch<4>(p, k.ctas, k.threads, stream);
+    case 5: return s3f_launch<5>(p, k.ctas, k.threads, stream);
+    case 6: return s3f_launch<6>(p, k.ctas, k.threads, stream);
+    case 7: return s3f_launch<7>(p, k.ctas, k.threads, stream);
+    default: return s3f_launch<8>(p, k.ctas, k.threads, stream);
+  }
+}
+
+}  // namespace carc

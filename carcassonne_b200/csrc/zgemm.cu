@@ -285,6 +285,33 @@ __global__ void __launch_bounds__(MAXT, 1) dmma_rate_distinct_kernel(double* out
   if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// DMMA and DFMA side by side: ND DMMA.8x8x4 (16 independent accumulator tiles) and NF DFMA (16 independent chains) per
+// loop trip and warp -- do the FP64 tensor instruction and the FP64 FMA pipe share execution resources on this part?
+template <int ND, int NF>
+__global__ void __launch_bounds__(512, 1) fp64_mix_kernel(double* out, int iters) {
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  double c0[16], c1[16], f[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    c0[j] = c1[j] = 0.0;
+    f[j] = j * 1e-3;
+  }
+  for (int i = 0; i < iters; ++i) {
+    constexpr int STEPS = ND > NF ? ND : NF;
+#pragma unroll
+    for (int j = 0; j < STEPS; ++j) {
+      // interleave the two instruction streams evenly
+      if ((j + 1) * ND / STEPS != j * ND / STEPS) dmma(c0[(j * ND / STEPS) & 15], c1[(j * ND / STEPS) & 15], a, b);
+      if ((j + 1) * NF / STEPS != j * NF / STEPS)
+        asm volatile("fma.rn.f64 %0, %1, %2, %0;\n" : "+d"(f[(j * NF / STEPS) & 15]) : "d"(a), "d"(b));
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s += c0[j] + c1[j] + f[j];
+  if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace
 
 // DMMA issue rate with `warps` warps per SM (one CTA per SM) and `chains` independent accumulators per warp
@@ -317,6 +344,41 @@ int dmma_rate(int iters, int warps, int chains, double* tflops_out, cudaStream_t
   return CARC_OK;
 }
 
+
+// Rates of a DMMA + DFMA instruction mix (per loop trip and warp: `ndmma` in {0, 16} DMMA.8x8x4 and `nfma` in
+// {0, 16, 32, 64, 128} DFMA), reported separately in TFLOP/s.
+int fp64_mix_rate(int iters, int warps, int ndmma, int nfma, double* tflops_dmma, double* tflops_fma, cudaStream_t stream) {
+  CARC_REQUIRE(warps >= 1 && warps <= 16 && (ndmma == 0 || ndmma == 16), CARC_ERR_VALUE, "fp64_mix_rate: invalid argument");
+  CARC_REQUIRE(nfma == 0 || nfma == 16 || nfma == 32 || nfma == 64 || nfma == 128, CARC_ERR_VALUE,
+               "fp64_mix_rate: nfma must be 0, 16, 32, 64 or 128");
+  CARC_REQUIRE(ndmma + nfma > 0, CARC_ERR_VALUE, "fp64_mix_rate: empty mix");
+  double* buf = nullptr;
+  CARC_CHECK_CUDA(cudaMalloc(&buf, sizeof(double) * 148 * 512));
+  cudaEvent_t e0, e1;
+  CARC_CHECK_CUDA(cudaEventCreate(&e0));
+  CARC_CHECK_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    CARC_CHECK_CUDA(cudaEventRecord(e0, stream));
+#define CARC_MIX(ND, NF) \
+  if (ndmma == ND && nfma == NF) fp64_mix_kernel<ND, NF><<<148, warps * 32, 0, stream>>>(buf, iters);
+    CARC_MIX(16, 0) CARC_MIX(16, 16) CARC_MIX(16, 32) CARC_MIX(16, 64) CARC_MIX(16, 128)
+    CARC_MIX(0, 16) CARC_MIX(0, 32) CARC_MIX(0, 64) CARC_MIX(0, 128)
+#undef CARC_MIX
+    CARC_CHECK_CUDA(cudaEventRecord(e1, stream));
+    CARC_CHECK_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    CARC_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  CARC_CHECK_CUDA(cudaGetLastError());
+  *tflops_dmma = 148.0 * warps * iters * (double)ndmma * 512.0 / (best * 1e-3) / 1e12;
+  *tflops_fma = 148.0 * warps * iters * (double)nfma * 64.0 / (best * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  return CARC_OK;
+}
 
 int index_table(int nlevels, const int64_t* extents, const int64_t* strides, int64_t* table, cudaStream_t stream) {
   CARC_REQUIRE(nlevels >= 0 && nlevels <= CARC_MAX_RANK, CARC_ERR_RANK, "index_table: %d levels unsupported", nlevels);

@@ -58,9 +58,14 @@ class Stage3Operator:
         return self
 
     def set_path(self, path):
-        """0 auto, 1 fused kernel only, 2 unfused DMMA GEMM path."""
+        """0 auto, 1 fused kernel only, 2 unfused DMMA GEMM path, 3 fused kernel with the folded tiling only."""
         check(lib.carc_operator_set_path(self._handle, int(path)))
         return self
+
+    @property
+    def path(self):
+        """The device path `__call__` runs: 1 fused kernel, 3 fused kernel with the folded tiling, 2 unfused GEMMs."""
+        return lib.carc_operator_path(self._handle)
 
     @property
     def num_terms(self):

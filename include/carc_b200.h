@@ -53,6 +53,11 @@ int carc_dmma_peak(int iters, double* tflops_out, void* stream);
 /* The same microbenchmark with `warps_per_sm` warps (one CTA per SM) and `chains` (2, 4, 8 or 16) independent
  * accumulator chains per warp: how the DMMA issue rate depends on occupancy and instruction-level parallelism. */
 int carc_dmma_rate(int iters, int warps_per_sm, int chains, double* tflops_out, void* stream);
+/* DMMA.8x8x4 and DFMA issued side by side (`ndmma` in {0, 16} and `nfma` in {0, 16, 32, 64, 128} instructions per loop
+ * trip and warp), rates reported separately in TFLOP/s: whether the FP64 tensor instruction and the FP64 FMA pipe
+ * overlap on this part decides whether tile padding / remainders can be moved off the tensor pipe. */
+int carc_fp64_mix_rate(int iters, int warps_per_sm, int ndmma, int nfma, double* tflops_dmma, double* tflops_fma,
+                       void* stream);
 
 /* ---- device memory for callers that do not bring their own allocator ------------------------------------ */
 int carc_malloc(void** ptr, size_t bytes);
@@ -120,8 +125,14 @@ int carc_operator_create(carc_operator** op, int P, int Q, int R, int S, int d);
 int carc_operator_add_term(carc_operator* op, const void* A, const void* B, int64_t X, const double* O_host);
 int carc_operator_finalize(carc_operator* op);
 int carc_operator_apply(carc_operator* op, const void* v, void* out, void* stream);
-/* force_path: 0 auto, 1 fused kernel only (error if the shape is unsupported), 2 unfused GEMM path */
+/* force_path: 0 auto, 1 fused kernel only (error if the shape is unsupported), 2 unfused GEMM path,
+ * 3 fused kernel with the folded tiling only (spin index folded into the tile columns; error if unsupported) */
 int carc_operator_set_path(carc_operator* op, int force_path);
+/* Which device path carc_operator_apply runs for this operator: 1 fused, 3 fused with the folded tiling, 2 unfused. */
+int carc_operator_path(const carc_operator* op);
+/* Diagnostics (library built with -DS3F_PROFILE only, else CARC_ERR_UNSUPPORTED): cycles every warp of the last
+ * folded-tiling launch spent in its three mbarrier waits and in total, [148][12][4] values. */
+int carc_stage3f_profile_read(unsigned long long* host);
 int carc_operator_num_terms(const carc_operator* op);
 /* cmac count the reference's CostTracker assigns to one apply (data/cost_tracker.py:17-21) */
 int64_t carc_operator_cost_of_multiply(const carc_operator* op);

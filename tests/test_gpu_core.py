@@ -196,7 +196,7 @@ def _stage3_case(rng, chi2, D, d=2, terms=1, dims=None):
 
 @pytest.mark.parametrize("chi2,D,terms", [(2, 2, 1), (4, 2, 3), (3, 3, 2), (4, 4, 2), (9, 3, 4), (5, 5, 1), (4, 6, 2),
                                           (3, 7, 1), (6, 8, 2)])
-@pytest.mark.parametrize("path", [1, 2])
+@pytest.mark.parametrize("path", [1, 2, 3])
 def test_stage3_operator(dd, chi2, D, terms, path):
     from carcassonne_b200.operator import Stage3Operator, prejoin_halves
     rng = np.random.default_rng(chi2 * 100 + D * 10 + terms)
@@ -214,21 +214,41 @@ def test_stage3_operator(dd, chi2, D, terms, path):
 
 
 @pytest.mark.parametrize("dims,d", [((2, 3, 3, 2), 2), ((1, 1, 1, 1), 2), ((3, 2, 2, 4), 3), ((2, 2, 2, 2), 1),
-                                     ((4, 4, 2, 2), 2), ((2, 2, 8, 8), 2)])
-def test_stage3_ragged_shapes(dd, dims, d):
+                                     ((4, 4, 2, 2), 2), ((2, 2, 8, 8), 2), ((3, 5, 7, 1), 2), ((7, 7, 5, 3), 2),
+                                     ((1, 5, 6, 6), 2)])
+@pytest.mark.parametrize("path", [0, 3])
+def test_stage3_ragged_shapes(dd, dims, d, path):
     from carcassonne_b200.operator import Stage3Operator, prejoin_halves
+    if path == 3 and d != 2:
+        pytest.skip("the folded tiling is specific to d = 2")
     rng = np.random.default_rng(sum(dims) + d)
     s2_0, s2_1, ops, v, ref = _stage3_case(rng, 3, None, d=d, terms=2, dims=dims)
     op = Stage3Operator(v.shape)
     for a, b, o in zip(s2_0, s2_1, ops):
         A, B = prejoin_halves(dd.fromArray(a), dd.fromArray(b))
         op.add_term(A, B, o)
+    op.finalize().set_path(path)
     out = op(dd.fromArray(v)).toArray()
     assert relerr(out, ref) < MATVEC_TOL
 
 
-@pytest.mark.parametrize("chi2,D", [(3, 2), (4, 4), (5, 8), (2, 6), (4, 3)])
-@pytest.mark.parametrize("path", [0, 2])
+def test_stage3_folded_rejects_other_physical_dimensions(dd):
+    """Forcing the folded tiling on a shape outside its envelope is an error, not a silent fallback."""
+    from carcassonne_b200 import _lib
+    from carcassonne_b200.operator import Stage3Operator, prejoin_halves
+    rng = np.random.default_rng(5)
+    s2_0, s2_1, ops, v, ref = _stage3_case(rng, 2, 2, d=3, terms=1)
+    op = Stage3Operator(v.shape)
+    A, B = prejoin_halves(dd.fromArray(s2_0[0]), dd.fromArray(s2_1[0]))
+    op.add_term(A, B, None).finalize().set_path(3)
+    with pytest.raises(Exception):
+        op(dd.fromArray(v))
+    op.set_path(0)
+    assert relerr(op(dd.fromArray(v)).toArray(), ref) < MATVEC_TOL
+
+
+@pytest.mark.parametrize("chi2,D", [(3, 2), (4, 4), (5, 8), (2, 6), (4, 3), (3, 5), (3, 7)])
+@pytest.mark.parametrize("path", [0, 1, 2, 3])
 def test_stage3_shared_tensors(dd, chi2, D, path):
     """The TFIM term structure of bench.py: 9 terms over 6 + 6 tensors, several sharing the same half-1 tensor (their
     first products are summed before one second product) and the same half-0 tensor."""

@@ -45,7 +45,7 @@ def _relerr(a, b):
     return float((a - b).norm() / b.norm())
 
 
-@pytest.mark.parametrize("D,chi", [(8, 12), (6, 16), (4, 24)])
+@pytest.mark.parametrize("D,chi", [(8, 12), (6, 16), (4, 24), (7, 12), (5, 16)])
 def test_matvec_properties_at_scale(D, chi):
     from carcassonne_b200.data import DeviceData
     X = chi ** 4
@@ -68,7 +68,12 @@ def test_matvec_properties_at_scale(D, chi):
     lo, hi = X // 2, X // 2 + 48
     fused = _operator(A, B, D, lo, hi, path=1)(DeviceData(v1))._t
     unfused = _operator(A, B, D, lo, hi, path=2)(DeviceData(v1))._t
+    folded = _operator(A, B, D, lo, hi, path=3)(DeviceData(v1))._t
     assert _relerr(fused, unfused) < 1e-12
+    assert _relerr(folded, unfused) < 1e-12
+    # both tilings of the fused kernel on the whole environment (whichever one the automatic choice did not take)
+    assert _relerr(_operator(A, B, D, path=1)(DeviceData(v1))._t, h1) < 1e-12
+    assert _relerr(_operator(A, B, D, path=3)(DeviceData(v1))._t, h1) < 1e-12
     from oracle import dense
     vh = v1.cpu().numpy()
     ref = sum(dense.stage3_multiply_joined(A[x]._t[lo:hi].cpu().numpy(), B[y]._t[lo:hi].cpu().numpy(), vh, o)
