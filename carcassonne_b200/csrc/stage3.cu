@@ -579,10 +579,13 @@ void s3_choose(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, int 
   *can_fuse = force_path != 2 && force_path != 3 && Xmax > 0 && s3_configure(nterms, P, Q, R, S, d, Xmax, k);
   *can_fold = force_path != 2 && force_path != 1 && Xmax > 0 && stage3f_configure(nterms, P, Q, R, S, d, Xmax, kf);
   if (*can_fuse && *can_fold) {
-    // both tilings fit: take the one that issues fewer DMMA steps for this shape (complex 8x8x4 steps per x and product
-    // pair; the folded tiling must win by a margin, its S blocks re-read A_x more often)
+    // Both tilings fit.  Take the one that issues fewer DMMA steps for this shape (complex 8x8x4 steps per x and product
+    // pair).  At equal work (P, Q, S multiples of 8 / 16: D = 4, 8) the measured winner depends on the work per op: the
+    // folded kernel's symmetric warps (every warp issues its own copies) win when an A_x tile is large (D = 8: 28.2 vs
+    // 27.6 TFLOP/s), stage3_kernel's single issuing warp when it is small (D = 4: 23.1 vs 21.1).
     const double work = (double)k->NPT * k->NSB * k->CH * (4.0 * k->Q8 + 4.0 * k->NRT);
-    if (kf->padded_work < 0.97 * work) *can_fuse = false;
+    const bool fold = kf->padded_work < 0.97 * work || (kf->padded_work <= 1.0001 * work && (int64_t)P * Q >= 1024);
+    if (fold) *can_fuse = false;
     else *can_fold = false;
   }
 }

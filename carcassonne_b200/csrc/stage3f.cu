@@ -14,6 +14,13 @@
 //     for both spins; its K extent is S rounded up to 4 instead of 16;
 //   * S blocks hold a whole number of tiles, spread as evenly as the shape allows (D = 7: 5 + 4 + 4 tiles), and the
 //     CTAs are shared out between the S blocks in proportion to their tile counts.
+// Warps are symmetric (no producer warp, and -- unlike stage3_kernel -- no producer role for warp 0 either: measured
+// there, the warp that issued all copies never waited while every other warp spent ~30 % of its time waiting for it):
+//   * a warp only ever reads its own 8 rows of A_x, so every warp owns a private TMA ring for those rows (its own
+//     full barriers, no empty barriers: it refills a slot itself after reading it);
+//   * the S block of B_x is shared by the warps of a group; each warp issues the row copies of its share of the rows
+//     (full barrier: one expect-tx arrival per warp) after waiting for the slot's empty barrier;
+//   * every warp runs the same producer cursor over the flattened op sequence, ahead of its consumer cursor.
 // DMMA work relative to stage3_kernel: 0.82 (D = 5), 0.86 (D = 6), 0.78 (D = 7), 0.66 (D = 3).
 #include <algorithm>
 #include <vector>
@@ -36,7 +43,7 @@ struct S3FParams {
   int Q4, NPT, G, NSB, nstA, nstB, QS, BSTR;
   int sb_cta0[S3F_MAX_SB + 1];    // CTAs [sb_cta0[i], sb_cta0[i+1]) work on S block i (one X slab each)
   int sb_tile0[S3F_MAX_SB + 1];   // S block i covers the tiles (4 S columns each) [sb_tile0[i], sb_tile0[i+1])
-  uint32_t slotA_bytes, slotB_bytes, ops_off, hasop_off, tab_off, vt_off, ring_off, smem_total;
+  uint32_t slotA_bytes, slotB_bytes, ops_off, hasop_off, tab_off, vt_off, vtail_off, ring_off, smem_total;
   const cplx* v;
   cplx* partial;
 };
@@ -61,12 +68,14 @@ __device__ unsigned long long s3f_prof[148 * 12 * 4];
 #endif
 
 struct S3FLane {
-  uint32_t a_pair, a_tail, v_pair, v_tail, tile_stride, a_first, a_second;
+  uint32_t a_pair, a_tail, v_pair, v_tail, tile_stride, tail_stride, a_first, a_second;
   int npairs, ntv;
   bool tail, eswap;
 };
 
-// T[jj] += A_x (8 rows of this warp) * Vt (tile jbase + jj), for the tiles below ntv
+// T[jj] += A_x (8 rows of this warp) * Vt (tile jbase + jj), for the tiles below ntv.  (Loading the next operands ahead
+// of the current DMMAs -- the asm statements keep their source order -- was measured: +2 % at D = 8, -5 % at D = 5
+// through spills, nothing at D = 6, 7; the plain order is kept.)
 template <int NJ>
 __device__ __forceinline__ void s3f_first(CTile (&T)[NJ], int jbase, const S3FLane& L, uint32_t slot) {
   const uint32_t a_base = slot + L.a_pair;
@@ -92,7 +101,7 @@ __device__ __forceinline__ void s3f_first(CTile (&T)[NJ], int jbase, const S3FLa
 #pragma unroll
     for (int jj = 0; jj < NJ; ++jj) {
       if (jbase + jj < L.ntv) {
-        const cplx b = lds_c(L.v_tail + (uint32_t)(jbase + jj) * L.tile_stride);
+        const cplx b = lds_c(L.v_tail + (uint32_t)(jbase + jj) * L.tail_stride);
         cmma(T[jj], a.x, a.y, -a.y, b.x, b.y);
       }
     }
@@ -121,14 +130,19 @@ __device__ __forceinline__ void s3f_apply_op(CTile& out, const CTile& U, const c
 }
 
 // acc[rt][s] += W (tile j, spin s) * B_x[8 rt .., 4 j ..]^T : W's C fragment is the A fragment, one B fragment per rt
+// (loaded one row tile ahead of the DMMAs that use it)
 template <int NRT>
 __device__ __forceinline__ void s3f_second(CTile (&acc)[NRT][2], const CTile& W, int j, uint32_t b_base, uint32_t rt_stride) {
   const double nim0 = -W.im0, nim1 = -W.im1;
+  const uint32_t bj = b_base + (uint32_t)j * 64;
+  cplx b = lds_c(bj);
 #pragma unroll
   for (int rt = 0; rt < NRT; ++rt) {
-    const cplx b = lds_c(b_base + rt * rt_stride + (uint32_t)j * 64);
+    cplx nb = b;
+    if (rt + 1 < NRT) nb = lds_c(bj + (rt + 1) * rt_stride);
     cmma(acc[rt][0], W.re0, W.im0, nim0, b.x, b.y);
     cmma(acc[rt][1], W.re1, W.im1, nim1, b.x, b.y);
+    b = nb;
   }
 }
 
@@ -140,12 +154,13 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r = lane >> 2, c = lane & 3;
   const int ncw = p.G * p.NPT;
-  const int nbar_g = 2 * (p.nstA + p.nstB);
+  const int nbar_g = p.NPT * p.nstA + 2 * p.nstB;   // per group: full A per (warp, stage), full B and empty B per stage
   const uint32_t bars = smem_u32(smem);
   cplx* ops = reinterpret_cast<cplx*>(smem + p.ops_off);
   cplx* Vt = reinterpret_cast<cplx*>(smem + p.vt_off);
+  cplx* VtTail = reinterpret_cast<cplx*>(smem + p.vtail_off);
   const int QS = p.QS, BSTR = p.BSTR;
-  const uint32_t group_bytes = p.nstA * p.slotA_bytes + p.nstB * p.slotB_bytes;
+  const uint32_t group_bytes = p.NPT * p.nstA * p.slotA_bytes + p.nstB * p.slotB_bytes;
 
   // zero everything behind the barriers: padding rows / columns must read as finite zeros forever
   {
@@ -156,13 +171,10 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
   if (tid == 0) {
     for (int g = 0; g < p.G; ++g) {
       const uint32_t b = bars + g * nbar_g * 8;
-      for (int i = 0; i < p.nstA; ++i) {
-        mbar_init(b + (2 * i) * 8, 1);           // full A
-        mbar_init(b + (2 * i + 1) * 8, p.NPT);   // empty A
-      }
+      for (int i = 0; i < p.NPT * p.nstA; ++i) mbar_init(b + i * 8, 1);   // full A, private to one warp
       for (int i = 0; i < p.nstB; ++i) {
-        mbar_init(b + (2 * p.nstA + 2 * i) * 8, 1);
-        mbar_init(b + (2 * p.nstA + 2 * i + 1) * 8, p.NPT);
+        mbar_init(b + (p.NPT * p.nstA + 2 * i) * 8, p.NPT);       // full B: every warp announces its rows
+        mbar_init(b + (p.NPT * p.nstA + 2 * i + 1) * 8, p.NPT);   // empty B
       }
     }
     fence_barrier_init();
@@ -196,9 +208,13 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
     groupCount[i] = p.groups[i].count;
   }
   // Vt[f = 2 * S_local + s][q] = v[q, S0 + S_local, s]
+  // (the trailing single k-step, q >= 8 * (Q4 / 2), lives in VtTail[f][4] so that its loads are conflict-free too)
   for (int i = tid; i < p.Q * SBv * DP; i += blockDim.x) {
     const int f = i % (DP * SBv), q = i / (DP * SBv);
-    Vt[f * QS + q] = p.v[((int64_t)q * p.S + S0) * DP + f];
+    const cplx val = p.v[((int64_t)q * p.S + S0) * DP + f];
+    const int qt = q - 8 * (p.Q4 >> 1);
+    if (qt < 0) Vt[f * QS + q] = val;
+    else VtTail[f * 4 + qt] = val;
   }
   fence_proxy_async();
   __syncthreads();
@@ -206,8 +222,10 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
   if (warp >= ncw) return;
   {
     const int g = warp / p.NPT, wg = warp % p.NPT;
-    const uint32_t b = bars + g * nbar_g * 8;
-    const uint32_t ring = smem_u32(smem + p.ring_off) + g * group_bytes;
+    const uint32_t bA = bars + (g * nbar_g + wg * p.nstA) * 8;          // this warp's full-A barriers
+    const uint32_t bB = bars + (g * nbar_g + p.NPT * p.nstA) * 8;       // the group's (full B, empty B) pairs
+    const uint32_t ringA = smem_u32(smem + p.ring_off) + g * group_bytes + wg * p.nstA * p.slotA_bytes;
+    const uint32_t ringB = smem_u32(smem + p.ring_off) + g * group_bytes + p.NPT * p.nstA * p.slotA_bytes;
     CTile acc[NRT][DP];
 #pragma unroll
     for (int i = 0; i < NRT; ++i)
@@ -225,11 +243,12 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
     L.eswap = ((p.Q & 1) == 0) && (r & 1);
     L.a_first = L.eswap ? 16u : 0u;
     L.a_second = 16u - L.a_first;
-    L.a_pair = (uint32_t)(((wg * 8 + r) * p.Q + 2 * c) * 16);
-    L.a_tail = (uint32_t)(((wg * 8 + r) * p.Q + 8 * L.npairs + c) * 16);
+    L.a_pair = (uint32_t)((r * p.Q + 2 * c) * 16);
+    L.a_tail = (uint32_t)((r * p.Q + 8 * L.npairs + c) * 16);
     L.v_pair = smem_u32(Vt) + (uint32_t)((r * QS + 2 * c) * 16);
-    L.v_tail = smem_u32(Vt) + (uint32_t)((r * QS + 8 * L.npairs + c) * 16);
+    L.v_tail = smem_u32(VtTail) + (uint32_t)((r * 4 + c) * 16);
     L.tile_stride = (uint32_t)(8 * QS * 16);
+    L.tail_stride = (uint32_t)(8 * 4 * 16);
     const uint32_t b_lane_off = (uint32_t)((r * BSTR + c) * 16);
     const uint32_t rt_stride = (uint32_t)(8 * BSTR * 16);
 
@@ -255,31 +274,35 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
       cu.j = 0;
       return next_item(cu);
     };
-    const uint32_t a_bytes = (uint32_t)(p.P * p.Q * 16);
+    // this warp's 8 rows of A_x (fewer in the last row tile: the rest of the slot stays zero)
+    const uint32_t a_bytes = (uint32_t)(min(8, p.P - 8 * wg) * p.Q * 16);
     const uint32_t b_row_bytes = (uint32_t)(SBv * 16);
+    // rows wg, wg + NPT, ... of the B block are this warp's to copy
+    const int my_rows = p.R > wg ? (p.R - wg + p.NPT - 1) / p.NPT : 0;
     auto issueA = [&](const Cursor& cu, uint32_t it) {
       const cplx* A = groupKind[cu.gi] ? groupCenter[cu.gi] : termA[groupFirst[cu.gi] + cu.j];
       const int sa = it % p.nstA;
-      const uint32_t fullA = b + (2 * sa) * 8;
       if (lane == 0) {
-        mbar_wait(fullA + 8, ((it / p.nstA) & 1) ^ 1);
-        mbar_arrive_expect_tx(fullA, a_bytes);
-        bulk_g2s(ring + sa * p.slotA_bytes, A + (int64_t)cu.x * p.P * p.Q, a_bytes, fullA);
+        // the slot was read by this warp's own lanes (all past the __syncwarp that follows every first product)
+        fence_proxy_async();
+        mbar_arrive_expect_tx(bA + sa * 8, a_bytes);
+        bulk_g2s(ringA + sa * p.slotA_bytes, A + ((int64_t)cu.x * p.P + 8 * wg) * p.Q, a_bytes, bA + sa * 8);
       }
-      __syncwarp();
     };
     auto issueB = [&](const Cursor& cu, uint32_t it) {
       const cplx* B = groupKind[cu.gi] ? termB[groupFirst[cu.gi] + cu.j - 1] : groupCenter[cu.gi];
       const int sbq = it % p.nstB;
-      const uint32_t fullB = b + (2 * p.nstA + 2 * sbq) * 8;
+      const uint32_t fullB = bB + (2 * sbq) * 8;
       if (lane == 0) {
         mbar_wait(fullB + 8, ((it / p.nstB) & 1) ^ 1);
-        mbar_arrive_expect_tx(fullB, b_row_bytes * p.R);
+        if (my_rows > 0) mbar_arrive_expect_tx(fullB, b_row_bytes * my_rows);
+        else mbar_arrive(fullB);
       }
       __syncwarp();
-      const uint32_t dst = ring + p.nstA * p.slotA_bytes + sbq * p.slotB_bytes;
+      const uint32_t dst = ringB + sbq * p.slotB_bytes;
       const cplx* src = B + ((int64_t)cu.x * p.R) * p.S + S0;
-      for (int rr = lane; rr < p.R; rr += 32) bulk_g2s(dst + rr * BSTR * 16, src + (int64_t)rr * p.S, b_row_bytes, fullB);
+      for (int rr = wg + p.NPT * lane; rr < p.R; rr += 32 * p.NPT)
+        bulk_g2s(dst + rr * BSTR * 16, src + (int64_t)rr * p.S, b_row_bytes, fullB);
     };
 
     Cursor cc = {-1, 0, 0, 0}, pc = {-1, 0, 0, 0};
@@ -309,13 +332,13 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
       const int kind = groupKind[cc.gi];
       {
         // ---- first term of the star: all tiles of the S block accumulate straight into T
-        if (wg == 0) run_ahead();
+        run_ahead();
         const bool has_op = !kind && hasop[first] != 0;   // an A-star keeps the raw product
         const int slot = itA % p.nstA;
-        S3F_WAIT(0, b + (2 * slot) * 8, (itA / p.nstA) & 1);
+        S3F_WAIT(0, bA + slot * 8, (itA / p.nstA) & 1);
 #pragma unroll
         for (int j = 0; j < NT; ++j) T[j].zero();
-        s3f_first<NT>(T, 0, L, ring + slot * p.slotA_bytes);
+        s3f_first<NT>(T, 0, L, ringA + slot * p.slotA_bytes);
         if (has_op) {
 #pragma unroll
           for (int j = 0; j < NT; ++j) {
@@ -325,18 +348,17 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(b + (2 * slot + 1) * 8);
         ++itA;
       }
       if (!kind) {
         for (int jt = 1; jt < cnt; ++jt) {
-          if (wg == 0) run_ahead();
+          run_ahead();
           // ---- a further term of a B-star: T += O (A_x v); without a site operator the DMMA chains simply continue
           const int term = first + jt;
           const bool has_op = hasop[term] != 0;
           const int slot = itA % p.nstA;
-          S3F_WAIT(1, b + (2 * slot) * 8, (itA / p.nstA) & 1);
-          const uint32_t aslot = ring + slot * p.slotA_bytes;
+          S3F_WAIT(1, bA + slot * 8, (itA / p.nstA) & 1);
+          const uint32_t aslot = ringA + slot * p.slotA_bytes;
           if (!has_op) {
             s3f_first<NT>(T, 0, L, aslot);
           } else {
@@ -352,31 +374,30 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
             }
           }
           __syncwarp();
-          if (lane == 0) mbar_arrive(b + (2 * slot + 1) * 8);
           ++itA;
         }
-        if (wg == 0) run_ahead();
+        run_ahead();
         // ---- second product of the star: acc += T * B_x^T
         {
           const int slot = itB % p.nstB;
-          S3F_WAIT(2, b + (2 * p.nstA + 2 * slot) * 8, (itB / p.nstB) & 1);
-          const uint32_t b_base = ring + p.nstA * p.slotA_bytes + slot * p.slotB_bytes + b_lane_off;
+          S3F_WAIT(2, bB + (2 * slot) * 8, (itB / p.nstB) & 1);
+          const uint32_t b_base = ringB + slot * p.slotB_bytes + b_lane_off;
 #pragma unroll
           for (int j = 0; j < NT; ++j)
             if (j < L.ntv) s3f_second<NRT>(acc, T[j], j, b_base, rt_stride);
           __syncwarp();
-          if (lane == 0) mbar_arrive(b + (2 * p.nstA + 2 * slot + 1) * 8);
+          if (lane == 0) mbar_arrive(bB + (2 * slot + 1) * 8);
           ++itB;
         }
       } else {
         // ---- A-star: T holds A_x v once; every term applies its own site operator and multiplies with its own B_x
         for (int jt = 0; jt < cnt; ++jt) {
-          if (wg == 0) run_ahead();
+          run_ahead();
           const int term = first + jt;
           const bool has_op = hasop[term] != 0;
           const int slot = itB % p.nstB;
-          S3F_WAIT(2, b + (2 * p.nstA + 2 * slot) * 8, (itB / p.nstB) & 1);
-          const uint32_t b_base = ring + p.nstA * p.slotA_bytes + slot * p.slotB_bytes + b_lane_off;
+          S3F_WAIT(2, bB + (2 * slot) * 8, (itB / p.nstB) & 1);
+          const uint32_t b_base = ringB + slot * p.slotB_bytes + b_lane_off;
 #pragma unroll
           for (int j = 0; j < NT; ++j) {
             if (j < L.ntv) {
@@ -391,7 +412,7 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
             }
           }
           __syncwarp();
-          if (lane == 0) mbar_arrive(b + (2 * p.nstA + 2 * slot + 1) * 8);
+          if (lane == 0) mbar_arrive(bB + (2 * slot + 1) * 8);
           ++itB;
         }
       }
@@ -479,26 +500,29 @@ bool stage3f_configure(int nterms, int P, int Q, int R, int S, int d, int64_t Xm
   k.sb_tile0[0] = 0;
   for (int i = 0; i < k.NSB; ++i) k.sb_tile0[i + 1] = k.sb_tile0[i] + ntt / k.NSB + (i < ntt % k.NSB ? 1 : 0);
   const int nt_block = k.sb_tile0[1];   // the widest block comes first
-  k.QS = k.Q4 * 4;
+  k.QS = (k.Q4 / 2) * 8;   // the paired k-steps; the trailing single step has its own array
   while (k.QS % 8 != 1) ++k.QS;
   k.BSTR = 4 * nt_block;
   while (k.BSTR % 8 != 4) ++k.BSTR;
-  k.slotA = (uint32_t)((k.NPT * 8 * Q + 8) * 16);
+  k.slotA = (uint32_t)((8 * Q + 8) * 16);   // one warp's 8 rows (+ the trailing k-step's overrun)
   k.slotB = (uint32_t)(k.NRT * 8 * k.BSTR * 16);
   const uint32_t vbytes = (uint32_t)(8 * nt_block * k.QS * 16);
+  const uint32_t vtail_bytes = (uint32_t)(8 * nt_block * 4 * 16);
   const uint32_t obytes = (uint32_t)(nterms * d * d * 16);
   int G = std::min(8, maxwarps / k.NPT);
   if (Xmax < G) G = (int)std::max<int64_t>(1, Xmax);
   for (; G >= 1; --G) {
     for (int nstA = 3; nstA >= 2; --nstA) {
       for (int nstB = 4; nstB >= nstA; --nstB) {
-        const uint32_t bar_bytes = (uint32_t)(((G * 2 * (nstA + nstB) * 8) + 127) / 128 * 128);
+        const uint32_t bar_bytes = (uint32_t)(((G * (k.NPT * nstA + 2 * nstB) * 8) + 127) / 128 * 128);
         const uint32_t ops_off = bar_bytes;
         const uint32_t hasop_off = ops_off + obytes;
         const uint32_t tab_off = (hasop_off + (uint32_t)nterms * 4 + 15) / 16 * 16;
         const uint32_t vt_off = (tab_off + (uint32_t)nterms * 16 + (uint32_t)nterms * 24 + 127) / 128 * 128;
-        const uint32_t ring_off = (vt_off + vbytes + 127) / 128 * 128;
-        const uint64_t total = (uint64_t)ring_off + (uint64_t)G * ((uint64_t)nstA * k.slotA + (uint64_t)nstB * k.slotB);
+        const uint32_t vtail_off = (vt_off + vbytes + 127) / 128 * 128;
+        const uint32_t ring_off = (vtail_off + vtail_bytes + 127) / 128 * 128;
+        const uint64_t total =
+            (uint64_t)ring_off + (uint64_t)G * ((uint64_t)k.NPT * nstA * k.slotA + (uint64_t)nstB * k.slotB);
         if (total > (uint64_t)S3F_SMEM_LIMIT) continue;
         k.G = G;
         k.nstA = nstA;
@@ -507,6 +531,7 @@ bool stage3f_configure(int nterms, int P, int Q, int R, int S, int d, int64_t Xm
         k.hasop_off = hasop_off;
         k.tab_off = tab_off;
         k.vt_off = vt_off;
+        k.vtail_off = vtail_off;
         k.ring_off = ring_off;
         k.total = (uint32_t)total;
         k.threads = G * k.NPT * 32;
@@ -548,7 +573,7 @@ int stage3f_launch(const Stage3Plan* plan, const Stage3FConfig& k, int P, int Q,
     p.sb_tile0[i] = i <= k.NSB ? k.sb_tile0[i] : 0;
   }
   p.slotA_bytes = k.slotA; p.slotB_bytes = k.slotB;
-  p.ops_off = k.ops_off; p.hasop_off = k.hasop_off; p.tab_off = k.tab_off; p.vt_off = k.vt_off; p.ring_off = k.ring_off;
+  p.ops_off = k.ops_off; p.hasop_off = k.hasop_off; p.tab_off = k.tab_off; p.vt_off = k.vt_off; p.vtail_off = k.vtail_off; p.ring_off = k.ring_off;
   p.smem_total = k.total;
   p.v = v;
   p.partial = partial;
