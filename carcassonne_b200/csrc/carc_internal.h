@@ -89,6 +89,7 @@ int stage3_path(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, int
 struct Stage3FConfig {
   int NPT, NRT, Q4, NSB, G, nstA, nstB, QS, BSTR;
   int sb_cta0[17], sb_tile0[17];
+  unsigned char cta_sb[160], cta_sl[160];
   uint32_t slotA, slotB, ops_off, hasop_off, tab_off, vt_off, vtail_off, ring_off, total;
   int threads, ctas, slots;
   double padded_work;

@@ -41,7 +41,8 @@ struct S3FParams {
   int nterms, ngroups;
   int P, Q, R, S;
   int Q4, NPT, G, NSB, nstA, nstB, QS, BSTR;
-  int sb_cta0[S3F_MAX_SB + 1];    // CTAs [sb_cta0[i], sb_cta0[i+1]) work on S block i (one X slab each)
+  int sb_cta0[S3F_MAX_SB + 1];    // S block i has sb_cta0[i+1] - sb_cta0[i] CTAs (one X slab each)
+  unsigned char cta_sb[160], cta_sl[160];   // CTA -> (S block, X slab): CTAs sharing a stretch of X are neighbours
   int sb_tile0[S3F_MAX_SB + 1];   // S block i covers the tiles (4 S columns each) [sb_tile0[i], sb_tile0[i+1])
   uint32_t slotA_bytes, slotB_bytes, ops_off, hasop_off, tab_off, vt_off, vtail_off, ring_off, smem_total;
   const cplx* v;
@@ -181,9 +182,8 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
   }
   __syncthreads();
 
-  int sb = 0;
-  while (sb + 1 < p.NSB && (int)blockIdx.x >= p.sb_cta0[sb + 1]) ++sb;
-  const int sl = (int)blockIdx.x - p.sb_cta0[sb], NSL = p.sb_cta0[sb + 1] - p.sb_cta0[sb];
+  const int sb = p.cta_sb[blockIdx.x], sl = p.cta_sl[blockIdx.x];
+  const int NSL = p.sb_cta0[sb + 1] - p.sb_cta0[sb];
   const int S0 = 4 * p.sb_tile0[sb];
   const int SBv = min(4 * (p.sb_tile0[sb + 1] - p.sb_tile0[sb]), p.S - S0);
   int* hasop = reinterpret_cast<int*>(smem + p.hasop_off);
@@ -549,6 +549,25 @@ bool stage3f_configure(int nterms, int P, int Q, int R, int S, int d, int64_t Xm
         }
         k.ctas = used;
         k.slots = used * G;
+        // CTA numbering: the CTAs of different S blocks that stream the same stretch of X read the same A_x; neighbours
+        // in blockIdx are placed on neighbouring SMs (same die, same L2 partition), so order all CTAs by the position of
+        // their slab (measured at D = 8: 73.6 GB of DRAM reads per launch with S-block-major numbering, 1.43 x the
+        // tensors' size)
+        {
+          int next[S3F_MAX_SB] = {0};
+          for (int c = 0; c < used; ++c) {
+            int best = -1;
+            double best_pos = 0.0;
+            for (int i = 0; i < k.NSB; ++i) {
+              const int n = k.sb_cta0[i + 1] - k.sb_cta0[i];
+              if (next[i] >= n) continue;
+              const double pos = (next[i] + 0.5) / n;
+              if (best < 0 || pos < best_pos) { best = i; best_pos = pos; }
+            }
+            k.cta_sb[c] = (unsigned char)best;
+            k.cta_sl[c] = (unsigned char)next[best]++;
+          }
+        }
         // DMMA work per x and product pair, in complex 8x8x4 steps, for the choice between the two kernels
         k.padded_work = (double)k.NPT * ntt * ((double)k.Q4 + 2.0 * k.NRT);
         *cfg = k;
@@ -571,6 +590,10 @@ int stage3f_launch(const Stage3Plan* plan, const Stage3FConfig& k, int P, int Q,
   for (int i = 0; i <= S3F_MAX_SB; ++i) {
     p.sb_cta0[i] = i <= k.NSB ? k.sb_cta0[i] : 0;
     p.sb_tile0[i] = i <= k.NSB ? k.sb_tile0[i] : 0;
+  }
+  for (int c = 0; c < 160; ++c) {
+    p.cta_sb[c] = c < k.ctas ? k.cta_sb[c] : 0;
+    p.cta_sl[c] = c < k.ctas ? k.cta_sl[c] : 0;
   }
   p.slotA_bytes = k.slotA; p.slotB_bytes = k.slotB;
   p.ops_off = k.ops_off; p.hasop_off = k.hasop_off; p.tab_off = k.tab_off; p.vt_off = k.vt_off; p.vtail_off = k.vtail_off; p.ring_off = k.ring_off;
