@@ -43,6 +43,7 @@ SIGNATURES = {
     "carc_mode_product": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp]),
     "carc_mul": (c_int, [c_i64, c_vp, c_vp, c_vp]),
     "carc_dotc": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "carc_dotu": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp]),
     "carc_sumsq": (c_int, [c_i64, c_vp, c_vp, c_vp]),
     "carc_count_nonfinite": (c_int, [c_i64, c_vp, c_vp, c_vp]),
     "carc_operator_num_groups": (c_int, [c_vp]),

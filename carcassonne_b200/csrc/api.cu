@@ -105,6 +105,9 @@ int carc_mul(int64_t n, const void* x, void* y, void* stream) {
 int carc_dotc(int64_t n, const void* x, const void* y, void* out, void* stream) {
   return carc::reduce(0, n, (const cplx*)x, (const cplx*)y, (double2*)out, S(stream));
 }
+int carc_dotu(int64_t n, const void* x, const void* y, void* out, void* stream) {
+  return carc::reduce(3, n, (const cplx*)x, (const cplx*)y, (double2*)out, S(stream));
+}
 int carc_sumsq(int64_t n, const void* x, void* out, void* stream) {
   return carc::reduce(1, n, (const cplx*)x, nullptr, (double2*)out, S(stream));
 }

@@ -4,6 +4,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <vector>
+
 #include "carc_internal.h"
 #include "common.cuh"
 
@@ -103,6 +105,77 @@ __global__ void __launch_bounds__(256) permute_tiled_kernel(const cplx* __restri
   }
 }
 
+// Block variant for permutations whose trailing destination axes are a rearrangement of the trailing source axes (the
+// Hermitian symmetrisation join(1,0,2,4,3,5,7,6) of system/_2d.py:42-47, every join that only swaps small state-bond
+// axes): the tensor is an array of m-element blocks that are contiguous in BOTH layouts, so a warp reads a block with
+// coalesced 16-byte loads, rearranges it through shared memory with a small index table and writes it coalesced.
+// The outer (block) index goes through the generic stride walk once per block instead of once per element.
+struct PermuteBlockParams {
+  int nd;                              // outer axes
+  int32_t m;                           // elements per block
+  int64_t nblocks;
+  int32_t outer_dim[CARC_MAX_RANK];    // extents of the outer axes in dst order
+  int64_t outer_src_stride[CARC_MAX_RANK];
+  const int32_t* inner_src;            // [m]: source offset inside the block of destination element j
+};
+
+template <bool CONJ>
+__global__ void __launch_bounds__(256) permute_block_kernel(const cplx* __restrict__ src, cplx* __restrict__ dst,
+                                                            PermuteBlockParams p) {
+  extern __shared__ __align__(16) unsigned char pb_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  cplx* buf = reinterpret_cast<cplx*>(pb_smem) + (size_t)warp * p.m;
+  int32_t* table = reinterpret_cast<int32_t*>(reinterpret_cast<cplx*>(pb_smem) + (size_t)nwarps * p.m);
+  for (int j = threadIdx.x; j < p.m; j += blockDim.x) table[j] = p.inner_src[j];
+  __syncthreads();
+  for (int64_t blk = (int64_t)blockIdx.x * nwarps + warp; blk < p.nblocks; blk += (int64_t)gridDim.x * nwarps) {
+    int64_t rem = blk, off = 0;
+#pragma unroll 1
+    for (int a = p.nd - 1; a > 0; --a) {
+      const int64_t q = rem / p.outer_dim[a];
+      off += (rem - q * p.outer_dim[a]) * p.outer_src_stride[a];
+      rem = q;
+    }
+    if (p.nd > 0) off += rem * p.outer_src_stride[0];
+    const cplx* s = src + off;
+    for (int j = lane; j < p.m; j += 32) buf[j] = __ldg(s + j);
+    __syncwarp();
+    cplx* d = dst + blk * p.m;
+    for (int j = lane; j < p.m; j += 32) {
+      cplx v = buf[table[j]];
+      if (CONJ) v.y = -v.y;
+      d[j] = v;
+    }
+    __syncwarp();
+  }
+}
+
+// device copies of inner index tables, keyed by their content (a handful of distinct joins per run)
+struct BlockTable {
+  std::vector<int32_t> host;
+  int32_t* dev;
+  int device;
+};
+static std::vector<BlockTable> g_block_tables;
+
+static int block_table(const std::vector<int32_t>& t, const int32_t** out) {
+  int dev = 0;
+  CARC_CHECK_CUDA(cudaGetDevice(&dev));
+  for (const auto& e : g_block_tables)
+    if (e.device == dev && e.host == t) {
+      *out = e.dev;
+      return CARC_OK;
+    }
+  BlockTable e;
+  e.host = t;
+  e.device = dev;
+  CARC_CHECK_CUDA(cudaMalloc(&e.dev, sizeof(int32_t) * t.size()));
+  CARC_CHECK_CUDA(cudaMemcpy(e.dev, t.data(), sizeof(int32_t) * t.size(), cudaMemcpyHostToDevice));
+  g_block_tables.push_back(e);
+  *out = e.dev;
+  return CARC_OK;
+}
+
 int permute(const cplx* src, cplx* dst, int ndim, const int64_t* shape, const int32_t* perm, int conj, int accumulate,
             cudaStream_t stream) {
   CARC_REQUIRE(ndim >= 0 && ndim <= 32, CARC_ERR_RANK, "permute: rank %d out of range", ndim);
@@ -143,6 +216,70 @@ int permute(const cplx* src, cplx* dst, int ndim, const int64_t* shape, const in
                CARC_MAX_RANK);
   for (int a = 0; a < nd; ++a)
     CARC_REQUIRE(dim[a] < (1ll << 31), CARC_ERR_VALUE, "permute: axis extent too large");
+
+  // block path: the last k >= 2 dst axes are exactly the last k source axes in another order, 8 <= m <= 1024 elements
+  if (!accumulate && nd >= 2 && str[nd - 1] != 1) {
+    // source order of the canonical axes: sort by stride (descending)
+    int order[32];
+    for (int a = 0; a < nd; ++a) order[a] = a;
+    for (int a = 0; a < nd; ++a)
+      for (int b = a + 1; b < nd; ++b)
+        if (str[order[b]] > str[order[a]]) { int t = order[a]; order[a] = order[b]; order[b] = t; }
+    int k = 0;
+    int64_t m = 1;
+    for (int kk = 2; kk <= nd; ++kk) {
+      // are dst axes [nd-kk, nd) the same set as the source's last kk axes?
+      bool same = true;
+      int64_t mm = 1;
+      for (int a = nd - kk; a < nd && same; ++a) {
+        bool found = false;
+        for (int b = nd - kk; b < nd; ++b) found = found || order[b] == a;
+        same = found;
+        mm *= dim[a];
+      }
+      if (same) { k = kk; m = mm; break; }
+    }
+    if (k >= 2 && k < nd && m >= 8 && m <= 1024) {
+      // inside a block the source is contiguous (its last k axes), so offsets are the strides themselves
+      std::vector<int32_t> table((size_t)m);
+      for (int64_t j = 0; j < m; ++j) {
+        int64_t rem = j, off = 0;
+        for (int a = nd - 1; a >= nd - k; --a) {
+          off += (rem % dim[a]) * str[a];
+          rem /= dim[a];
+        }
+        table[(size_t)j] = (int32_t)off;
+      }
+      PermuteBlockParams p;
+      int rc = block_table(table, &p.inner_src);
+      if (rc) return rc;
+      p.nd = nd - k;
+      p.m = (int32_t)m;
+      p.nblocks = total / m;
+      for (int a = 0; a < nd - k; ++a) {
+        p.outer_dim[a] = (int32_t)dim[a];
+        p.outer_src_stride[a] = str[a];
+      }
+      const int threads = 256, nwarps = threads / 32;
+      const size_t smem = (size_t)nwarps * m * sizeof(cplx) + (size_t)m * sizeof(int32_t);
+      static bool configured[16] = {false};
+      int dev = 0;
+      CARC_CHECK_CUDA(cudaGetDevice(&dev));
+      if (dev < 16 && !configured[dev]) {
+        CARC_CHECK_CUDA(cudaFuncSetAttribute(permute_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        CARC_CHECK_CUDA(cudaFuncSetAttribute(permute_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        configured[dev] = true;
+      }
+      int64_t want = (p.nblocks + nwarps - 1) / nwarps;
+      unsigned blocks = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+      if (conj)
+        permute_block_kernel<true><<<blocks, threads, smem, stream>>>(src, dst, p);
+      else
+        permute_block_kernel<false><<<blocks, threads, smem, stream>>>(src, dst, p);
+      CARC_CHECK_CUDA(cudaGetLastError());
+      return CARC_OK;
+    }
+  }
 
   // tiled path: source-innermost axis exists in dst at position j != nd-1 with reasonable extents
   if (!accumulate && nd >= 2 && str[nd - 1] != 1) {
@@ -285,7 +422,7 @@ __device__ __forceinline__ void block_reduce2(double& a, double& b, double* sh) 
   }
 }
 
-template <int MODE>  // 0: dotc(x,y)  1: sum |x|^2 (real)  2: nan/inf count
+template <int MODE>  // 0: dotc(x,y)  1: sum |x|^2 (real)  2: nan/inf count  3: dotu(x,y) = sum x*y
 __global__ void __launch_bounds__(256) reduce_kernel(int64_t n, const cplx* __restrict__ x, const cplx* __restrict__ y,
                                                      double2* __restrict__ out, ReduceWorkspace ws) {
   __shared__ double sh[16];
@@ -298,6 +435,10 @@ __global__ void __launch_bounds__(256) reduce_kernel(int64_t n, const cplx* __re
       cplx v = y[i];
       a += u.x * v.x + u.y * v.y;
       b += u.x * v.y - u.y * v.x;
+    } else if (MODE == 3) {
+      cplx v = y[i];
+      a += u.x * v.x - u.y * v.y;
+      b += u.x * v.y + u.y * v.x;
     } else if (MODE == 1) {
       a += u.x * u.x + u.y * u.y;
     } else {
@@ -354,6 +495,8 @@ int reduce(int mode, int64_t n, const cplx* x, const cplx* y, double2* out_dev, 
     reduce_kernel<0><<<g, 256, 0, stream>>>(n, x, y, out_dev, ws);
   else if (mode == 1)
     reduce_kernel<1><<<g, 256, 0, stream>>>(n, x, y, out_dev, ws);
+  else if (mode == 3)
+    reduce_kernel<3><<<g, 256, 0, stream>>>(n, x, y, out_dev, ws);
   else
     reduce_kernel<2><<<g, 256, 0, stream>>>(n, x, y, out_dev, ws);
   CARC_CHECK_CUDA(cudaGetLastError());

@@ -285,8 +285,7 @@ class DeviceData:
         """sum_i self_i * other_i (no conjugation; data/__init__.py:160-163); returns a host complex scalar."""
         self._check_same_shape(other)
         buf = _scalar_buffer()
-        tmp = self.conj()
-        check(lib.carc_dotc(self.size(), _ptr(tmp._t), _ptr(other._t), _ptr(buf), _stream()))
+        check(lib.carc_dotu(self.size(), _ptr(self._t), _ptr(other._t), _ptr(buf), _stream()))
         r = buf.cpu().numpy()
         return np.complex128(complex(r[0], r[1]))
 

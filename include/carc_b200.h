@@ -87,6 +87,7 @@ int carc_mul(int64_t n, const void* x, void* y, void* stream);
 /* ---- reductions (NDArrayData.norm, contractWithAlongAll, hasNaN; utils.py:845-870 Arnoldi scalars) --------
  * Results are written to DEVICE memory (two doubles) so iteration loops never synchronise. */
 int carc_dotc(int64_t n, const void* x, const void* y, void* out2_dev, void* stream); /* sum conj(x) y  */
+int carc_dotu(int64_t n, const void* x, const void* y, void* out2_dev, void* stream); /* sum x y: contractWithAlongAll (data/__init__.py:160-163) */
 int carc_sumsq(int64_t n, const void* x, void* out2_dev, void* stream);               /* (sum |x|^2, 0) */
 int carc_count_nonfinite(int64_t n, const void* x, void* out2_dev, void* stream);     /* (#nonfinite, #nan) */
 

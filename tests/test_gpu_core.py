@@ -30,6 +30,12 @@ def dd():
     ((5, 40, 3, 36), (2, 3, 0, 1)),
     ((2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2), (11, 0, 9, 2, 7, 4, 5, 6, 3, 8, 1, 10)),
     ((4, 4, 1, 4, 4, 1, 3, 3), (1, 0, 2, 4, 3, 5, 7, 6)),
+    # trailing axes rearranged among themselves (block path): Hermitian symmetrisation at D = 8, small state-bond swaps
+    ((6, 5, 1, 4, 3, 1, 8, 8), (1, 0, 2, 4, 3, 5, 7, 6)),
+    ((37, 3, 4, 5), (0, 3, 2, 1)),
+    ((3, 7, 2, 3, 2, 3), (1, 0, 4, 5, 2, 3)),
+    ((9, 11, 32, 32), (1, 0, 3, 2)),
+    ((5, 2, 2, 2, 2, 2, 2), (0, 6, 5, 4, 3, 2, 1)),
 ])
 def test_permute(dd, shape, perm):
     rng = np.random.default_rng(0)
@@ -174,6 +180,7 @@ def test_elementwise_and_reductions(dd):
     assert relerr(A.conj().toArray(), a.conj()) == 0
     assert abs(A.norm() - np.linalg.norm(a)) < 1e-13 * np.linalg.norm(a)
     assert abs(A.contractWithAlongAll(B) - np.sum(a * b)) < 1e-12
+    assert abs(A.conj().contractWithAlongAll(B) - np.vdot(a, b)) < 1e-12
     Cc = A.copy()
     Cc += B
     assert relerr(Cc.toArray(), a + b) < 1e-15
