@@ -87,7 +87,7 @@ int stage3_path(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, int
 
 // stage3f.cu: the folded tiling of the fused kernel (spin index folded into the columns of the first product)
 struct Stage3FConfig {
-  int NPT, NRT, Q4, NSB, G, nstA, nstB, QS, BSTR;
+  int NPT, NRT, Q4, NSB, G, nstA, nstB, QS, BSTR, b_whole;
   int sb_cta0[17], sb_tile0[17];
   unsigned char cta_sb[160], cta_sl[160];
   uint32_t slotA, slotB, ops_off, hasop_off, tab_off, vt_off, vtail_off, ring_off, total;

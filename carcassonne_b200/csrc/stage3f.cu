@@ -41,6 +41,7 @@ struct S3FParams {
   int nterms, ngroups;
   int P, Q, R, S;
   int Q4, NPT, G, NSB, nstA, nstB, QS, BSTR;
+  int b_whole;                    // one S block: B_x is one contiguous copy, issued by the warps in turn
   int sb_cta0[S3F_MAX_SB + 1];    // S block i has sb_cta0[i+1] - sb_cta0[i] CTAs (one X slab each)
   unsigned char cta_sb[160], cta_sl[160];   // CTA -> (S block, X slab): CTAs sharing a stretch of X are neighbours
   int sb_tile0[S3F_MAX_SB + 1];   // S block i covers the tiles (4 S columns each) [sb_tile0[i], sb_tile0[i+1])
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
       const uint32_t b = bars + g * nbar_g * 8;
       for (int i = 0; i < p.NPT * p.nstA; ++i) mbar_init(b + i * 8, 1);   // full A, private to one warp
       for (int i = 0; i < p.nstB; ++i) {
-        mbar_init(b + (p.NPT * p.nstA + 2 * i) * 8, p.NPT);       // full B: every warp announces its rows
+        mbar_init(b + (p.NPT * p.nstA + 2 * i) * 8, p.b_whole ? 1 : p.NPT);   // full B: every warp announces its rows
         mbar_init(b + (p.NPT * p.nstA + 2 * i + 1) * 8, p.NPT);   // empty B
       }
     }
@@ -293,13 +294,22 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
       const cplx* B = groupKind[cu.gi] ? termB[groupFirst[cu.gi] + cu.j - 1] : groupCenter[cu.gi];
       const int sbq = it % p.nstB;
       const uint32_t fullB = bB + (2 * sbq) * 8;
+      const uint32_t dst = ringB + sbq * p.slotB_bytes;
+      if (p.b_whole) {
+        // the S block is all of S: B_x is contiguous (row stride S), one copy, issued by the group's warps in turn
+        if ((int)(it % (uint32_t)p.NPT) == wg && lane == 0) {
+          mbar_wait(fullB + 8, ((it / p.nstB) & 1) ^ 1);
+          mbar_arrive_expect_tx(fullB, (uint32_t)(p.R * p.S * 16));
+          bulk_g2s(dst, B + (int64_t)cu.x * p.R * p.S, (uint32_t)(p.R * p.S * 16), fullB);
+        }
+        return;
+      }
       if (lane == 0) {
         mbar_wait(fullB + 8, ((it / p.nstB) & 1) ^ 1);
         if (my_rows > 0) mbar_arrive_expect_tx(fullB, b_row_bytes * my_rows);
         else mbar_arrive(fullB);
       }
       __syncwarp();
-      const uint32_t dst = ringB + sbq * p.slotB_bytes;
       const cplx* src = B + ((int64_t)cu.x * p.R) * p.S + S0;
       for (int rr = wg + p.NPT * lane; rr < p.R; rr += 32 * p.NPT)
         bulk_g2s(dst + rr * BSTR * 16, src + (int64_t)rr * p.S, b_row_bytes, fullB);
@@ -504,8 +514,13 @@ bool stage3f_configure(int nterms, int P, int Q, int R, int S, int d, int64_t Xm
   while (k.QS % 8 != 1) ++k.QS;
   k.BSTR = 4 * nt_block;
   while (k.BSTR % 8 != 4) ++k.BSTR;
+  // One S block: B_x is contiguous in memory, so it is staged with its own row stride by a single copy instead of R
+  // row copies (the per-copy issue cost is what limits the small shapes; the 2-way bank conflict that a row stride of
+  // 0 mod 8 causes on the B fragments is the smaller price)
+  k.b_whole = k.NSB == 1 ? 1 : 0;
+  if (k.b_whole) k.BSTR = S;
   k.slotA = (uint32_t)((8 * Q + 8) * 16);   // one warp's 8 rows (+ the trailing k-step's overrun)
-  k.slotB = (uint32_t)(k.NRT * 8 * k.BSTR * 16);
+  k.slotB = (uint32_t)((k.NRT * 8 * k.BSTR + 4) * 16);   // + the last row's overrun into padded columns
   const uint32_t vbytes = (uint32_t)(8 * nt_block * k.QS * 16);
   const uint32_t vtail_bytes = (uint32_t)(8 * nt_block * 4 * 16);
   const uint32_t obytes = (uint32_t)(nterms * d * d * 16);
@@ -587,6 +602,7 @@ int stage3f_launch(const Stage3Plan* plan, const Stage3FConfig& k, int P, int Q,
   p.ngroups = (int)plan->groups.size();
   p.P = P; p.Q = Q; p.R = R; p.S = S;
   p.Q4 = k.Q4; p.NPT = k.NPT; p.G = k.G; p.NSB = k.NSB; p.nstA = k.nstA; p.nstB = k.nstB; p.QS = k.QS; p.BSTR = k.BSTR;
+  p.b_whole = k.b_whole;
   for (int i = 0; i <= S3F_MAX_SB; ++i) {
     p.sb_cta0[i] = i <= k.NSB ? k.sb_cta0[i] : 0;
     p.sb_tile0[i] = i <= k.NSB ? k.sb_tile0[i] : 0;
