@@ -250,6 +250,40 @@ class RelativeStateDifferenceThresholdConvergencePolicy(_LastCurrent):
         self.current = self.system.state_center_data
 
 
+class BoundedConvergencePolicy(ConvergencePolicy):
+    """Not in the reference.  Wraps another convergence policy: additionally reports convergence after
+    ``maximum_updates`` updates, and raises ``FloatingPointError`` as soon as the wrapped policy's tracked value stops
+    being finite -- a NaN compares false against every threshold, so the reference's run loop (base.py:87-111) would
+    never return once the environment's norm has under- or overflowed (the reference never
+    renormalises a full-2D run)."""
+
+    def __init__(self, policy, maximum_updates):
+        self.policy = policy
+        self.maximum_updates = maximum_updates
+
+    def createBindingToSystem(self, system):
+        binding = _Binding(self, system)
+        binding.inner = self.policy.createBindingToSystem(system)
+        binding.updates = 0
+        return binding
+
+    def reset(self):
+        self.inner.reset()
+        self.updates = 0
+
+    def update(self):
+        self.inner.update()
+        self.updates += 1
+        value = getattr(self.inner, "current", None)
+        if isinstance(value, (int, float, complex, np.number)) and not np.isfinite(value):
+            raise FloatingPointError("convergence value is not finite after {} updates: {}".format(self.updates, value))
+
+    def converged(self):
+        if self.updates >= self.maximum_updates:
+            return True
+        return self.inner.converged()
+
+
 # -- hooks ----------------------------------------------------------------------------------------------------------
 class HookPolicy(Policy):
     def __init__(self, callback):
@@ -269,6 +303,6 @@ __all__ = [
     "RelativeEstimatedOneSiteExpectationDifferenceThresholdConvergencePolicy",
     "RelativeExpectationDifferenceDifferenceThresholdConvergencePolicy",
     "RelativeOneSiteExpectationDifferenceThresholdConvergencePolicy",
-    "RelativeStateDifferenceThresholdConvergencePolicy",
+    "RelativeStateDifferenceThresholdConvergencePolicy", "BoundedConvergencePolicy",
     "HookPolicy",
 ]
