@@ -241,6 +241,23 @@ int carc_operator_path(const carc_operator* op) {
   return carc::stage3_path((int)op->terms.size(), op->P, op->Q, op->R, op->S, op->d, Xmax, op->force_path);
 }
 int carc_stage3f_profile_read(unsigned long long* host) { return carc::stage3f_profile_read(host); }
+int carc_stage3f_describe(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, int32_t* out, int out_len) {
+  CARC_REQUIRE(out != nullptr && out_len >= 16 + 17 + 17 + 160 + 160, CARC_ERR_VALUE, "stage3f_describe: buffer too small");
+  carc::Stage3FConfig k;
+  if (!carc::stage3f_configure(nterms, P, Q, R, S, d, Xmax, &k)) {
+    carc::set_error("stage3f_describe: shape outside the folded kernel's envelope");
+    return CARC_ERR_UNSUPPORTED;
+  }
+  const int32_t head[16] = {k.NPT, k.NRT, k.Q4, k.NSB, k.G, k.nstA, k.nstB, k.QS, k.BSTR, k.b_whole, k.threads, k.ctas,
+                            k.slots, (int32_t)k.total, (int32_t)k.slotA, (int32_t)k.slotB};
+  int o = 0;
+  for (int i = 0; i < 16; ++i) out[o++] = head[i];
+  for (int i = 0; i < 17; ++i) out[o++] = i <= k.NSB ? k.sb_tile0[i] : -1;
+  for (int i = 0; i < 17; ++i) out[o++] = i <= k.NSB ? k.sb_cta0[i] : -1;
+  for (int i = 0; i < 160; ++i) out[o++] = i < k.ctas ? k.cta_sb[i] : -1;
+  for (int i = 0; i < 160; ++i) out[o++] = i < k.ctas ? k.cta_sl[i] : -1;
+  return CARC_OK;
+}
 int carc_operator_num_groups(const carc_operator* op) { return (op && op->plan) ? (int)op->plan->groups.size() : -1; }
 
 int carc_operator_apply(carc_operator* op, const void* v, void* out, void* stream) {

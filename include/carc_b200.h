@@ -134,6 +134,11 @@ int carc_operator_path(const carc_operator* op);
 /* Diagnostics (library built with -DS3F_PROFILE only, else CARC_ERR_UNSUPPORTED): cycles every warp of the last
  * folded-tiling launch spent in its three mbarrier waits and in total, [148][12][4] values. */
 int carc_stage3f_profile_read(unsigned long long* host);
+/* Host-side launch plan of the folded fused kernel for one shape (no device call): out = {NPT, NRT, Q4, NSB, G, nstA,
+ * nstB, QS, BSTR, b_whole, threads, ctas, slots, smem bytes, A slot bytes, B slot bytes}, then sb_tile0[17], sb_cta0[17],
+ * cta_sb[160], cta_sl[160] (-1 beyond the used entries); CARC_ERR_UNSUPPORTED outside the kernel's envelope.  What the
+ * CPU test suite checks the work partition with. */
+int carc_stage3f_describe(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, int32_t* out, int out_len);
 int carc_operator_num_terms(const carc_operator* op);
 /* cmac count the reference's CostTracker assigns to one apply (data/cost_tracker.py:17-21) */
 int64_t carc_operator_cost_of_multiply(const carc_operator* op);

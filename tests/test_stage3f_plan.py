@@ -1,0 +1,91 @@
+"""Host-side launch plan of the folded fused kernel (csrc/stage3f.cu: stage3f_configure) checked on the CPU through
+carc_stage3f_describe: the S blocks tile S exactly once, every environment index x is visited exactly once per S block
+by the (CTA, group) work items -- walked with the kernel's own slab formula -- and the launch fits the SM."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from carcassonne_b200 import _lib
+
+SMEM_LIMIT = 227 * 1024
+
+
+def describe(P, Q, R, S, X, nterms=9):
+    buf = np.full(16 + 17 + 17 + 160 + 160, -7, dtype=np.int32)
+    rc = _lib.lib.carc_stage3f_describe(nterms, P, Q, R, S, 2, X, buf.ctypes.data, len(buf))
+    if rc == _lib.ERR_UNSUPPORTED:
+        return None
+    assert rc == 0
+    keys = ("NPT", "NRT", "Q4", "NSB", "G", "nstA", "nstB", "QS", "BSTR", "b_whole", "threads", "ctas", "slots", "smem",
+            "slotA", "slotB")
+    k = dict(zip(keys, (int(x) for x in buf[:16])))
+    k["sb_tile0"] = buf[16:33]
+    k["sb_cta0"] = buf[33:50]
+    k["cta_sb"] = buf[50:210]
+    k["cta_sl"] = buf[210:370]
+    return k
+
+
+def check_plan(P, Q, R, S, X):
+    k = describe(P, Q, R, S, X)
+    assert k is not None
+    # the launch fits one SM: one CTA per SM, register-file split of 2 / 3 warps per sub-partition, shared memory
+    assert 1 <= k["ctas"] <= 148 and k["slots"] == k["ctas"] * k["G"]
+    assert k["threads"] == 32 * k["G"] * k["NPT"] and k["threads"] <= (256 if k["NRT"] >= 7 else 384)
+    assert k["smem"] <= SMEM_LIMIT
+    assert k["NPT"] == -(-P // 8) and k["NRT"] == -(-R // 8) and k["Q4"] == -(-Q // 4)
+    # strides that keep the fragment loads conflict-free, and room for the copies
+    assert k["QS"] % 8 == 1 and k["QS"] >= 8 * (k["Q4"] // 2)
+    nsb = k["NSB"]
+    tiles = k["sb_tile0"][:nsb + 1]
+    assert tiles[0] == 0 and tiles[-1] == -(-S // 4) and all(b > a for a, b in zip(tiles, tiles[1:]))
+    widest = max(b - a for a, b in zip(tiles, tiles[1:]))
+    if k["b_whole"]:
+        assert nsb == 1 and k["BSTR"] == S
+    else:
+        assert k["BSTR"] % 8 == 4 and k["BSTR"] >= 4 * widest
+    assert k["slotA"] >= (8 * Q + 4) * 16 and k["slotB"] >= k["NRT"] * 8 * k["BSTR"] * 16
+    # CTA table: a permutation of (S block, slab) pairs
+    ctas0 = k["sb_cta0"][:nsb + 1]
+    assert ctas0[0] == 0 and ctas0[-1] == k["ctas"]
+    pairs = {(int(k["cta_sb"][c]), int(k["cta_sl"][c])) for c in range(k["ctas"])}
+    assert pairs == {(i, s) for i in range(nsb) for s in range(ctas0[i + 1] - ctas0[i])}
+    assert all(x == -1 for x in k["cta_sb"][k["ctas"]:])
+    # every x exactly once per S block, walking the kernel's slab formula
+    for i in range(nsb):
+        nsl = int(ctas0[i + 1] - ctas0[i])
+        seen = np.zeros(X, dtype=np.int32)
+        for sl in range(nsl):
+            lo, hi = X * sl // nsl, X * (sl + 1) // nsl
+            for g in range(k["G"]):
+                seen[lo + g:hi:k["G"]] += 1
+        assert (seen == 1).all()
+    return k
+
+
+@pytest.mark.parametrize("D", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("X", [1, 5, 81, 6561, 65536])
+def test_uniform_bond_dimensions(D, X):
+    check_plan(D * D, D * D, D * D, D * D, X)
+
+
+def test_ragged_shapes_and_envelope():
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        P, R = int(rng.integers(1, 65)), int(rng.integers(1, 65))
+        X = int(rng.integers(1, 5000))
+        check_plan(P, P, R, R, X)
+    assert describe(65, 65, 8, 8, 100) is None        # more than 8 row tiles: the unfused path takes over
+    assert describe(8, 8, 72, 72, 100) is None
+
+
+def test_block_shares_follow_the_tile_counts():
+    k = check_plan(49, 49, 49, 49, 65536)             # D = 7: 13 tiles as 5 + 4 + 4
+    tiles = np.diff(k["sb_tile0"][:k["NSB"] + 1])
+    ctas = np.diff(k["sb_cta0"][:k["NSB"] + 1])
+    assert list(tiles) == [5, 4, 4]
+    assert abs(ctas[0] / ctas[1] - 5 / 4) < 0.05 and ctas.sum() >= 145
+    # neighbours in blockIdx stream neighbouring stretches of X
+    pos = [(k["cta_sl"][c] + 0.5) / ctas[k["cta_sb"][c]] for c in range(k["ctas"])]
+    assert all(b >= a for a, b in zip(pos, pos[1:]))
