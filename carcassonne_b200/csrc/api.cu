@@ -241,6 +241,30 @@ int carc_operator_path(const carc_operator* op) {
   return carc::stage3_path((int)op->terms.size(), op->P, op->Q, op->R, op->S, op->d, Xmax, op->force_path);
 }
 int carc_stage3f_profile_read(unsigned long long* host) { return carc::stage3f_profile_read(host); }
+int carc_stage3_describe_stars(int nterms, const int32_t* a_id, const int32_t* b_id, const int64_t* X, int32_t* n_groups,
+                               int32_t* group_kind, int32_t* group_first, int32_t* group_count, int32_t* sorted_term) {
+  CARC_REQUIRE(nterms >= 0 && a_id && b_id && X && n_groups && group_kind && group_first && group_count && sorted_term,
+               CARC_ERR_VALUE, "stage3_describe_stars: invalid argument");
+  // stand-in tensors: the planner only compares pointers, so distinct ids become distinct (never dereferenced) addresses
+  std::vector<carc::Stage3Term> terms((size_t)nterms);
+  for (int t = 0; t < nterms; ++t) {
+    terms[t].A = reinterpret_cast<const cplx*>((uintptr_t)(a_id[t] + 1) * 4096);
+    terms[t].B = reinterpret_cast<const cplx*>((uintptr_t)(b_id[t] + 1) * 4096 + 2048);
+    terms[t].X = X[t];
+    terms[t].has_op = 0;
+    terms[t].op[0] = make_double2((double)t, 0.0);      // carries the original index through the sort
+  }
+  carc::Stage3Plan plan;
+  carc::stage3_plan_host(terms.data(), nterms, &plan);
+  *n_groups = (int32_t)plan.groups.size();
+  for (size_t g = 0; g < plan.groups.size(); ++g) {
+    group_kind[g] = plan.groups[g].kind;
+    group_first[g] = plan.groups[g].first;
+    group_count[g] = plan.groups[g].count;
+  }
+  for (int t = 0; t < nterms; ++t) sorted_term[t] = (int32_t)plan.terms[t].op[0].x;
+  return CARC_OK;
+}
 int carc_stage3f_describe(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, int32_t* out, int out_len) {
   CARC_REQUIRE(out != nullptr && out_len >= 16 + 17 + 17 + 160 + 160, CARC_ERR_VALUE, "stage3f_describe: buffer too small");
   carc::Stage3FConfig k;

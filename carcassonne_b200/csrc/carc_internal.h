@@ -78,6 +78,7 @@ struct Stage3Plan {
   Stage3Group* groups_dev;
 };
 int stage3_plan_create(const Stage3Term* terms, int nterms, Stage3Plan** out);
+void stage3_plan_host(const Stage3Term* terms, int nterms, Stage3Plan* plan);
 void stage3_plan_destroy(Stage3Plan* plan);
 double stage3_executed_flops(const Stage3Plan* plan, int P, int Q, int R, int S, int d);
 int stage3_apply(const Stage3Plan* plan, int P, int Q, int R, int S, int d, const cplx* v, cplx* out, cplx* workspace,

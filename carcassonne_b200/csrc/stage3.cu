@@ -619,8 +619,9 @@ int stage3_path(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, int
 // of them.  A B-star (kind 0) sums the first products of its terms before ONE second product; an A-star (kind 1)
 // computes ONE first product and reuses it for the second product of each of its terms.  For the transverse-Ising
 // operator (9 terms over 6 + 6 tensors) this gives 7 first + 6 second products per x instead of 9 + 9.
-int stage3_plan_create(const Stage3Term* terms, int nterms, Stage3Plan** out) {
-  Stage3Plan* plan = new Stage3Plan();
+// host half of the plan: groups and the term table sorted by group (no device call; carc_stage3_describe_stars and the
+// CPU test suite use it directly)
+void stage3_plan_host(const Stage3Term* terms, int nterms, Stage3Plan* plan) {
   std::vector<int> group_of(nterms, -1);
   int remaining = nterms;
   while (remaining > 0) {
@@ -666,6 +667,11 @@ int stage3_plan_create(const Stage3Term* terms, int nterms, Stage3Plan** out) {
   }
   plan->terms_dev = nullptr;
   plan->groups_dev = nullptr;
+}
+
+int stage3_plan_create(const Stage3Term* terms, int nterms, Stage3Plan** out) {
+  Stage3Plan* plan = new Stage3Plan();
+  stage3_plan_host(terms, nterms, plan);
   if (nterms > 0) {
     CARC_CHECK_CUDA(cudaMalloc(&plan->terms_dev, sizeof(Stage3Term) * nterms));
     CARC_CHECK_CUDA(cudaMemcpy(plan->terms_dev, plan->terms.data(), sizeof(Stage3Term) * nterms, cudaMemcpyHostToDevice));

@@ -138,6 +138,13 @@ int carc_stage3f_profile_read(unsigned long long* host);
  * nstB, QS, BSTR, b_whole, threads, ctas, slots, smem bytes, A slot bytes, B slot bytes}, then sb_tile0[17], sb_cta0[17],
  * cta_sb[160], cta_sl[160] (-1 beyond the used entries); CARC_ERR_UNSUPPORTED outside the kernel's envelope.  What the
  * CPU test suite checks the work partition with. */
+/* Host-side star decomposition of a stage-3 term list (no device call): term t joins half-0 tensor a_id[t] and half-1
+ * tensor b_id[t] over X[t] environment indices.  Outputs the groups (kind 0: terms sharing a half-1 tensor, first
+ * products summed before one second product; kind 1: terms sharing a half-0 tensor, one first product reused), each
+ * with its range [first, first + count) in the sorted term order, and sorted_term[i] = original index of sorted term i.
+ * All output arrays hold nterms entries. */
+int carc_stage3_describe_stars(int nterms, const int32_t* a_id, const int32_t* b_id, const int64_t* X, int32_t* n_groups,
+                               int32_t* group_kind, int32_t* group_first, int32_t* group_count, int32_t* sorted_term);
 int carc_stage3f_describe(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, int32_t* out, int out_len);
 int carc_operator_num_terms(const carc_operator* op);
 /* cmac count the reference's CostTracker assigns to one apply (data/cost_tracker.py:17-21) */
