@@ -79,6 +79,7 @@ SIGNATURES = {
     "carc_operator_set_path": (c_int, [c_vp, c_int]),
     "carc_operator_path": (c_int, [c_vp]),
     "carc_stage3f_profile_read": (c_int, [c_vp]),
+    "carc_stage3_path": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_i64, c_int]),
     "carc_stage3_describe_stars": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "carc_stage3f_describe": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_i64, c_vp, c_int]),
     "carc_operator_num_terms": (c_int, [c_vp]),

@@ -241,6 +241,9 @@ int carc_operator_path(const carc_operator* op) {
   return carc::stage3_path((int)op->terms.size(), op->P, op->Q, op->R, op->S, op->d, Xmax, op->force_path);
 }
 int carc_stage3f_profile_read(unsigned long long* host) { return carc::stage3f_profile_read(host); }
+int carc_stage3_path(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, int force_path) {
+  return carc::stage3_path(nterms, P, Q, R, S, d, Xmax, force_path);
+}
 int carc_stage3_describe_stars(int nterms, const int32_t* a_id, const int32_t* b_id, const int64_t* X, int32_t* n_groups,
                                int32_t* group_kind, int32_t* group_first, int32_t* group_count, int32_t* sorted_term) {
   CARC_REQUIRE(nterms >= 0 && a_id && b_id && X && n_groups && group_kind && group_first && group_count && sorted_term,

@@ -138,6 +138,9 @@ int carc_stage3f_profile_read(unsigned long long* host);
  * nstB, QS, BSTR, b_whole, threads, ctas, slots, smem bytes, A slot bytes, B slot bytes}, then sb_tile0[17], sb_cta0[17],
  * cta_sb[160], cta_sl[160] (-1 beyond the used entries); CARC_ERR_UNSUPPORTED outside the kernel's envelope.  What the
  * CPU test suite checks the work partition with. */
+/* Which device path a stage-3 operator of this shape takes (host-side decision, no device call): 1 fused kernel,
+ * 3 fused kernel with the folded tiling, 2 unfused GEMMs; force_path as in carc_operator_set_path. */
+int carc_stage3_path(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, int force_path);
 /* Host-side star decomposition of a stage-3 term list (no device call): term t joins half-0 tensor a_id[t] and half-1
  * tensor b_id[t] over X[t] environment indices.  Outputs the groups (kind 0: terms sharing a half-1 tensor, first
  * products summed before one second product; kind 1: terms sharing a half-0 tensor, one first product reused), each
