@@ -88,9 +88,9 @@ def computeNewDimension(old_dimension, by=None, to=None):
         raise ValueError("Either 'by' or 'to' must not be None.")
     if by is not None and to is not None:
         raise ValueError("Both 'by' and 'to' cannot be None.")
-    if by is not None:
-        return old_dimension + by
-    return to
+    new_dimension = old_dimension + by if by is not None else to
+    assert new_dimension >= old_dimension     # as the reference: a bond never shrinks through this door
+    return new_dimension
 
 
 def dropAt(iterable, index):
