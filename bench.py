@@ -231,7 +231,7 @@ def workload_config(args, X, nterms):
     name = "TFIM" if args.model == "tfim" else "Heisenberg"
     return {"workload": "%s expectation matvec, T=%d terms, D=%d, chi=%d (X=%d), d=2" % (name, nterms, args.D,
                                                                                           args.chi, X),
-            "D": args.D, "chi": args.chi, "terms": nterms, "model": args.model,
+            "D": args.D, "chi": args.chi, "terms": nterms, "hamiltonian": args.model,
             "l2": "inputs (stage-2 tensors of 16*X*D^4 B each) larger than L2",
             "sharding": "X slabs over ranks + one-shot all-reduce of the output vector (%s)" % (
                 "NVLink peer memory, fused into the stage-3 partial-sum kernel" if getattr(args, "reduce", "peer") == "peer"
