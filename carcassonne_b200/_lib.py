@@ -99,7 +99,7 @@ for _name, (_res, _args) in SIGNATURES.items():
 
 # error codes (include/carc_b200.h)
 OK, ERR_CUDA, ERR_DIMENSION_MISMATCH, ERR_RANK, ERR_VALUE, ERR_RELAX_FAILED, ERR_INVARIANT, ERR_NO_CONVERGENCE, \
-    ERR_UNSUPPORTED = range(9)
+    ERR_UNSUPPORTED, ERR_EXCHANGE = range(10)
 OP_N, OP_T, OP_C, OP_J = range(4)
 
 

@@ -42,9 +42,28 @@ static void keep_pool_memory() {
   done[dev] = true;
 }
 
+namespace carc {
+int sm_count() {
+  static int cached[16] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return 148;   // host-side planning without a device (CPU test suite): a B200's count
+  }
+  if (dev < 16 && cached[dev]) return cached[dev];
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return 148;
+  }
+  if (dev < 16) cached[dev] = n;
+  return n;
+}
+}  // namespace carc
+
 extern "C" {
 
-int carc_version(void) { return 100; }
+int carc_version(void) { return 200; }
 const char* carc_last_error(void) { return carc::get_error(); }
 
 int carc_dmma_peak(int iters, double* tflops_out, void* stream) { return carc::dmma_peak(iters, tflops_out, S(stream)); }
@@ -567,6 +586,19 @@ int carc_relax(carc_operator* H, carc_operator* N_op, const void* N_lu, const vo
     cudaFreeAsync(hv, st);
     cudaFreeAsync(gwork, st);
     cudaFreeAsync(gstate, st);
+  }
+  // sticky error words of the bounded device-side waits (the stream is idle here: relax() ends with a read-back)
+  if (rc == CARC_OK || rc == CARC_ERR_EXCHANGE) {
+    int timed_out = 0;
+    for (carc_operator* o : {H, N_op})
+      if (o && o->kind == 0 && o->comm && carc::comm_status(o->comm, &timed_out) == CARC_OK && timed_out) {
+        carc::set_error("relax: the peer all-reduce of a sharded operator timed out (a rank fell out of step)");
+        return CARC_ERR_EXCHANGE;
+      }
+    if (use_lu && N_inv_blocks && carc::lu_solve_status((const cplx*)N_inv_blocks, (int)n, &timed_out) == CARC_OK && timed_out) {
+      carc::set_error("relax: the wavefront triangular solve timed out");
+      return CARC_ERR_EXCHANGE;
+    }
   }
   if (info_out && (rc == CARC_OK || rc == CARC_ERR_RELAX_FAILED)) {
     info_out[0] = info.initial_value[0]; info_out[1] = info.initial_value[1];

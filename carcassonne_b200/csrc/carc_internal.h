@@ -12,6 +12,8 @@ namespace carc {
 typedef double2 cplx;
 
 const char* get_error();
+// Number of SMs of the current device (cached per device): grids of co-resident CTAs are sized from it.
+int sm_count();
 
 // tensor_ops.cu
 int permute(const cplx* src, cplx* dst, int ndim, const int64_t* shape, const int32_t* perm, int conj, int accumulate,
@@ -122,6 +124,8 @@ int hermitian_defect(const cplx* A, int n, double* sums_dev, cudaStream_t stream
 int lu_solve(const cplx* LU, int n, const int* piv, cplx* x, cudaStream_t stream);
 int lu_invert_diagonal_blocks(const cplx* LU, int n, cplx* inv, cudaStream_t stream);
 int64_t lu_inverse_blocks_elems(int n);
+// *timed_out = 1 when a wavefront solve on these inverse blocks gave up waiting (sticky); synchronises the device word
+int lu_solve_status(const cplx* inv, int n, int* timed_out);
 int lu_solve_fast(const cplx* LU, int n, const int* piv, const cplx* inv, cplx* x, cplx* tmp, cudaStream_t stream);
 int gmres(const LinOp& A, const cplx* b, cplx* x, int64_t n, double rtol, int restart, int maxiter, cplx* work,
           void* state_dev, int* iters_out, double* resid_out, cudaStream_t stream);

@@ -100,7 +100,13 @@ __global__ void __launch_bounds__(256) xgpu_allreduce_kernel(const cplx* __restr
     failed = bad;
   }
   __syncthreads();
-  if (failed) return;
+  if (failed) {
+    // never hand back uninitialised memory: a NaN result trips every downstream guard (hasNaN, the solver's
+    // non-finite Ritz check) and the host reads the sticky flag at its next synchronisation point
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = make_double2(nan, nan);
+    return;
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     double re = 0.0, im = 0.0;
     for (int r = 0; r < c.world; ++r) {
@@ -170,7 +176,7 @@ int comm_allreduce(Comm* c, const cplx* src, int slots, int64_t n, cplx* out, cu
   }
   ++c->epoch;
   int64_t blocks = (n + 255) / 256;
-  if (blocks > 148) blocks = 148;   // all CTAs must be co-resident: they wait on each other through the ticket
+  if (blocks > sm_count()) blocks = sm_count();   // all CTAs must be co-resident: they wait on each other through the ticket
   xgpu_allreduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, slots, n, out, d, c->epoch);
   CARC_CHECK_CUDA(cudaGetLastError());
   return CARC_OK;

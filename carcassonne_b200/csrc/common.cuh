@@ -136,3 +136,4 @@ __device__ __forceinline__ double warp_sum(double v) {
 #define CARC_ERR_INVARIANT 6
 #define CARC_ERR_NO_CONVERGENCE 7
 #define CARC_ERR_UNSUPPORTED 8
+#define CARC_ERR_EXCHANGE 9

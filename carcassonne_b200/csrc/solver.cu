@@ -12,6 +12,7 @@
 #include <cooperative_groups.h>
 #include <math.h>
 
+#include <atomic>
 #include <vector>
 
 #include "carc_internal.h"
@@ -468,7 +469,11 @@ __global__ void __launch_bounds__(256) tri_wavefront_kernel(const cplx* __restri
     __syncthreads();
   }
   if (failed) {
+    // sticky error word for the host (read by carc_relax / carc_lu_solve_blocks at their synchronisation points) and a
+    // NaN block so that nothing downstream mistakes the unsolved right-hand side for a solution
     if (tid == 0) flags[2 * nblk] = 1ull;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    if (tid < nb) x[j0 + tid] = make_double2(nan, nan);
     return;
   }
   {
@@ -1228,8 +1233,8 @@ int64_t lu_inverse_blocks_elems(int n) {
 int lu_solve_fast(const cplx* LU, int n, const int* piv, const cplx* inv, cplx* x, cplx* tmp, cudaStream_t stream) {
   const int nblk = (n + SB - 1) / SB;
   lu_permute_kernel<<<1, 32, 0, stream>>>(x, piv, n);
-  if (nblk <= 148) {
-    static unsigned long long epoch_counter = 0;
+  if (nblk <= sm_count()) {
+    static std::atomic<unsigned long long> epoch_counter{0};
     unsigned long long* flags = reinterpret_cast<unsigned long long*>(const_cast<cplx*>(inv) + 2ll * nblk * SB * SB);
     const unsigned long long epoch = ++epoch_counter;
     const size_t smem = sizeof(cplx) * 2 * SB * (SB + 1);
@@ -1356,6 +1361,15 @@ int cg(const LinOp& A, const cplx* b, cplx* x, int64_t n, double rtol, int maxit
   return CARC_OK;
 }
 
+int lu_solve_status(const cplx* inv, int n, int* timed_out) {
+  const int nblk = (n + SB - 1) / SB;
+  const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(inv + 2ll * nblk * SB * SB);
+  unsigned long long v = 0;
+  CARC_CHECK_CUDA(cudaMemcpy(&v, flags + 2 * nblk, sizeof(v), cudaMemcpyDeviceToHost));
+  *timed_out = v != 0;
+  return CARC_OK;
+}
+
 size_t cg_state_bytes() { return sizeof(CgState); }
 
 
@@ -1400,6 +1414,11 @@ int relax(const LinOp& M, cplx* v, int64_t n, int max_mults, double tol, int k, 
     ritz_kernel<<<1, VT, 0, stream>>>(V, MV, n, k, v, st);
     CARC_CHECK_CUDA(cudaMemcpyAsync(&host, st, sizeof(RelaxState), cudaMemcpyDeviceToHost, stream));
     CARC_CHECK_CUDA(cudaStreamSynchronize(stream));
+    // a timed-out peer exchange or wavefront solve hands back NaNs (comm.cu, tri_wavefront_kernel): stop here instead of
+    // iterating on garbage up to the multiplication cap
+    CARC_REQUIRE(isfinite(host.ritz.x) && isfinite(host.ritz.y), CARC_ERR_EXCHANGE,
+                 "relax: non-finite Ritz value after %d multiplications (NaN input, or a bounded device-side wait timed out)",
+                 mults);
     if (host.complete) complete = true;
     const double dre = host.ritz.x - last_re, dim = host.ritz.y - last_im;
     const bool small_change = have_last && sqrt(dre * dre + dim * dim) <= tol;

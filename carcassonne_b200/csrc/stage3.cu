@@ -498,7 +498,7 @@ bool s3_configure(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, S
           k.ring_off = ring_off;
           k.total = (uint32_t)total;
           k.threads = G * k.NPT * 32;
-          int64_t nsl = std::max<int64_t>(1, 148 / k.NSB);
+          int64_t nsl = std::max<int64_t>(1, sm_count() / k.NSB);
           nsl = std::min<int64_t>(nsl, std::max<int64_t>(1, Xmax / G));
           k.NSL = (int)nsl;
           k.slots = k.NSB * k.NSL * G;

@@ -552,7 +552,7 @@ bool stage3f_configure(int nterms, int P, int Q, int R, int S, int d, int64_t Xm
         k.threads = G * k.NPT * 32;
         // share the CTAs (one per SM) between the S blocks in proportion to their tile counts
         const int64_t max_slabs = std::max<int64_t>(1, Xmax / G);
-        int budget = 148, used = 0;
+        int budget = std::min(sm_count(), 160), used = 0;   // one CTA per SM (the CTA tables hold 160)
         if (k.NSB > budget) budget = k.NSB;
         k.sb_cta0[0] = 0;
         for (int i = 0; i < k.NSB; ++i) {

@@ -4,6 +4,9 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "carc_internal.h"
@@ -471,24 +474,31 @@ __global__ void __launch_bounds__(256) reduce_kernel(int64_t n, const cplx* __re
   }
 }
 
-static ReduceWorkspace g_ws[16] = {};
+// One workspace per (device, stream): reductions on the same stream are ordered, so they can share partials and the
+// ticket; reductions on different streams (or issued by different host threads) must not interleave tickets.
+static std::mutex g_ws_mutex;
+static std::map<std::pair<int, cudaStream_t>, ReduceWorkspace> g_ws;
 
-static int get_ws(ReduceWorkspace* ws) {
+static int get_ws(ReduceWorkspace* ws, cudaStream_t stream) {
   int dev = 0;
   CARC_CHECK_CUDA(cudaGetDevice(&dev));
-  CARC_REQUIRE(dev < 16, CARC_ERR_VALUE, "device index %d not supported", dev);
-  if (!g_ws[dev].partials) {
-    CARC_CHECK_CUDA(cudaMalloc(&g_ws[dev].partials, sizeof(double2) * RED_MAX_BLOCKS));
-    CARC_CHECK_CUDA(cudaMalloc(&g_ws[dev].ticket, sizeof(unsigned int)));
-    CARC_CHECK_CUDA(cudaMemset(g_ws[dev].ticket, 0, sizeof(unsigned int)));
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  auto key = std::make_pair(dev, stream);
+  auto it = g_ws.find(key);
+  if (it == g_ws.end()) {
+    ReduceWorkspace w;
+    CARC_CHECK_CUDA(cudaMalloc(&w.partials, sizeof(double2) * RED_MAX_BLOCKS));
+    CARC_CHECK_CUDA(cudaMalloc(&w.ticket, sizeof(unsigned int)));
+    CARC_CHECK_CUDA(cudaMemset(w.ticket, 0, sizeof(unsigned int)));
+    it = g_ws.emplace(key, w).first;
   }
-  *ws = g_ws[dev];
+  *ws = it->second;
   return CARC_OK;
 }
 
 int reduce(int mode, int64_t n, const cplx* x, const cplx* y, double2* out_dev, cudaStream_t stream) {
   ReduceWorkspace ws;
-  int rc = get_ws(&ws);
+  int rc = get_ws(&ws, stream);
   if (rc) return rc;
   unsigned g = grid_for(n);
   if (mode == 0)

@@ -198,9 +198,20 @@ class DeviceData:
         return "DeviceData(shape={})".format(self.shape)
 
     # -- elementwise ------------------------------------------------------------------------------------
+    def _touch(self):
+        """Called by everything that writes this buffer through a raw pointer: drops the derived record and bumps
+        torch's version counter, which every view of the same storage shares -- the environment cache keys on it
+        (tensors/_2d/sparse.py), so an in-place update can never be answered with stale multipliers."""
+        self._factors = None
+        torch.autograd.graph.increment_version(self._t)
+
+    @property
+    def version(self):
+        return self._t._version
+
     def _axpby(self, alpha, x, beta, conj_x=0):
         """self = alpha * x + beta * self (in place)."""
-        self._factors = None
+        self._touch()
         check(lib.carc_axpby(self.size(), _lib.cplx2(alpha), _ptr(x._t), _lib.cplx2(beta), _ptr(self._t), conj_x,
                              _stream()))
         return self
@@ -247,7 +258,7 @@ class DeviceData:
 
     def __imul__(self, other):
         self._check_same_shape(other)
-        self._factors = None
+        self._touch()
         check(lib.carc_mul(self.size(), _ptr(other._t), _ptr(self._t), _stream()))
         return self
 

@@ -94,6 +94,105 @@ class PeerComm:
             pass
 
 
+class ExchangeTimeout(RuntimeError):
+    """A bounded device-side wait of the peer all-reduce gave up: a rank fell out of step (CARC_ERR_EXCHANGE)."""
+
+
+class EnvironmentSharding:
+    """System-level multi-GPU mode: while active, every ``System`` of this process builds only
+    its rank's X slab of the stage-2 halves (``formExpectationStage2``), its expectation / normalization operators
+    finish each matvec with the all-reduce of the output vector, and the dense matrices of the
+    ``isCheaperToFormMatrix`` branches are summed over ranks -- so ``System.minimizeExpectation`` and everything built
+    on the multipliers run on all GPUs, while absorption / compression (small next to the environment) are
+    replicated.  Every rank must execute the same sequence of calls on the same (seeded) system."""
+
+    def __init__(self):
+        self.rank, self.world = rank(), world()
+        self._comm = None
+        self._comm_elems = 0
+        self._retired = []      # outgrown communicators stay mapped while operators built on them may still exist
+
+    @property
+    def slab(self):
+        return (self.rank, self.world)
+
+    def comm_for(self, n):
+        """The peer communicator, grown (collectively: every rank asks for the same sizes in the same order) to hold
+        vectors of ``n`` elements."""
+        if self.world == 1:
+            return None
+        if self._comm is None or n > self._comm_elems:
+            if self._comm is not None:
+                self._retired.append(self._comm)
+            self._comm_elems = max(int(n), 1 << 14)
+            self._comm = PeerComm(self._comm_elems)
+        return self._comm
+
+    def attach(self, operator):
+        """Make ``operator`` (a finalized ``Stage3Operator`` over this rank's slabs) return the sum over ranks."""
+        if self.world == 1:
+            return operator
+        # the exchange is part of carc_operator_apply itself (the device solver calls it without coming back to Python),
+        # so it is always the NVLink peer-memory all-reduce fused into the partial-sum pass; NCCL is only used for the
+        # one-off sums of dense matrices
+        shard_operator(operator, self.comm_for(operator.P * operator.R * operator.d))
+        return operator
+
+    def sum_matrix_(self, matrix):
+        """In-place sum over ranks of a dense matrix formed from this rank's slabs (``Multiplier.formMatrix``)."""
+        if self.world > 1:
+            dist.all_reduce(matrix._t)
+            matrix._touch()
+        return matrix
+
+    def raise_if_timed_out(self):
+        if self._comm is not None and self._comm.timed_out():
+            raise ExchangeTimeout("peer all-reduce timed out on rank {}".format(self.rank))
+
+    def close(self):
+        for comm in self._retired + ([self._comm] if self._comm is not None else []):
+            comm.close()
+        self._retired, self._comm = [], None
+
+
+_environment_sharding = None
+
+
+def shard_environment():
+    """Turn the system-level multi-GPU mode on (collective; needs an initialised process group)."""
+    global _environment_sharding
+    unshard_environment()
+    from .tensors._2d.sparse import environment_cache
+    environment_cache.clear()
+    _environment_sharding = EnvironmentSharding() if world() > 1 else None
+    return _environment_sharding
+
+
+def unshard_environment():
+    global _environment_sharding
+    if _environment_sharding is not None:
+        _environment_sharding.close()
+        _environment_sharding = None
+        from .tensors._2d.sparse import environment_cache
+        environment_cache.clear()
+
+
+def environment_sharding():
+    return _environment_sharding
+
+
+def balance_terms(costs, world):
+    """Term sharding (BASELINE config 4): whole (A_t, B_t) pairs per rank.  Longest-processing-time greedy: terms in
+    decreasing cost go to the least loaded rank -> list of term indices per rank.  Pure host logic."""
+    order = sorted(range(len(costs)), key=lambda t: (-costs[t], t))
+    load, owner = [0] * world, [[] for _ in range(world)]
+    for t in order:
+        r = min(range(world), key=lambda q: (load[q], q))
+        owner[r].append(t)
+        load[r] += costs[t]
+    return [sorted(o) for o in owner]
+
+
 def shard_operator(operator, comm):
     """Attach the communicator to a ``Stage3Operator`` whose terms hold this rank's X slabs: every apply then
     returns the full vector on every rank."""

@@ -5,6 +5,7 @@ numerical work each policy triggers runs on the device through the bound ``Syste
 template: ``createBindingToSystem(system)`` returns a bound copy-on-read view whose ``apply`` / ``update`` /
 ``reset`` / ``converged`` see ``self.system`` (reference policies.py:12-44).
 """
+import inspect
 import logging
 
 import numpy as np
@@ -23,9 +24,13 @@ class _Binding:
         object.__setattr__(self, "system", system)
 
     def __getattr__(self, name):
-        value = getattr(object.__getattribute__(self, "forward"), name)
-        if callable(value) and hasattr(value, "__func__"):
-            return value.__func__.__get__(self, type(self))   # rebind methods so that they see self.system
+        forward = object.__getattribute__(self, "forward")
+        value = getattr(forward, name)
+        # rebind the template's OWN methods so that they see self.system; any other attribute -- including a bound
+        # method of some other object stored on the policy, e.g. HookPolicy(recorder.hook) -- is forwarded untouched,
+        # as the reference's Proxy does (policies.py:12-44)
+        if inspect.ismethod(value) and value.__self__ is forward:
+            return value.__func__.__get__(self, type(self))
         return value
 
 

@@ -13,6 +13,7 @@ import numpy as np
 
 from ..compression import computeProductCompressor, factored_side_gram
 from ..data import DeviceData, _init_constants
+from ..distributed import environment_sharding
 from ..sparse import (Identity, OneSiteOperator, TwoSiteOperator, TwoSiteOperatorCompressed, makeSimpleSparseOperator,
                       makeSparseOperator, mapOverSparseData, stripAllButIdentityFrom)
 from ..tensors._2d.dense import formNormalizationMultiplier, formNormalizationSubmatrix
@@ -197,7 +198,11 @@ class System(BaseSystem):
 
     def computeScalarUsingMultiplier(self, multiply):
         """<center| multiply |center> with the stored conjugate (no extra conjugation)."""
-        return self.state_center_data_conj.contractWithAlongAll(multiply(self.state_center_data))
+        value = self.state_center_data_conj.contractWithAlongAll(multiply(self.state_center_data))
+        sharding = environment_sharding()
+        if sharding is not None:      # the scalar read-back above synchronised: look at the exchange's error word
+            sharding.raise_if_timed_out()
+        return value
 
     def computeExpectationAndNormalization(self, operator_center_tensor=None):
         expectation, normalization = self.formExpectationAndNormalizationMultipliers(operator_center_tensor)

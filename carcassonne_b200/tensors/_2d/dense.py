@@ -37,7 +37,7 @@ def _target(shape, accumulate_into):
         return _empty(shape), 0.0
     if accumulate_into.shape != tuple(shape):
         raise ValueError("cannot accumulate a result of shape {} into {}".format(tuple(shape), accumulate_into.shape))
-    accumulate_into._factors = None
+    accumulate_into._touch()
     return accumulate_into._t, 1.0
 
 
@@ -171,33 +171,55 @@ def formNormalizationStage1(corner, side, accumulate_into=None):
     return accumulate_into if accumulate_into is not None else DeviceData(out)
 
 
-def formNormalizationStage2(stage1_a, stage1_b, accumulate_into=None, half=None):
+def stage2SlabPlan(a, b, half, slab=None):
+    """Launch plan of stage 2 as ONE batched GEMM  C_b[(A1 A2 A3), (B2 B3)] = A[K, (A1 A2 A3)]^T . B_b[K, (B2 B3)]
+    (b = B0) with a scatter epilogue.  ``a`` / ``b``: shapes of the two stage-1 tensors; ``half`` = None (reference
+    layout), 0 or 1 (stage-3 streaming layouts); ``slab`` = (rank, world) restricts the result to that rank's slab of
+    the joined environment bond X -- contiguous in the SLOW factor of X, which is B0 for half 0 (a range of the GEMM
+    batch) and A1 for half 1 (a range of the GEMM rows), the same index range on both halves because half 0's B0 and
+    half 1's A1 are the two ends of the same ring bond ("each GPU builds its X-slab: slice x of
+    the stage-1 tensors").  Pure host logic (no device call): the CPU suite checks it against NumPy slicing."""
+    K = a[0]
+    Nn = b[2] * b[3]
+    plan = {"K": K, "N": Nn, "lda": a[1] * a[2] * a[3], "ldb": Nn, "strideB": K * Nn, "a_offset": 0, "b_offset": 0}
+    if half is None:
+        if slab is not None:
+            raise ValueError("X slabs exist only in the stage-3 layouts (half = 0 or 1)")
+        st = _row_major_strides((a[1], a[2], b[2], a[3], b[3]))
+        plan.update(out_shape=(b[0], a[1], a[2], b[2], a[3], b[3]), M=a[1] * a[2] * a[3], batch=b[0],
+                    rows=((a[1], st[0]), (a[2], st[1]), (a[3], st[3])), cols=((b[2], st[2]), (b[3], st[4])),
+                    strideC=a[1] * a[2] * b[2] * a[3] * b[3], full_X=b[0] * a[1], x_range=(0, b[0] * a[1]))
+        return plan
+    rest = a[3] * b[3] * a[2] * b[2]
+    st = _row_major_strides((a[3], b[3], a[2], b[2]))
+    slow = b[0] if half == 0 else a[1]
+    lo, hi = (0, slow) if slab is None else (slow * slab[0] // slab[1], slow * (slab[0] + 1) // slab[1])
+    n_b0, n_a1 = (hi - lo, a[1]) if half == 0 else (b[0], hi - lo)
+    a1_stride, stride_c = (rest, n_a1 * rest) if half == 0 else (n_b0 * rest, rest)
+    inner = a[1] if half == 0 else b[0]
+    plan.update(out_shape=(n_b0 * n_a1, a[3], b[3], a[2], b[2]), M=n_a1 * a[2] * a[3], batch=n_b0,
+                rows=((n_a1, a1_stride), (a[2], st[2]), (a[3], st[0])), cols=((b[2], st[3]), (b[3], st[1])),
+                strideC=stride_c, full_X=b[0] * a[1], x_range=(lo * inner, hi * inner))
+    if half == 0:
+        plan["b_offset"] = lo * K * Nn          # batches lo .. hi of B
+    else:
+        plan["a_offset"] = lo * a[2] * a[3]     # rows (A1 = lo .. hi) of the K x (A1 A2 A3) operand, lda unchanged
+    return plan
+
+
+def formNormalizationStage2(stage1_a, stage1_b, accumulate_into=None, half=None, slab=None):
     """reference dense.py:102-112: sum A(0) = B(1)  ->  [B0][A1][A2][B2][A3][B3].
 
     ``half`` = 0 / 1 writes instead the layout stage 3 consumes, [(B0 A1), A3, B3, A2, B2] /
     [(A1 B0), A3, B3, A2, B2] (the pre-joins of reference dense.py:130-131), so the X D^4-element transposing copy in
-    front of every matvec disappears."""
+    front of every matvec disappears.  ``slab`` = (rank, world): only this rank's slab of X is built (multi-GPU)."""
     _check_ranks((stage1_a, 4), (stage1_b, 4))
     _check_bond(0, 0, stage1_a, 1, 1, stage1_b)
-    a, b = stage1_a.shape, stage1_b.shape
-    K = a[0]
-    M, Nn = a[1] * a[2] * a[3], b[2] * b[3]
-    if half is None:
-        out_shape = (b[0], a[1], a[2], b[2], a[3], b[3])
-        st = _row_major_strides((a[1], a[2], b[2], a[3], b[3]))
-        rows = ((a[1], st[0]), (a[2], st[1]), (a[3], st[3]))
-        cols = ((b[2], st[2]), (b[3], st[4]))
-        stride_c = prod(out_shape[1:])
-    else:
-        rest = a[3] * b[3] * a[2] * b[2]
-        st = _row_major_strides((a[3], b[3], a[2], b[2]))
-        out_shape = (b[0] * a[1], a[3], b[3], a[2], b[2])
-        a1_stride, stride_c = (rest, a[1] * rest) if half == 0 else (b[0] * rest, rest)
-        rows = ((a[1], a1_stride), (a[2], st[2]), (a[3], st[0]))
-        cols = ((b[2], st[3]), (b[3], st[1]))
-    out, beta = _target(out_shape, accumulate_into)
-    gemm_scatter(OP_T, OP_N, M, Nn, K, stage1_a._t, M, stage1_b._t, Nn, out, rows, cols, beta=beta,
-                 batch=b[0], strideB=K * Nn, strideC=stride_c)
+    p = stage2SlabPlan(stage1_a.shape, stage1_b.shape, half, slab)
+    out, beta = _target(p["out_shape"], accumulate_into)
+    gemm_scatter(OP_T, OP_N, p["M"], p["N"], p["K"], stage1_a._t, p["lda"], stage1_b._t, p["ldb"], out, p["rows"],
+                 p["cols"], beta=beta, batch=p["batch"], strideB=p["strideB"], strideC=p["strideC"],
+                 a_offset=p["a_offset"], b_offset=p["b_offset"])
     return accumulate_into if accumulate_into is not None else DeviceData(out)
 
 
@@ -216,9 +238,11 @@ def unjoinStage2(joined, half, x, y):
 
 
 # -- stage 3 -------------------------------------------------------------------------------------------------
-def stage3CostOfMultiply(A, B, d, with_operator):
-    """cmac count the reference's CostTracker gives the generated contractors of dense.py:115-128 / 146-160."""
+def stage3CostOfMultiply(A, B, d, with_operator, full_X=None):
+    """cmac count the reference's CostTracker gives the generated contractors of dense.py:115-128 / 146-160
+    (``full_X``: extent of the whole joined bond when A, B hold one rank's slab of it)."""
     X, c, dd, a, b = A.shape
+    X = X if full_X is None else full_X
     _, g, h, e, f = B.shape
     cost = X * c * dd * (e * f * d) * (a * b) + (g * h) * (c * dd * d) * (e * f * X)
     if with_operator:
@@ -226,8 +250,9 @@ def stage3CostOfMultiply(A, B, d, with_operator):
     return cost
 
 
-def stage3CostOfFormMatrix(A, B, d):
+def stage3CostOfFormMatrix(A, B, d, full_X=None):
     X, c, dd, a, b = A.shape
+    X = X if full_X is None else full_X
     _, g, h, e, f = B.shape
     m = (a * b * c * dd) * (e * f * g * h)
     return m * X + m * d * d
@@ -245,11 +270,13 @@ def stage3FormMatrix(A, B, operator, accumulate_into=None):
     d = op.shape[0]
     P, Q, Rr, S = c * dd, a * b, g * h, e * f
     n_out, n_in = P * Rr * d, Q * S * d
-    G = _empty((P * Q, Rr * S))
-    gemm(OP_T, OP_N, P * Q, Rr * S, X, A._t, P * Q, B._t, Rr * S, G)
     out, _ = _target((n_out, n_in), accumulate_into)
     if accumulate_into is None:
         out.zero_()
+    if X == 0:        # an empty X slab (multi-GPU with more ranks than slow bond indices)
+        return accumulate_into if accumulate_into is not None else DeviceData(out)
+    G = _empty((P * Q, Rr * S))
+    gemm(OP_T, OP_N, P * Q, Rr * S, X, A._t, P * Q, B._t, Rr * S, G)
     opd = DeviceData.fromArray(op.reshape(1, d * d))
     # matrix[(P R s'), (Q S s)] += G[(P Q), (R S)] * O[s', s]   (a K = 1 product with scattered output)
     gemm_scatter(OP_N, OP_N, P * Q * Rr * S, d * d, 1, G, 1, opd._t, d * d, out,
@@ -257,20 +284,32 @@ def stage3FormMatrix(A, B, operator, accumulate_into=None):
     return accumulate_into if accumulate_into is not None else DeviceData(out)
 
 
-def _stage3_multiplier(A, B, operator, d):
+def _stage3_multiplier(A, B, operator, d, sharding=None, full_X=None):
+    """``sharding`` (a ``distributed.EnvironmentSharding``): A, B hold this rank's slab of the ``full_X`` joined bond;
+    the operator then ends with the all-reduce over ranks and ``formMatrix`` sums the ranks' partial matrices."""
     from ...operator import Stage3Operator
     state_shape = (A.shape[3], A.shape[4], B.shape[3], B.shape[4], d)
     if A.shape[1:3] != A.shape[3:5] or B.shape[1:3] != B.shape[3:5]:
         raise ValueError("stage-2 halves must carry equal state / conjugate-state bonds")
-    op = Stage3Operator(state_shape).add_term(A, B, operator).finalize()
+    op = Stage3Operator(state_shape)
+    if A.shape[0] > 0:
+        op.add_term(A, B, operator)
+    op.finalize()
     n = prod(state_shape)
     identity = np.eye(d, dtype=np.complex128)
+
+    def form_matrix():
+        matrix = stage3FormMatrix(A, B, identity if operator is None else operator)
+        return sharding.sum_matrix_(matrix) if sharding is not None else matrix
+
+    if sharding is not None:
+        sharding.attach(op)
     multiplier = Multiplier(
         (n, n),
         op,
-        stage3CostOfMultiply(A, B, d, operator is not None),
-        lambda: stage3FormMatrix(A, B, identity if operator is None else operator),
-        stage3CostOfFormMatrix(A, B, d),
+        stage3CostOfMultiply(A, B, d, operator is not None, full_X),
+        form_matrix,
+        stage3CostOfFormMatrix(A, B, d, full_X),
     )
     multiplier.device_operator = op
     multiplier.terms = [(A, B, operator)]
@@ -288,18 +327,25 @@ def formDenseStage3(stage2_0, stage2_1, operator):
 
 
 def formNormalizationHalves(corners, sides):
+    """-> (A, B, sharding, full_X): the two stage-2 halves in the stage-3 layout -- this rank's X slab of them in the
+    multi-GPU mode (``distributed.shard_environment``)."""
+    from ... import distributed as _dist
+    sharding = _dist.environment_sharding()
+    slab = sharding.slab if sharding is not None else None
     stage1 = [formNormalizationStage1(corners[i], sides[i]) for i in range(4)]
-    return (formNormalizationStage2(stage1[0], stage1[1], half=0),
-            formNormalizationStage2(stage1[2], stage1[3], half=1))
+    full_X = stage1[1].shape[0] * stage1[0].shape[1]
+    return (formNormalizationStage2(stage1[0], stage1[1], half=0, slab=slab),
+            formNormalizationStage2(stage1[2], stage1[3], half=1, slab=slab), sharding, full_X)
 
 
 def formNormalizationMultiplier(corners, sides, center_identity):
     """reference dense.py:82-94."""
-    A, B = formNormalizationHalves(corners, sides)
-    return _stage3_multiplier(A, B, None, center_identity.shape[0])
+    A, B, sharding, full_X = formNormalizationHalves(corners, sides)
+    return _stage3_multiplier(A, B, None, center_identity.shape[0], sharding, full_X)
 
 
 def formNormalizationSubmatrix(corners, sides):
     """reference dense.py:205-225: sum s2_0(0,1) = s2_1(1,0)  ->  [(D0* D1* D2* D3*)][(D0 D1 D2 D3)]."""
-    A, B = formNormalizationHalves(corners, sides)
-    return stage3FormMatrix(A, B, np.ones((1, 1), dtype=np.complex128))
+    A, B, sharding, _ = formNormalizationHalves(corners, sides)
+    matrix = stage3FormMatrix(A, B, np.ones((1, 1), dtype=np.complex128))
+    return sharding.sum_matrix_(matrix) if sharding is not None else matrix

@@ -36,7 +36,7 @@ class _Memo:
 
     @staticmethod
     def _key(sparse_tensors, extra):
-        return tuple(tuple((tag, id(data)) for tag, data in t.items()) for t in sparse_tensors) + (extra,)
+        return tuple(tuple((tag, id(data), data.version) for tag, data in t.items()) for t in sparse_tensors) + (extra,)
 
     def get(self, sparse_tensors, extra, compute):
         key = self._key(sparse_tensors, extra)
@@ -67,10 +67,12 @@ class Stage2Half(dict):
     """{tag: tensor} of one half-ring in the stage-3 streaming layout [(x y), D*, D*, D, D] (``half`` = 0 or 1);
     ``bonds`` keeps the two environment bond extents of the reference layout."""
 
-    def __init__(self, half, bonds=None):
+    def __init__(self, half, bonds=None, slab=None):
         dict.__init__(self)
         self.half = half
         self.bonds = bonds
+        self.slab = slab          # (rank, world) when only this rank's slab of X is held (multi-GPU), else None
+        self.full_X = {}          # tag -> extent of the whole joined bond X (== shape[0] when not sharded)
 
 
 def absorbSparseSideIntoCornerFromLeft(corner, side):
@@ -111,17 +113,29 @@ def formExpectationStage1(corner, side):
 
 
 def formExpectationStage2(right, left, half=None):
-    """reference tensors/_2d/sparse.py:86-99.  ``half`` = 0 / 1 produces a ``Stage2Half`` in the stage-3 layout."""
+    """reference tensors/_2d/sparse.py:86-99.  ``half`` = 0 / 1 produces a ``Stage2Half`` in the stage-3 layout; in
+    the multi-GPU mode (``distributed.shard_environment``) it holds this rank's slab of X only."""
+    from ... import distributed as _dist
+    sharding = _dist.environment_sharding() if half is not None else None
+    slab = sharding.slab if sharding is not None else None
+
     def compute():
-        result = contractSparseTensors(
-            rule_stage2, lambda r, l, acc, _: _dense.formNormalizationStage2(r, l, acc, half=half), right, left)
+        full_X = {}
+
+        def dense(r, l, acc, _):
+            result = _dense.formNormalizationStage2(r, l, acc, half=half, slab=slab)
+            full_X[id(result)] = l.shape[0] * r.shape[1]      # extent of the whole joined bond (B0 A1)
+            return result
+
+        result = contractSparseTensors(rule_stage2, dense, right, left)
         if half is None:
             return result
-        out = Stage2Half(half, (left[Identity()].shape[0], right[Identity()].shape[1]))
+        out = Stage2Half(half, (left[Identity()].shape[0], right[Identity()].shape[1]), slab)
         out.update(result)
+        out.full_X = {tag: full_X[id(data)] for tag, data in result.items()}
         return out
 
-    return environment_cache.get((right, left), ("stage2", half), compute)
+    return environment_cache.get((right, left), ("stage2", half, slab), compute)
 
 
 def _as_half(stage2, half):
@@ -132,6 +146,7 @@ def _as_half(stage2, half):
     out = Stage2Half(half, tuple(stage2[Identity()].shape[:2]))
     for tag, data in stage2.items():
         out[tag] = _dense.prejoinStage2(data, half)
+        out.full_X[tag] = out[tag].shape[0]
     return out
 
 
@@ -143,7 +158,13 @@ def stage3Terms(stage2_0, stage2_1, operator_center):
 def formExpectationStage3(stage2_0, stage2_1, operator_center):
     """reference tensors/_2d/sparse.py:100-161 -> (expectation Multiplier, normalization Multiplier)."""
     from ...operator import Stage3Operator
+    from ... import distributed as _dist
     half_0, half_1 = _as_half(stage2_0, 0), _as_half(stage2_1, 1)
+    if half_0.slab != half_1.slab:
+        raise ValueError("stage-2 halves were built for different X slabs: {} vs {}".format(half_0.slab, half_1.slab))
+    sharding = _dist.environment_sharding() if half_0.slab is not None else None
+    if half_0.slab is not None and (sharding is None or sharding.slab != half_0.slab):
+        raise ValueError("stage-2 halves hold an X slab but the multi-GPU mode that built them is no longer active")
     physical_dimension, _, DataClass = getInformationFromOperatorCenter(operator_center)
     A_id, B_id = half_0[Identity()], half_1[Identity()]
     state_shape = (A_id.shape[3], A_id.shape[4], B_id.shape[3], B_id.shape[4], physical_dimension)
@@ -154,10 +175,15 @@ def formExpectationStage3(stage2_0, stage2_1, operator_center):
     cost_of_multiply = cost_of_formMatrix = 0
     for x, y, z in terms:
         site = None if z == Identity() else operator_center[z]
-        expectation_operator.add_term(half_0[x], half_1[y], site)
-        cost_of_multiply += _dense.stage3CostOfMultiply(half_0[x], half_1[y], physical_dimension, site is not None)
-        cost_of_formMatrix += _dense.stage3CostOfFormMatrix(half_0[x], half_1[y], physical_dimension)
+        if half_0[x].shape[0] > 0:          # an empty slab (more ranks than slow bond indices) contributes nothing
+            expectation_operator.add_term(half_0[x], half_1[y], site)
+        # costs are those of the WHOLE operator, so that every rank (and a single GPU) takes the same solver branches
+        cost_of_multiply += _dense.stage3CostOfMultiply(half_0[x], half_1[y], physical_dimension, site is not None,
+                                                        half_0.full_X[x])
+        cost_of_formMatrix += _dense.stage3CostOfFormMatrix(half_0[x], half_1[y], physical_dimension, half_0.full_X[x])
     expectation_operator.finalize()
+    if sharding is not None:
+        sharding.attach(expectation_operator)
 
     identity = np.eye(physical_dimension, dtype=np.complex128)
 
@@ -165,13 +191,14 @@ def formExpectationStage3(stage2_0, stage2_1, operator_center):
         matrix = DataClass.newZeros((dimension, dimension))
         for x, y, z in terms:
             _dense.stage3FormMatrix(half_0[x], half_1[y], identity if z == Identity() else operator_center[z], matrix)
-        return matrix
+        return sharding.sum_matrix_(matrix) if sharding is not None else matrix
 
     expectation_multiplier = Multiplier((dimension, dimension), expectation_operator, cost_of_multiply,
                                         formExpectationMatrix, cost_of_formMatrix)
     expectation_multiplier.device_operator = expectation_operator
     expectation_multiplier.terms = terms
-    normalization_multiplier = _dense._stage3_multiplier(A_id, B_id, None, physical_dimension)
+    normalization_multiplier = _dense._stage3_multiplier(A_id, B_id, None, physical_dimension, sharding,
+                                                         half_0.full_X[Identity()])
     return expectation_multiplier, normalization_multiplier
 
 

@@ -35,6 +35,7 @@ extern "C" {
 #define CARC_ERR_INVARIANT 6          /* InvariantViolatedError (utils.py:25)                         */
 #define CARC_ERR_NO_CONVERGENCE 7     /* the reference's `assert info == 0` after GMRES (utils.py:824) */
 #define CARC_ERR_UNSUPPORTED 8
+#define CARC_ERR_EXCHANGE 9        /* a bounded device-side wait (peer all-reduce, wavefront solve) timed out */
 
 /* operand flags of carc_zgemm */
 #define CARC_OP_N 0 /* as stored                     */

@@ -69,12 +69,106 @@ def main():
         if not all(torch.equal(gathered[0], g) for g in gathered):
             failures.append((D, X, "relax state differs across ranks"))
         comm.close()
+    failures += system_level_checks(rank, world)
     ok = torch.tensor([0 if failures else 1], device="cuda")
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("MULTI_GPU_CHECK", "PASS" if ok.item() == 1 else "FAIL", failures, flush=True)
     dist.destroy_process_group()
     sys.exit(0 if ok.item() == 1 else 1)
+
+
+def _identical_on_all_ranks(t, world):
+    gathered = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(gathered, t.contiguous())
+    return all(torch.equal(gathered[0], g) for g in gathered)
+
+
+def system_level_checks(rank, world):
+    """System-level multi-GPU mode: every rank holds the same seeded ``System``; with
+    ``shard_environment()`` each builds only its X slab of the stage-2 halves and ``minimizeExpectation`` /
+    ``computeExpectation`` run on all GPUs.  Checked: matvec, <H>, <N>, dense matrices and the minimised energy against
+    the unsharded system on the same GPU (summation order differs, so not bit-for-bit: <= 1e-12 / 1e-10), and bit-identical
+    states on all ranks (the replicated Arnoldi iteration relies on it)."""
+    from copy import copy
+    from carcassonne_b200 import distributed as cd
+    from carcassonne_b200 import synthetic, utils
+    failures = []
+
+    def rel(a, b):
+        return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+    # (chi, D, absorptions before the check, force GMRES for N^-1)
+    cases = [(2, 2, (0, 1, 2, 3), False), (3, 3, (0, 1), False), (1, 2, (0, 1, 2, 3), False), (4, 4, (0, 2), False),
+             (2, 3, (0, 1, 2, 3), True), (5, 2, (1,), False)]
+    for chi, D, walk, force_gmres in cases:
+        base = synthetic.device_system(chi, D, J=0.7, seed=10 + chi + D)
+        for direction in walk:
+            base.contractTowards(direction)
+        v = base.state_center_data
+        # ---- unsharded reference on this GPU
+        cd.unshard_environment()
+        H0, N0 = base.formExpectationAndNormalizationMultipliers()
+        hv0, nv0 = H0(v).toArray(), N0(v).toArray()
+        e0, n0 = base.computeExpectationAndNormalization()
+        Hm0, Nm0 = H0.formMatrix().toArray(), N0.formMatrix().toArray()
+        sub0 = base.formNormalizationSubmatrix().toArray()
+        one = copy(base)
+        saved = utils.Multiplier.isCheaperToFormMatrix
+        if force_gmres:
+            utils.Multiplier.isCheaperToFormMatrix = lambda self, n: False
+        try:
+            one.minimizeExpectation()
+            energy0 = one.computeExpectation()
+            # ---- sharded over all ranks
+            sharding = cd.shard_environment()
+            H1, N1 = base.formExpectationAndNormalizationMultipliers()
+            hv1, nv1 = H1(v), N1(v)
+            e1, n1 = base.computeExpectationAndNormalization()
+            Hm1, Nm1 = H1.formMatrix(), N1.formMatrix()
+            sub1 = base.formNormalizationSubmatrix()
+            many = copy(base)
+            stats = {}
+            many.minimizeExpectation(statistics=stats)
+            energy1 = many.computeExpectation()
+            state = many.state_center_data._t
+            checks = {
+                "Hv": rel(hv1.toArray(), hv0), "Nv": rel(nv1.toArray(), nv0),
+                "<H>": abs(e1 - e0) / abs(e0), "<N>": abs(n1 - n0) / abs(n0),
+                "H matrix": rel(Hm1.toArray(), Hm0), "N matrix": rel(Nm1.toArray(), Nm0),
+                "N submatrix": rel(sub1.toArray(), sub0),
+            }
+            worst = max(checks.values())
+            same = all(_identical_on_all_ranks(t, world) for t in (hv1._t, nv1._t, Hm1._t, Nm1._t, state))
+            de = abs(energy1 - energy0) / abs(energy0)
+            if worst > 1e-12 or not same or de > 1e-10 or sharding.world != world:
+                failures.append(("system", chi, D, walk, checks, same, de))
+            if rank == 0:
+                print("system chi=%d D=%d walk=%s gmres=%s: worst rel err %.2e, minimised energy rel diff %.2e, "
+                      "N^-1 by %s, identical_across_ranks=%s" % (chi, D, walk, force_gmres, worst, de,
+                                                                 stats.get("normalization"), same), flush=True)
+        finally:
+            utils.Multiplier.isCheaperToFormMatrix = saved
+            cd.unshard_environment()
+    # a short sharded sweep: minimise + absorb + compress, replicated parts must stay in lock step
+    np.random.seed(5)
+    system = synthetic.device_system(2, 2, J=0.5, seed=3)
+    cd.shard_environment()
+    try:
+        for direction in (0, 1, 2, 3, 0, 1):
+            system.minimizeExpectation()
+            system.contractTowards(direction)
+            for corner_id in range(4):          # ConstantStateCompressionPolicy(2).apply()
+                for d in (0, 1):
+                    system.compressCornerStateTowards(corner_id, d, 2)
+        energy = system.computeExpectation()
+        if not _identical_on_all_ranks(system.state_center_data._t, world) or not np.isfinite(energy):
+            failures.append(("sharded sweep diverged across ranks", energy))
+        if rank == 0:
+            print("sharded sweep of 6 iterations: <H> = %.12f, states identical across ranks" % energy.real, flush=True)
+    finally:
+        cd.unshard_environment()
+    return failures
 
 
 if __name__ == "__main__":

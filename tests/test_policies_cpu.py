@@ -140,3 +140,22 @@ def test_relative_state_difference_policy_with_stand_in_tensors():
     system.state_center_data = Vec(1.0, 0.5, 0.0)      # a bandwidth increase changes the shape: never converged
     p.update()
     assert p.converged() is False
+
+
+def test_hook_policy_accepts_a_bound_method_callback():
+    """A callable stored on a policy that is a bound method of ANOTHER object must reach the policy untouched (the
+    reference's Proxy forwards plain attributes, policies.py:12-44); only the template's own methods are rebound."""
+    class Spy:
+        def __init__(self):
+            self.seen = []
+
+        def hook(self, system):
+            self.seen.append(system)
+            return "called"
+
+    spy = Spy()
+    system = Recorder([1.0])
+    binding = pol.HookPolicy(spy.hook).createBindingToSystem(system)
+    assert binding.apply() == "called"
+    assert spy.seen == [system]
+    assert binding.callback.__self__ is spy
