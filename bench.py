@@ -1,34 +1,51 @@
 #!/usr/bin/env python
 """Headline benchmark: the center-site expectation matvec (BASELINE.json metric "center-site matvec GFLOP/s").
 
-(The term structure is read off the planner itself: see term_table_device / term_table_cpu.)
-
 A step is one application of the expectation multiplier H = sum_t B_t . (A_t . (O_t v)) that
 ``System.formExpectationMultiplier()`` builds (reference tensors/_2d/sparse.py:100-161, dense.py:115-203) for the
 2D transverse-field Ising Hamiltonian after one absorption round: T = 9 sparse terms over 6 + 6 stage-2
 environment tensors, state bond D and boundary bond chi, d = 2.
 Tensors are synthetic (random complex128) and stay resident in HBM, exactly as they do between the reference's
 formExpectationStage2 and the Arnoldi iteration; the environment is far larger than L2 (12 x 16 X D^4 bytes).
+The term structure is read off the planner itself (term_table_device / term_table_cpu).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--D 8] [--chi 16] [--impl reference]
 
 N > 1 (under torchrun): the joined environment bond X = chi^4 is split into N slabs, one per GPU (strong
 scaling: the same matvec, sharded); every rank holds the full vector and the partial results are summed by
-one allreduce of the N-vector over NVLink.
+one all-reduce of the N-vector over NVLink.
+
+Before anything is timed the job checks itself (``parity`` in the JSON line; the run aborts on a miss): the fused
+kernel against the CPU oracle on an X slab of THE BENCH TENSORS, the fused kernel against the unfused DMMA GEMM path
+on the whole local environment, and at N > 1 the sharded result against the NCCL sum of the ranks' unsharded results
+plus bit-identity across ranks.
+
+Sub-lines of the same JSON object: ``heisenberg`` (BASELINE config 4: T = 20 terms, X-slab sharding and, at N > 1,
+term sharding beside it), ``capacity`` (N = 8: (D, chi) = (8, 32), 824 GB of stage-2 tensors built per X slab through
+the library's own formExpectationStage1/2/3 in the system-level multi-GPU mode -- impossible on one GPU) and ``sweep``
+(N = 1: seconds per sweep iteration vs bond dimension).
 
 FLOP accounting: 8 x the cmac count the reference's CostTracker assigns to the multiplier
 (``Multiplier.cost_of_multiply``, data/cost_tracker.py:17-21) = 16 T X D^6 d -- the work the reference performs
 for this call, whatever shortcuts the device path takes.
 """
-import argparse
-import json
 import os
-import subprocess
 import sys
-import threading
-import time
 
-import numpy as np
+# The reference arm and the cpu_baseline leg use every host core.  torchrun exports OMP_NUM_THREADS=1 to its workers
+# (round 1's N >= 2 reference lines were timed on one BLAS thread because of it), so the thread count is set
+# explicitly, before NumPy loads its BLAS.
+if "--impl" in sys.argv and "reference" in sys.argv:
+    for _var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_var] = str(os.cpu_count() or 1)
+
+import argparse  # noqa: E402
+import json  # noqa: E402
+import subprocess  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -36,6 +53,7 @@ if ROOT not in sys.path:
 
 METRIC = "center_site_expectation_matvec_gflops"
 UNIT = "GFLOP/s"
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
 _Z = np.array([[1, 0], [0, -1]], dtype=np.complex128)
 _X = np.array([[0, 1], [1, 0]], dtype=np.complex128)
@@ -60,13 +78,9 @@ def _operator_lists(model, J):
     return [], list(pairs), list(pairs)
 
 
-def term_table_device(model, J=1.0):
-    """The stage-3 term structure as the product's own planner produces it: a trivial system (all bonds 1) of the
-    model is absorbed once in every direction and its expectation multiplier's term list is read off.  Only the
-    STRUCTURE (which half-0 tensor meets which half-1 tensor under which site operator) is used; the benchmark's
-    tensors are synthetic."""
+def trivial_device_system(model, J=1.0):
+    """A bond-1 system of the model absorbed once in every direction: carries the tag structure of a real run."""
     from carcassonne_b200.data import DeviceData
-    from carcassonne_b200.sparse import Identity
     from carcassonne_b200.system import System
     Os, UDs, LRs = _operator_lists(model, J)
     dev = DeviceData.fromArray
@@ -74,6 +88,14 @@ def term_table_device(model, J=1.0):
                                                  [(dev(a), dev(b)) for a, b in LRs])
     for direction in range(4):
         system.contractTowards(direction)
+    return system
+
+
+def term_table_device(model, J=1.0):
+    """The stage-3 term structure as the product's own planner produces it.  Only the STRUCTURE (which half-0 tensor
+    meets which half-1 tensor under which site operator) is used; the benchmark's tensors are synthetic."""
+    from carcassonne_b200.sparse import Identity
+    system = trivial_device_system(model, J)
     H, _ = system.formExpectationAndNormalizationMultipliers()
     ops = system.operator_center_tensor
     return _index_terms(H.terms, lambda z: None if z == Identity() else ops[z].toArray())
@@ -152,75 +174,141 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------
-def cpu_matvec_sample(D, d, table, X_sample, repeats=1, seed=0):
-    """Times the oracle's restatement of the reference matvec (two tensordots per term, NumPy -> BLAS zgemm)
-    on an X slab of the workload.  Returns (GFLOP/s, seconds, threads)."""
-    from oracle import dense
+# CPU side: the reference itself (baseline/_ref, copied from /root/reference by oracle/install_reference.py) or, when it
+# is absent, the oracle's restatement of it.
+def blas_threads():
     try:
         from threadpoolctl import threadpool_info
-        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
     except Exception:
-        threads = os.cpu_count() or 1
-    rng = np.random.default_rng(seed)
-    P = D * D
+        return os.cpu_count() or 1
 
-    def crand(*shape):
-        return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
 
-    na, nb, terms = table
-    A = [crand(X_sample, D, D, D, D) for _ in range(na)]
-    B = [crand(X_sample, D, D, D, D) for _ in range(nb)]
-    v = crand(D, D, D, D, d)
+def use_all_host_threads():
+    """Best effort at run time as well (the environment variables above only help before BLAS is loaded)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
+    return blas_threads()
 
-    def matvec():
-        out = np.zeros_like(v)
-        for a, b, o in terms:
-            out += dense.stage3_multiply_joined(A[a], B[b], v, o)
+
+class ReferenceMatvec:
+    """The UNMODIFIED reference's expectation multiplier on an X slab of the workload: the tag structure comes from the
+    reference's own System (trivial model system absorbed in all four directions, then its formExpectationStage1/2),
+    the stage-2 tensors are synthetic [xs, 1, D, D, D, D] / [1, xs, D, D, D, D] NDArrayData, and the timed call is
+    ``formExpectationStage3(...)[0](center)`` (reference tensors/_2d/sparse.py:100-161)."""
+    kind = "reference"
+
+    def __init__(self, model, D, d, xs, seed=0):
+        if REF_DIR not in sys.path:
+            sys.path.insert(0, REF_DIR)
+        sys.dont_write_bytecode = True
+        from carcassonne.data import NDArrayData
+        from carcassonne.system import System
+        from carcassonne.tensors._2d.sparse import formExpectationStage1, formExpectationStage2, formExpectationStage3
+        Os, UDs, LRs = _operator_lists(model, 1.0)
+        N = NDArrayData
+        system = System.newTrivialWithSparseOperator(Os=[N(o) for o in Os], OO_UDs=[(N(a), N(b)) for a, b in UDs],
+                                                     OO_LRs=[(N(a), N(b)) for a, b in LRs])
+        for direction in range(4):
+            system.contractTowards(direction)
+        s1 = [formExpectationStage1(system.corners[i], system.sides[i]) for i in range(4)]
+        tags_0, tags_1 = list(formExpectationStage2(s1[0], s1[1])), list(formExpectationStage2(s1[2], s1[3]))
+        rng = np.random.default_rng(seed)
+
+        def crand(*shape):
+            return N(rng.standard_normal(shape) + 1j * rng.standard_normal(shape))
+
+        stage2_0 = {tag: crand(xs, 1, D, D, D, D) for tag in tags_0}
+        stage2_1 = {tag: crand(1, xs, D, D, D, D) for tag in tags_1}
+        self.multiplier, _ = formExpectationStage3(stage2_0, stage2_1, system.operator_center_tensor)
+        self.center = crand(D, D, D, D, d)
+        self.flops = 8.0 * self.multiplier.cost_of_multiply       # the reference's own CostTracker count
+        self.what = "carcassonne.tensors._2d.sparse.formExpectationStage3 multiplier of the unmodified reference " \
+                    "(baseline/_ref), NumPy tensordot -> OpenBLAS zgemm"
+
+    def __call__(self):
+        return self.multiplier(self.center)
+
+
+class PortMatvec:
+    """Fallback when baseline/_ref is absent: the oracle's restatement (two tensordots per term)."""
+    kind = "port"
+
+    def __init__(self, model, D, d, xs, seed=0):
+        from oracle import dense
+        self.dense = dense
+        na, nb, self.terms = term_table_cpu(model)
+        rng = np.random.default_rng(seed)
+
+        def crand(*shape):
+            return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+        self.A = [crand(xs, D, D, D, D) for _ in range(na)]
+        self.B = [crand(xs, D, D, D, D) for _ in range(nb)]
+        self.v = crand(D, D, D, D, d)
+        self.flops = 8.0 * cost_of_multiply(self.terms, xs, D, d)
+        self.what = "oracle.dense.stage3_multiply_joined (NumPy tensordot -> BLAS zgemm)"
+
+    def __call__(self):
+        out = np.zeros_like(self.v)
+        for a, b, o in self.terms:
+            out += self.dense.stage3_multiply_joined(self.A[a], self.B[b], self.v, o)
         return out
 
-    matvec() if X_sample <= 64 else None  # tiny warm-up only when cheap
-    best = float("inf")
+
+def make_cpu_matvec(model, D, d, xs):
+    if os.path.isdir(os.path.join(REF_DIR, "carcassonne")):
+        try:
+            return ReferenceMatvec(model, D, d, xs)
+        except Exception as exc:      # pragma: no cover - a broken copy must not hide the baseline altogether
+            sys.stderr.write("reference package under baseline/_ref failed to run (%r); timing the oracle port\n" % (exc,))
+    return PortMatvec(model, D, d, xs)
+
+
+def pick_cpu_sample(D, X, nterms, seconds=1.5, gflops=60.0):
+    """X slab that costs about `seconds` of host work at a typical rate."""
+    per_x = 8.0 * nterms * 2 * (D ** 6) * 2
+    return int(max(1, min(X, seconds * gflops * 1e9 / per_x)))
+
+
+def time_cpu(matvec, repeats):
+    secs = []
     for _ in range(repeats):
         t0 = time.perf_counter()
         matvec()
-        best = min(best, time.perf_counter() - t0)
-    flops = 8.0 * cost_of_multiply(terms, X_sample, D, d)
-    return flops / best / 1e9, best, threads
-
-
-def pick_cpu_sample(D, X, nterms=9):
-    """X slab that costs about 10-20 s of CPU work at ~10 GFLOP/s."""
-    per_x = 8.0 * nterms * 2 * (D ** 6) * 2
-    xs = int(max(1, min(X, 1.5e11 / per_x)))
-    return xs
+        secs.append(time.perf_counter() - t0)
+    return secs
 
 
 def run_reference(args, rank, world):
+    """Reference arm: the reference's own CPU implementation of the path on the box's host cores (all of them), each
+    step one matvec over a bounded X slab of the workload.  `ms_per_step` is the MEASURED slab time; the extrapolation
+    to the whole environment is a separate key."""
     if rank != 0:
         return
+    threads = use_all_host_threads()
     D, chi, d = args.D, args.chi, 2
     X = chi ** 4
-    table = term_table_cpu(args.model)
-    terms = table[2]
-    xs = pick_cpu_sample(D, X, len(terms))
-    if args.steps * 1.0 > 6:
-        xs = max(1, xs * 6 // args.steps)
-    for _ in range(args.warmup):
-        cpu_matvec_sample(D, d, table, max(1, xs // 8))
-    vals, secs = [], []
-    threads = 1
-    for _ in range(args.steps):
-        g, s, threads = cpu_matvec_sample(D, d, table, xs)
-        vals.append(g)
-        secs.append(s)
-    value = float(np.mean(vals))
-    sample = "T=%d %s terms, D=%d, X slab of %d of %d (chi=%d)" % (len(terms), args.model, D, xs, X, chi)
+    nterms = 9 if args.model == "tfim" else 20
+    xs = pick_cpu_sample(D, X, nterms)
+    matvec = make_cpu_matvec(args.model, D, d, xs)
+    time_cpu(matvec, max(1, min(args.warmup, 3)))
+    secs = time_cpu(matvec, args.steps)
+    mean_s = float(np.mean(secs))
+    value = matvec.flops / mean_s / 1e9
+    sample = "T=%d %s terms, D=%d, X slab of %d of %d (chi=%d), %.2f s per step; %s" % (
+        nterms, args.model, D, xs, X, chi, mean_s, matvec.what)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3 * (X / xs),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean_s * 1e3,
+        "ms_per_full_matvec_extrapolated": mean_s * 1e3 * (X / xs), "x_sample": xs, "x_full": X,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "complex128 (f64)",
-        "data": "synthetic", "config": workload_config(args, X, len(terms)),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "data": "synthetic", "config": workload_config(args, X, nterms),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": matvec.kind, "sample": sample,
+                         "host_cpus": os.cpu_count(), "best_gflops": matvec.flops / min(secs) / 1e9},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -239,57 +327,174 @@ def workload_config(args, X, nterms):
 
 
 # ------------------------------------------------------------------------------------------------------------
-def run_device(args, rank, world, local_rank):
-    import torch
-    import torch.distributed as dist
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    import ctypes as C
-    from carcassonne_b200 import _lib
-    from carcassonne_b200.data import DeviceData
-    from carcassonne_b200.operator import Stage3Operator
+class DeviceJob:
+    """Rank-local state shared by the sections of the device arm."""
 
-    D, chi, d = args.D, args.chi, 2
-    X = chi ** 4
-    x_lo, x_hi = X * rank // world, X * (rank + 1) // world
-    Xl = x_hi - x_lo
-    na, nb, terms = term_table_device(args.model)
-    gen = torch.Generator(device="cuda")
-    gen.manual_seed(1234 + rank)
+    def __init__(self, args, rank, world, local_rank):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.args, self.rank, self.world, self.local_rank = args, rank, world, local_rank
+        self.gen = torch.Generator(device="cuda")
+        self.gen.manual_seed(1234 + rank)
+        self.comm = None
 
-    def rnd(*shape):
-        t = torch.empty(shape, dtype=torch.complex128, device="cuda")
-        torch.view_as_real(t).normal_(generator=gen)
+    def rnd(self, *shape):
+        t = self.torch.empty(shape, dtype=self.torch.complex128, device="cuda")
+        self.torch.view_as_real(t).normal_(generator=self.gen)
         return t
 
-    scale = 1.0 / (D * D * np.sqrt(X))
-    A = [DeviceData(rnd(Xl, D, D, D, D).mul_(scale)) for _ in range(na)]
-    B = [DeviceData(rnd(Xl, D, D, D, D).mul_(scale)) for _ in range(nb)]
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        """Device time of `steps` calls (CUDA events on the launching stream), max over ranks, in ms."""
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def peer_comm(self, n):
+        from carcassonne_b200 import distributed as cd
+        if self.comm is None and self.world > 1 and self.args.reduce == "peer":
+            self.comm = cd.PeerComm(max(n, 1 << 16))
+        return self.comm
+
+    def identical_on_all_ranks(self, t):
+        if self.world == 1:
+            return True
+        gathered = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(gathered, t.contiguous())
+        return all(self.torch.equal(gathered[0], g) for g in gathered)
+
+
+def build_operator(job, model, D, d, X_local, mode="xslab"):
+    """Synthetic environment of one rank + its device operator.  mode "xslab": every term over this rank's X slab;
+    "terms": whole (A_t, B_t) pairs dealt to the ranks by cost (BASELINE config 4's term sharding)."""
+    from carcassonne_b200 import distributed as cd
+    from carcassonne_b200.data import DeviceData
+    from carcassonne_b200.operator import Stage3Operator
+    na, nb, terms = term_table_device(model)
+    mine = list(range(len(terms)))
+    if mode == "terms" and job.world > 1:
+        mine = cd.balance_terms([1 + (o is not None) * 1e-6 for _, _, o in terms], job.world)[job.rank]
+    used_a = sorted({terms[t][0] for t in mine})
+    used_b = sorted({terms[t][1] for t in mine})
+    scale = 1.0 / (D * D * np.sqrt(max(X_local, 1) * job.world))
+    A = {a: DeviceData(job.rnd(X_local, D, D, D, D).mul_(scale)) for a in used_a}
+    B = {b: DeviceData(job.rnd(X_local, D, D, D, D).mul_(scale)) for b in used_b}
     op = Stage3Operator((D, D, D, D, d))
-    for a, b, o in terms:
+    for t in mine:
+        a, b, o = terms[t]
         op.add_term(A[a], B[b], o)
     op.finalize()
-    if args.path:
-        op.set_path(args.path)
-    kernel_name = {1: "stage3_kernel (fused A.v -> O -> B^T, DMMA.8x8x4)",
-                   3: "stage3f_kernel (fused A.v -> O -> B^T, spin index folded into the tile columns, DMMA.8x8x4)",
-                   2: "zgemm_kernel x 3 per term (unfused DMMA GEMMs)"}.get(op.path, "?")
-    A_keep.extend([A, B, op])
-    comm = None
-    if world > 1 and args.reduce == "peer":
-        from carcassonne_b200 import distributed as cd
-        comm = cd.PeerComm(D ** 4 * d)
-        cd.shard_operator(op, comm)
-    use_nccl = world > 1 and comm is None
+    return {"op": op, "A": A, "B": B, "terms": terms, "mine": mine, "na": na, "nb": nb}
+
+
+def parity_gate(job, env, D, d, v, tol=1e-12):
+    """In-job parity ("parity gates run in the same job").  Returns the record for the JSON line
+    and raises SystemExit when a check misses `tol`."""
+    torch, dist = job.torch, job.dist
+    from carcassonne_b200 import distributed as cd
+    from carcassonne_b200.data import DeviceData
+    from carcassonne_b200.operator import Stage3Operator
+    from oracle import dense
+    op, A, B, terms, mine = env["op"], env["A"], env["B"], env["terms"], env["mine"]
+    record = {"tolerance": tol}
+    # (a) the device kernel against the CPU oracle on an X slab of the bench tensors themselves
+    xs = 8
+    slab = Stage3Operator((D, D, D, D, d))
+    keep = []
+    for t in mine:
+        a, b, o = terms[t]
+        As, Bs = DeviceData(A[a]._t[:xs]), DeviceData(B[b]._t[:xs])
+        keep += [As, Bs]
+        slab.add_term(As, Bs, o)
+    slab.finalize()
+    got = slab(DeviceData(v)).toArray()
+    want = np.zeros_like(got)
+    v_host = v.cpu().numpy()
+    for t in mine:
+        a, b, o = terms[t]
+        want += dense.stage3_multiply_joined(A[a]._t[:xs].cpu().numpy(), B[b]._t[:xs].cpu().numpy(), v_host, o)
+    record["slab_vs_oracle"] = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+    record["slab"] = "first %d X entries of every local tensor, device path %d" % (xs, slab.path)
+    slab.close()
+    # (b) the whole local environment: fused kernel against the unfused DMMA GEMM path (no exchange)
+    cd.shard_operator(op, None)
+    fused = torch.empty_like(v)
+    op.apply_raw(v, fused)
+    chosen = op.path
+    op.set_path(2)
+    unfused = torch.empty_like(v)
+    op.apply_raw(v, unfused)
+    op.set_path(job.args.path)
+    record["fused_vs_unfused_full_size"] = float((torch.linalg.vector_norm(fused - unfused) /
+                                                  torch.linalg.vector_norm(unfused)).item())
+    record["fused_path"] = chosen
+    # (c) N > 1: the sharded apply (exchange fused into the partial-sum pass) against the NCCL sum of the local results
+    if job.world > 1:
+        total = fused.clone()
+        dist.all_reduce(total)
+        comm = job.peer_comm(v.numel())
+        if comm is not None:
+            cd.shard_operator(op, comm)
+            sharded = torch.empty_like(v)
+            op.apply_raw(v, sharded)
+        else:
+            sharded = fused.clone()
+            dist.all_reduce(sharded)
+        record["sharded_vs_nccl_sum"] = float((torch.linalg.vector_norm(sharded - total) /
+                                               torch.linalg.vector_norm(total)).item())
+        record["identical_across_ranks"] = bool(job.identical_on_all_ranks(sharded))
+        if comm is not None and comm.timed_out():
+            raise SystemExit("parity gate: peer all-reduce timed out")
+    worst = torch.tensor([max(record["slab_vs_oracle"], record["fused_vs_unfused_full_size"],
+                              record.get("sharded_vs_nccl_sum", 0.0))], dtype=torch.float64, device="cuda")
+    same = torch.tensor([1 if record.get("identical_across_ranks", True) else 0], device="cuda")
+    if job.world > 1:
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    record["worst_over_ranks"] = float(worst.item())
+    record["ok"] = bool(worst.item() <= tol and same.item() == 1)
+    if not record["ok"]:
+        raise SystemExit("PARITY GATE FAILED: %s" % json.dumps(record))
+    return record
+
+
+def matvec_section(job, model, D, chi, d, steps, warmup, mode="xslab", gate=True, e2e=False):
+    """Builds the synthetic environment of `model`, checks it, times `steps` matvecs.  -> dict of measurements."""
+    torch, dist = job.torch, job.dist
+    from carcassonne_b200 import distributed as cd
+    X = chi ** 4
+    x_lo, x_hi = cd.slab_bounds(X, job.rank, job.world) if mode == "xslab" else (0, X)
+    Xl = x_hi - x_lo
+    env = build_operator(job, model, D, d, Xl, mode)
+    op, terms = env["op"], env["terms"]
+    if job.args.path:
+        op.set_path(job.args.path)
     n = D ** 4 * d
     v_host = torch.empty((D, D, D, D, d), dtype=torch.complex128).pin_memory()
     torch.view_as_real(v_host).normal_()
     out_host = torch.empty_like(v_host).pin_memory()
     v = v_host.cuda()
     out = torch.empty_like(v)
-    if world > 1:
+    if job.world > 1:
         dist.broadcast(v, 0)
+    parity = parity_gate(job, env, D, d, v) if gate else None
+    comm = job.peer_comm(n)
+    cd.shard_operator(op, comm)
+    use_nccl = job.world > 1 and comm is None
 
     def step():
         op.apply_raw(v, out)
@@ -298,120 +503,280 @@ def run_device(args, rank, world, local_rank):
 
     def step_e2e():
         v.copy_(v_host, non_blocking=True)
-        op.apply_raw(v, out)
-        if use_nccl:
-            dist.all_reduce(out)
+        step()
         out_host.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         step()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(job.local_rank)
+    if job.rank == 0:
         sampler.start()
         time.sleep(0.3)
     t0 = time.time()
-    total_ms = timed(step, args.steps)
+    total_ms = job.timed(step, steps)
     t1 = time.time()
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
-
+    clocks = sampler.stop(t0, t1) if job.rank == 0 else None
+    res = {"ms_per_step": total_ms / steps, "clocks": clocks, "parity": parity, "terms": len(terms),
+           "flops": 8.0 * cost_of_multiply(terms, X, D, d), "executed_local": op.executed_flops,
+           "path": op.path, "X_local": Xl, "n": n,
+           "bytes_local": (len(env["A"]) + len(env["B"])) * 16 * Xl * D ** 4 + 32 * n}
     # duration of the dominant kernel (fused stage-3 + its partial-sum pass; with the peer communicator attached the
     # partial-sum pass is the cross-GPU one, so at N > 1 this includes the exchange)
-    kern_ms = timed(lambda: op.apply_raw(v, out), args.steps) / args.steps
+    res["kernel_ms"] = job.timed(lambda: op.apply_raw(v, out), steps) / steps
+    if e2e:
+        for _ in range(3):
+            step_e2e()
+        res["e2e_ms_per_step"] = job.timed(step_e2e, steps) / steps
+    res["timed_out"] = bool(comm.timed_out()) if comm is not None else False
+    cd.shard_operator(op, None)
+    op.close()
+    del env, op
+    torch.cuda.empty_cache()
+    return res
 
-    for _ in range(3):
-        step_e2e()
-    e2e_ms = timed(step_e2e, args.steps)
 
-    flops = 8.0 * cost_of_multiply(terms, X, D, d)            # whole job, reference accounting
-    flops_local = 8.0 * cost_of_multiply(terms, Xl, D, d)
-    ms_per_step = total_ms / args.steps
-    value = flops / (ms_per_step * 1e-3) / 1e9
+KERNEL_NAMES = {1: "stage3_kernel (fused A.v -> O -> B^T, DMMA.8x8x4)",
+                3: "stage3f_kernel (fused A.v -> O -> B^T, spin index folded into the tile columns, DMMA.8x8x4)",
+                2: "zgemm_kernel x 3 per term (unfused DMMA GEMMs)"}
 
-    comm_failed = comm.timed_out() if comm is not None else False
-    if comm is not None:
-        comm.close()
+
+def fp64_peaks(torch):
+    """FP64 rates measured in this process on this GPU: the DMMA issue-rate microbenchmark (roofline denominator), the
+    vendor library (cuBLAS ZGEMM through torch.matmul) and this library's zgemm_kernel on the same 4096^3 product."""
+    import ctypes as C
+    from carcassonne_b200 import _lib
+    from carcassonne_b200.data import gemm
+    tf = C.c_double()
+    _lib.check(_lib.lib.carc_dmma_peak(4000, C.byref(tf), None))
+    m = 4096
+    a = torch.randn(m, m, dtype=torch.complex128, device="cuda")
+    b = torch.randn(m, m, dtype=torch.complex128, device="cuda")
+    c = torch.empty_like(a)
+
+    def rate(fn):
+        fn()
+        torch.cuda.synchronize()
+        best = float("inf")
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 8.0 * m ** 3 / (best * 1e-3) / 1e12
+
+    cublas = rate(lambda: torch.matmul(a, b, out=c))
+    ours = rate(lambda: gemm(_lib.OP_N, _lib.OP_N, m, m, m, a, m, b, m, c))
+    del a, b, c
+    return tf.value, cublas, ours
+
+
+def static_traffic(D, chi, world):
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(path)).get("D%d_chi%d_n%d" % (D, chi, world))
+    except Exception:
+        return None
+
+
+def capacity_section(job, D, chi, d, steps):
+    """(D, chi) = (8, 32): 12 stage-2 tensors of 68.7 GB each (824 GB) -- SURVEY.md section 7's "sharding is a
+    capacity requirement" case.  Every rank holds the same synthetic corners / sides (tag structure of a real TFIM
+    run) and, in the system-level multi-GPU mode, builds only its X slab through the library's own
+    formExpectationStage1 / Stage2 / Stage3; the expectation multiplier is then applied and a capped device relaxOver
+    (N^-1 by LU of the all-reduced dense normalization matrix) is run on it."""
+    torch = job.torch
+    from carcassonne_b200 import distributed as cd
+    from carcassonne_b200.data import DeviceData
+    from carcassonne_b200.tensors._2d import sparse as sp
+    from carcassonne_b200.utils import relaxOver
+    free = torch.tensor([torch.cuda.mem_get_info()[0]], dtype=torch.float64, device="cuda")
+    if job.world > 1:
+        job.dist.all_reduce(free, op=job.dist.ReduceOp.MIN)     # one decision for all ranks
+    free = float(free.item())
+    per_rank = 12 * 16 * chi ** 4 * D ** 4 / job.world
+    if free < per_rank * 1.35:
+        return {"skipped": "needs %.0f GB per GPU for the stage-2 slabs, %.0f GB free" % (per_rank / 1e9, free / 1e9)}
+    template = trivial_device_system("tfim")
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(99)                      # the SAME environment on every rank (replicated corners / sides)
+
+    def rnd(*shape):
+        t = torch.empty(shape, dtype=torch.complex128, device="cuda")
+        torch.view_as_real(t).normal_(generator=gen)
+        return DeviceData(t.mul_(1.0 / (chi * np.sqrt(chi))))
+
+    t_build0 = time.time()
+    cd.shard_environment()
+    try:
+        halves = []
+        for pair in ((0, 1), (2, 3)):
+            stage1 = []
+            for i in pair:
+                corner = {tag: rnd(chi, chi, 1, chi, chi, 1) for tag in template.corners[i]}
+                side = {tag: rnd(chi, chi, 1, chi, chi, 1, D, D) for tag in template.sides[i]}
+                stage1.append(sp.formExpectationStage1(corner, side))
+                del corner, side
+            halves.append(sp.formExpectationStage2(stage1[0], stage1[1], half=len(halves)))
+            del stage1
+            torch.cuda.empty_cache()
+        H, N = sp.formExpectationStage3(halves[0], halves[1], template.operator_center_tensor)
+        torch.cuda.synchronize()
+        build_s = time.time() - t_build0
+        held = sum(16 * t.size() for h in halves for t in h.values())
+        v = DeviceData(torch.randn(D, D, D, D, d, dtype=torch.complex128, device="cuda", generator=gen))
+        out = torch.empty_like(v._t)
+        op = H.device_operator
+        for _ in range(2):
+            op.apply_raw(v._t, out)
+        ms = job.timed(lambda: op.apply_raw(v._t, out), steps) / steps
+        same = job.identical_on_all_ranks(out)
+        flops = 8.0 * H.cost_of_multiply
+        res = {"D": D, "chi": chi, "X": chi ** 4, "terms": len(H.terms),
+               "stage2_bytes_total": float(sum(16 * h.full_X[tag] * D ** 4 for h in halves for tag in h)),
+               "stage2_bytes_this_rank": float(held), "build_s": build_s, "ms_per_matvec": ms,
+               "value": flops / (ms * 1e-3) / 1e9, "unit": UNIT,
+               "executed_tflops_per_gpu": op.executed_flops / (ms * 1e-3) / 1e12,
+               "identical_across_ranks": bool(same),
+               "how": "formExpectationStage1/2/3 of carcassonne_b200.tensors._2d.sparse with "
+                      "distributed.shard_environment() active; replicated synthetic corners / sides"}
+        if not job.args.no_capacity_relax:
+            # the environment is random, not a physical double layer: the generalised problem need not be definite and
+            # the reference's RelaxFailed test may fire -- identically on every rank (bit-identical vectors)
+            stats = {}
+            t0 = time.time()
+            try:
+                state = relaxOver(v, H, N, maximum_number_of_multiplications=6, statistics=stats)._t
+                outcome = "ok"
+            except Exception as exc:
+                state, outcome = out, repr(exc)[:200]
+            torch.cuda.synchronize()
+            res["relax"] = {"seconds": time.time() - t0, "outcome": outcome,
+                            "multiplications": stats.get("multiplications"), "normalization": stats.get("normalization"),
+                            "initial": [stats["initial_value"].real, stats["initial_value"].imag] if stats else None,
+                            "final": [stats["final_value"].real, stats["final_value"].imag] if stats else None,
+                            "state_identical_across_ranks": bool(job.identical_on_all_ranks(state))}
+        del H, N, halves, op
+        return res
+    finally:
+        cd.unshard_environment()
+        sp.environment_cache.clear()
+        torch.cuda.empty_cache()
+
+
+def run_device(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        from datetime import timedelta
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=timedelta(seconds=180))
+    job = DeviceJob(args, rank, world, local_rank)
+    D, chi, d = args.D, args.chi, 2
+    X = chi ** 4
+    warmup = max(args.warmup, 3)
+
+    main = matvec_section(job, args.model, D, chi, d, args.steps, warmup, e2e=True)
+    if main["timed_out"]:
+        raise SystemExit("peer all-reduce timed out")
+
+    heis = None
+    if not args.no_heisenberg and args.model == "tfim":
+        hsteps = max(3, min(args.steps, 10))
+        h = matvec_section(job, "heisenberg", D, chi, d, hsteps, 3)
+        heis = {"config": "Heisenberg expectation matvec, T=%d terms over 14 + 14 stage-2 tensors, D=%d, chi=%d"
+                          % (h["terms"], D, chi),
+                "value": h["flops"] / (h["ms_per_step"] * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": h["ms_per_step"],
+                "steps": hsteps, "sharding": "X slabs",
+                "executed_tflops_per_gpu": h["executed_local"] / (h["kernel_ms"] * 1e-3) / 1e12,
+                "parity": h["parity"]}
+        if world > 1:
+            ht = matvec_section(job, "heisenberg", D, chi, d, hsteps, 3, mode="terms", gate=False)
+            heis["term_sharding"] = {"value": ht["flops"] / (ht["ms_per_step"] * 1e-3) / 1e9,
+                                     "ms_per_step": ht["ms_per_step"],
+                                     "note": "whole (A_t, B_t) pairs dealt to the ranks (BASELINE config 4); uneven "
+                                             "(20 terms, stars broken up) next to the perfectly balanced X slabs"}
+
+    capacity = None
+    if (args.capacity or world == 8) and not args.no_capacity:
+        try:
+            capacity = capacity_section(job, 8, 32, d, max(3, min(args.steps, 5)))
+        except Exception as exc:       # the headline line must survive a failed extra
+            capacity = {"error": repr(exc)[:300]}
+            torch.cuda.empty_cache()
+
+    if job.comm is not None:
+        job.comm.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    if comm_failed:
-        raise SystemExit("peer all-reduce timed out")
 
-    tf = C.c_double()
-    _lib.check(_lib.lib.carc_dmma_peak(4000, C.byref(tf), None))
-    executed = op.executed_flops                              # DMMA flops the kernel issues (shared-B grouping)
-    achieved_tf = executed / (kern_ms * 1e-3) / 1e12
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("D%d_chi%d_n%d" % (D, chi, world))
-        except Exception:
-            traffic = None
-    roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": tf.value, "unit": "TFLOP/s",
-                "frac": achieved_tf / tf.value, "traffic": traffic,
-                "kernel": kernel_name,
+    peak, cublas_tf, zgemm_tf = fp64_peaks(torch)
+    flops = main["flops"]
+    ms_per_step = main["ms_per_step"]
+    value = flops / (ms_per_step * 1e-3) / 1e9
+    executed = main["executed_local"]
+    achieved_tf = executed / (main["kernel_ms"] * 1e-3) / 1e12
+    flops_local = flops / world
+    n = main["n"]
+    roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak, "traffic": static_traffic(D, chi, world),
+                "traffic_source": "static: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of "
+                                  "this kernel at this size (profiles/traffic.json), NOT measured in this run",
+                "kernel": KERNEL_NAMES.get(main["path"], "?"),
                 "executed_flops_per_launch": executed, "reference_flops_per_launch": flops_local,
                 "note": "achieved = FP64 flops the kernel issues / its duration.  The kernel decomposes the term list "
                         "into stars (terms sharing a half-1 tensor: first products summed before one second product; "
                         "terms sharing a half-0 tensor: one first product reused), so it issues %.0f%% of the flops "
                         "the reference performs for the same result -- `value` counts the reference's flops"
                         % (100.0 * executed / flops_local),
+                "cublas_zgemm_tflops": cublas_tf, "zgemm_kernel_tflops": zgemm_tf,
+                "vendor_note": "torch.matmul complex128 (cuBLAS ZGEMM) and this library's zgemm_kernel on the same "
+                               "4096^3 product, measured in this process: the vendor library's FP64 rate beside the "
+                               "DMMA issue-rate peak and beside the fused kernel",
                 "peak_distinct_operands": 31.4,
                 "peak_note": "peak = DMMA.8x8x4 issue rate with register-resident operands; with a fresh A/B fragment "
                              "per instruction (what any GEMM inner loop needs) the same microbenchmark tops out at "
                              "31.4 TFLOP/s on this part (scripts/dmma_rate.py, 8 warps/SM)",
                 "peak_source": "DMMA.8x8x4 issue-rate microbenchmark run in this process (carc_dmma_peak); "
                                "MEASURED_PEAKS.json has no FP64 figure",
-                "algorithmic_bytes": (na + nb) * 16 * Xl * D ** 4 + 32 * n,
-                "hbm_gbs": ((na + nb) * 16 * Xl * D ** 4 + 32 * n) / (kern_ms * 1e-3) / 1e9}
+                "algorithmic_bytes": main["bytes_local"],
+                "hbm_gbs": main["bytes_local"] / (main["kernel_ms"] * 1e-3) / 1e9}
 
     cpu = None
     if world == 1 and not args.no_cpu:
-        xs = pick_cpu_sample(D, X, len(terms))
-        g, s, threads = cpu_matvec_sample(D, d, term_table_cpu(args.model), xs)
-        cpu = {"value": g, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "T=%d %s terms, D=%d, X slab of %d of %d, %.1f s, oracle.dense.stage3_multiply_joined "
-                         "(NumPy tensordot -> BLAS zgemm)" % (len(terms), args.model, D, xs, X, s)}
+        threads = use_all_host_threads()
+        xs = pick_cpu_sample(D, X, main["terms"], seconds=4.0)
+        matvec = make_cpu_matvec(args.model, D, d, xs)
+        time_cpu(matvec, 1)
+        secs = time_cpu(matvec, 3)
+        cpu = {"value": matvec.flops / float(np.mean(secs)) / 1e9, "unit": UNIT, "cores": threads, "kind": matvec.kind,
+               "sample": "T=%d %s terms, D=%d, X slab of %d of %d, 3 x %.1f s; %s" % (
+                   main["terms"], args.model, D, xs, X, float(np.mean(secs)), matvec.what)}
 
     sweep = None
     if world == 1 and not args.no_sweep:
-        op.close()
-        del A, B, op
         sweep = sweep_section(args.no_cpu)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "complex128 (f64)", "data": "synthetic",
-        "config": workload_config(args, X, len(terms)),
-        "clocks": clocks,
-        "e2e": {"value": flops / (e2e_ms / args.steps * 1e-3) / 1e9, "unit": UNIT,
+        "config": workload_config(args, X, main["terms"]),
+        "clocks": main["clocks"],
+        "e2e": {"value": flops / (main["e2e_ms_per_step"] * 1e-3) / 1e9, "unit": UNIT,
                 "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n,
                 "what": "Stage3Operator applied to a pinned host vector: H2D of v, matvec (+allreduce), D2H of H v; "
                         "the environment stays resident as it does behind the reference's Multiplier closure"},
-        "gpu_launches": 2 * args.steps,   # stage3_kernel + (s3_reduce_kernel | xgpu_allreduce_kernel) per step
+        "gpu_launches": 2 * args.steps,   # stage3f_kernel + (s3_reduce_kernel | xgpu_allreduce_kernel) per step
+        "parity": main["parity"],
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "heisenberg": heis,
+        "capacity": capacity,
         "sweep": sweep,
     }
     print(json.dumps(line), flush=True)
@@ -423,11 +788,9 @@ def sweep_section(no_cpu):
     """Second half of the BASELINE metric: seconds per sweep iteration vs bond dimension.  One iteration =
     minimizeExpectation + contractTowards + ConstantStateCompressionPolicy(chi) on a synthetic double-layer TFIM
     environment (scripts/sweep_bench.py); four iterations (one per direction) per size.  The CPU column is the
-    oracle's restatement of the same calls on the host cores, at the size where it finishes in tens of seconds."""
-    import torch
+    oracle's restatement of the same calls on the host cores, at the sizes where it finishes in tens of seconds."""
     sys.path.insert(0, os.path.join(ROOT, "scripts"))
     import sweep_bench
-    del A_keep[:]                      # drop the matvec environment (51 GB); torch's allocator reuses the blocks
     rows = []
     sweep_bench.device_iterations(2, 2, False)   # warm-up
     for D, chi in ((3, 6), (4, 8), (6, 8), (8, 8)):
@@ -447,9 +810,6 @@ def sweep_section(no_cpu):
     return out
 
 
-A_keep = []
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -462,6 +822,11 @@ def main():
                     help="which Hamiltonian's sparse term structure to benchmark (T = 9 / 20 terms)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sweep", action="store_true", help="skip the seconds-per-sweep-iteration section")
+    ap.add_argument("--no-heisenberg", action="store_true", help="skip the Heisenberg (T = 20) sub-line")
+    ap.add_argument("--capacity", action="store_true",
+                    help="run the (D, chi) = (8, 32) capacity section (default: only at 8 GPUs)")
+    ap.add_argument("--no-capacity", action="store_true")
+    ap.add_argument("--no-capacity-relax", action="store_true")
     ap.add_argument("--path", type=int, default=0, choices=[0, 1, 2, 3],
                     help="device path of the matvec: 0 automatic, 1 fused kernel, 3 fused kernel with the folded "
                          "tiling, 2 unfused GEMMs (kernel comparisons; the default is what the library picks)")
