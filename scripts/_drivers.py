@@ -149,7 +149,7 @@ def _seed(seed):
     random.seed(seed)
 
 
-def run_tfim_chain(J, seed=0, sweep_tol=1e-5, run_tol=1e-7, increment=2):
+def run_tfim_chain(J, seed=0, sweep_tol=1e-5, run_tol=1e-7, increment=2, counts=None):
     """Infinite transverse-Ising chain through the 2D system driven along one axis (reference
     tests/test_simulator_2d_in_1d.py:36-47 with the coupling as a parameter).  Returns (energy per site, seconds,
     final bond dimension, sweeps)."""
@@ -166,6 +166,8 @@ def run_tfim_chain(J, seed=0, sweep_tol=1e-5, run_tol=1e-7, increment=2):
     t0 = time.perf_counter()
     system.runUntilConverged()
     energy = complex(system.computeOneSiteExpectation())
+    if counts is not None:
+        counts.update(sweeps=system.number_of_sweeps, iterations=system.number_of_iterations)
     return energy.real, time.perf_counter() - t0, system.state_center_data.shape[0], system.number_of_sweeps
 
 
