@@ -584,7 +584,9 @@ void s3_choose(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, int 
     // folded kernel's symmetric warps (every warp issues its own copies) win when an A_x tile is large (D = 8: 28.2 vs
     // 27.6 TFLOP/s), stage3_kernel's single issuing warp when it is small (D = 4: 23.1 vs 21.1).
     const double work = (double)k->NPT * k->NSB * k->CH * (4.0 * k->Q8 + 4.0 * k->NRT);
-    const bool fold = kf->padded_work < 0.97 * work || (kf->padded_work <= 1.0001 * work && (int64_t)P * Q >= 1024);
+    // (round 2: with its tile loops free of run-time predicates the folded kernel wins at equal work for every size --
+    // D = 4, chi = 16: 25.8 vs 23.1 TFLOP/s)
+    const bool fold = kf->padded_work <= 1.0001 * work;
     if (fold) *can_fuse = false;
     else *can_fold = false;
   }

@@ -22,6 +22,8 @@
 //     (full barrier: one expect-tx arrival per warp) after waiting for the slot's empty barrier;
 //   * every warp runs the same producer cursor over the flattened op sequence, ahead of its consumer cursor.
 // DMMA work relative to stage3_kernel: 0.82 (D = 5), 0.86 (D = 6), 0.78 (D = 7), 0.66 (D = 3).
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -42,8 +44,10 @@ struct S3FParams {
   int P, Q, R, S;
   int Q4, NPT, G, NSB, nstA, nstB, QS, BSTR;
   int b_whole;                    // one S block: B_x is one contiguous copy, issued by the warps in turn
+  int skew_cycles;                // start-up delay per co-resident warp of an SM sub-partition (see the kernel)
   int sb_cta0[S3F_MAX_SB + 1];    // S block i has sb_cta0[i+1] - sb_cta0[i] CTAs (one X slab each)
   unsigned char cta_sb[160], cta_sl[160];   // CTA -> (S block, X slab): CTAs sharing a stretch of X are neighbours
+  unsigned char cta_map[160];               // blockIdx.x of this launch -> CTA (launches are per S-block width)
   int sb_tile0[S3F_MAX_SB + 1];   // S block i covers the tiles (4 S columns each) [sb_tile0[i], sb_tile0[i+1])
   uint32_t slotA_bytes, slotB_bytes, ops_off, hasop_off, tab_off, vt_off, vtail_off, ring_off, smem_total;
   const cplx* v;
@@ -75,34 +79,55 @@ struct S3FLane {
   bool tail, eswap;
 };
 
-// T[jj] += A_x (8 rows of this warp) * Vt (tile jbase + jj), for the tiles below ntv.  (Loading the next operands ahead
-// of the current DMMAs -- the asm statements keep their source order -- was measured: +2 % at D = 8, -5 % at D = 5
-// through spills, nothing at D = 6, 7; the plain order is kept.)
-template <int NJ>
+// Is tile j of the S block active?  NA > 0: the block holds exactly NA tiles, known at compile time; NA == 0: it holds
+// L.ntv tiles, a run-time number.  This distinction is what the kernel's speed hangs on: a run-time test around the
+// DMMAs of a tile is a (possibly divergent) branch, after which mma.sync needs a WARPSYNC, and it pins the tile's
+// operand loads directly in front of their first use -- the SASS was [BRA, WARPSYNC, LDS, LDS, 8 DMMA] per tile, every
+// load latency exposed, 76 % DMMA pipe utilisation at D = 8.  With the tile count a template parameter the same loop
+// is straight-line code that ptxas software-pipelines (scripts/dmma_loops.cu: these loops alone reach 37.1 TFLOP/s,
+// the issue-rate peak).
+template <int NA>
+__device__ __forceinline__ bool s3f_active(int j, const S3FLane& L) {
+  return NA > 0 ? j < NA : j < L.ntv;
+}
+
+// One paired k-step (8 values of Q) of the first product for the active tiles.
+template <int NJ, int NA>
+__device__ __forceinline__ void s3f_first_step(CTile (&T)[NJ], int jbase, const S3FLane& L, uint32_t a_base, int kp) {
+  const cplx x0 = lds_c(a_base + kp * 128 + L.a_first);
+  const cplx x1 = lds_c(a_base + kp * 128 + L.a_second);
+  const cplx a0 = L.eswap ? x1 : x0;
+  const cplx a1 = L.eswap ? x0 : x1;
+#pragma unroll
+  for (int jj = 0; jj < NJ; ++jj) {
+    if (s3f_active<NA>(jbase + jj, L)) {
+      const uint32_t va = L.v_pair + (uint32_t)(jbase + jj) * L.tile_stride + kp * 128;
+      const cplx b0 = lds_c(va);
+      const cplx b1 = lds_c(va + 16);
+      cmma(T[jj], a0.x, a0.y, -a0.y, b0.x, b0.y);
+      cmma(T[jj], a1.x, a1.y, -a1.y, b1.x, b1.y);
+    }
+  }
+}
+
+// T[jj] += A_x (8 rows of this warp) * Vt (tile jbase + jj), for the active tiles.  NP > 0: the number of paired k-steps
+// is known at compile time (NP = Q / 8 for the uniform bond dimensions) and the k loop is unrolled completely -- no loop
+// branch, and every operand load of the op is free to move ahead of the DMMAs before it.
+template <int NJ, int NA, int NP>
 __device__ __forceinline__ void s3f_first(CTile (&T)[NJ], int jbase, const S3FLane& L, uint32_t slot) {
   const uint32_t a_base = slot + L.a_pair;
-#pragma unroll 2
-  for (int kp = 0; kp < L.npairs; ++kp) {
-    const cplx x0 = lds_c(a_base + kp * 128 + L.a_first);
-    const cplx x1 = lds_c(a_base + kp * 128 + L.a_second);
-    const cplx a0 = L.eswap ? x1 : x0;
-    const cplx a1 = L.eswap ? x0 : x1;
+  if (NP > 0) {
 #pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) {
-      if (jbase + jj < L.ntv) {
-        const uint32_t va = L.v_pair + (uint32_t)(jbase + jj) * L.tile_stride + kp * 128;
-        const cplx b0 = lds_c(va);
-        const cplx b1 = lds_c(va + 16);
-        cmma(T[jj], a0.x, a0.y, -a0.y, b0.x, b0.y);
-        cmma(T[jj], a1.x, a1.y, -a1.y, b1.x, b1.y);
-      }
-    }
+    for (int kp = 0; kp < NP; ++kp) s3f_first_step<NJ, NA>(T, jbase, L, a_base, kp);
+  } else {
+#pragma unroll 2
+    for (int kp = 0; kp < L.npairs; ++kp) s3f_first_step<NJ, NA>(T, jbase, L, a_base, kp);
   }
   if (L.tail) {
     const cplx a = lds_c(slot + L.a_tail);
 #pragma unroll
     for (int jj = 0; jj < NJ; ++jj) {
-      if (jbase + jj < L.ntv) {
+      if (s3f_active<NA>(jbase + jj, L)) {
         const cplx b = lds_c(L.v_tail + (uint32_t)(jbase + jj) * L.tail_stride);
         cmma(T[jj], a.x, a.y, -a.y, b.x, b.y);
       }
@@ -148,8 +173,12 @@ __device__ __forceinline__ void s3f_second(CTile (&acc)[NRT][2], const CTile& W,
   }
 }
 
-template <int NRT, int NT>
+// NA: number of tiles the S blocks of THIS launch hold (NT or NT - 1: an uneven split of S gives blocks of both widths
+// and one launch per width), or 0 for "read it at run time" (see s3f_active).
+// NP: number of paired k-steps of the first product when it is a compile-time constant for this launch, else 0.
+template <int NRT, int NT, int NA, int NP>
 __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const S3FParams p) {
+  const int cta = p.cta_map[blockIdx.x];   // position in the whole job's CTA table (slab, S block, partial slot)
   constexpr int DP = 2;
   constexpr int UW = NT < 2 ? NT : 2;   // tiles per pass of a later term's first product (register budget)
   extern __shared__ __align__(128) unsigned char smem[];
@@ -183,7 +212,7 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
   }
   __syncthreads();
 
-  const int sb = p.cta_sb[blockIdx.x], sl = p.cta_sl[blockIdx.x];
+  const int sb = p.cta_sb[cta], sl = p.cta_sl[cta];
   const int NSL = p.sb_cta0[sb + 1] - p.sb_cta0[sb];
   const int S0 = 4 * p.sb_tile0[sb];
   const int SBv = min(4 * (p.sb_tile0[sb + 1] - p.sb_tile0[sb]), p.S - S0);
@@ -280,9 +309,14 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
     const uint32_t b_row_bytes = (uint32_t)(SBv * 16);
     // rows wg, wg + NPT, ... of the B block are this warp's to copy
     const int my_rows = p.R > wg ? (p.R - wg + p.NPT - 1) / p.NPT : 0;
-    auto issueA = [&](const Cursor& cu, uint32_t it) {
+    // ring positions are kept as (slot, parity) counters: the stage counts are run-time values and a modulo / division
+    // per op costs as much as a dozen DMMAs' worth of issue slots between two ops
+    int pA_slot = 0, pB_slot = 0, pB_par = 1, pB_turn = 0;      // producer side (pB_par: parity of the EMPTY barrier)
+    int cA_slot = 0, cA_par = 0, cB_slot = 0, cB_par = 0;       // consumer side
+    auto issueA = [&](const Cursor& cu) {
       const cplx* A = groupKind[cu.gi] ? groupCenter[cu.gi] : termA[groupFirst[cu.gi] + cu.j];
-      const int sa = it % p.nstA;
+      const int sa = pA_slot;
+      if (++pA_slot == p.nstA) pA_slot = 0;
       if (lane == 0) {
         // the slot was read by this warp's own lanes (all past the __syncwarp that follows every first product)
         fence_proxy_async();
@@ -290,22 +324,29 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
         bulk_g2s(ringA + sa * p.slotA_bytes, A + ((int64_t)cu.x * p.P + 8 * wg) * p.Q, a_bytes, bA + sa * 8);
       }
     };
-    auto issueB = [&](const Cursor& cu, uint32_t it) {
+    auto issueB = [&](const Cursor& cu) {
       const cplx* B = groupKind[cu.gi] ? termB[groupFirst[cu.gi] + cu.j - 1] : groupCenter[cu.gi];
-      const int sbq = it % p.nstB;
+      const int sbq = pB_slot;
+      const uint32_t empty_parity = (uint32_t)pB_par;
+      const bool my_turn = pB_turn == wg;
+      if (++pB_slot == p.nstB) {
+        pB_slot = 0;
+        pB_par ^= 1;
+      }
+      if (++pB_turn == p.NPT) pB_turn = 0;
       const uint32_t fullB = bB + (2 * sbq) * 8;
       const uint32_t dst = ringB + sbq * p.slotB_bytes;
       if (p.b_whole) {
         // the S block is all of S: B_x is contiguous (row stride S), one copy, issued by the group's warps in turn
-        if ((int)(it % (uint32_t)p.NPT) == wg && lane == 0) {
-          mbar_wait(fullB + 8, ((it / p.nstB) & 1) ^ 1);
+        if (my_turn && lane == 0) {
+          mbar_wait(fullB + 8, empty_parity);
           mbar_arrive_expect_tx(fullB, (uint32_t)(p.R * p.S * 16));
           bulk_g2s(dst, B + (int64_t)cu.x * p.R * p.S, (uint32_t)(p.R * p.S * 16), fullB);
         }
         return;
       }
       if (lane == 0) {
-        mbar_wait(fullB + 8, ((it / p.nstB) & 1) ^ 1);
+        mbar_wait(fullB + 8, empty_parity);
         if (my_rows > 0) mbar_arrive_expect_tx(fullB, b_row_bytes * my_rows);
         else mbar_arrive(fullB);
       }
@@ -318,6 +359,16 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
     Cursor cc = {-1, 0, 0, 0}, pc = {-1, 0, 0, 0};
     uint32_t issuedA = 0, issuedB = 0, itA = 0, itB = 0;
     bool more = true, pending = false;
+    // Warps w, w + 4, w + 8 share an SM sub-partition and with it one DMMA pipe.  They run the same op sequence, and
+    // started together they stay phase-locked: both reach the stretch between two ops (cursor, copies, site operator,
+    // accumulator shuffling -- no DMMA for ~1500 cycles) at the same time and the pipe idles.  Starting each co-resident
+    // warp a fraction of an op later keeps one warp's bookkeeping under the other's DMMAs; the offset is stable because
+    // a warp that has the pipe to itself runs at twice the shared rate for exactly the other's bookkeeping time.
+    if (p.skew_cycles > 0 && (warp >> 2) > 0) {
+      const long long t_skew = clock64() + (long long)(warp >> 2) * p.skew_cycles;
+      while (clock64() < t_skew) {
+      }
+    }
     auto run_ahead = [&]() {
       while (more) {
         if (!pending) {
@@ -327,10 +378,12 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
         }
         if (groupKind[pc.gi] ? (pc.j == 0) : (pc.j < groupCount[pc.gi])) {
           if (issuedA - itA >= (uint32_t)p.nstA) break;
-          issueA(pc, issuedA++);
+          issueA(pc);
+          ++issuedA;
         } else {
           if (issuedB - itB >= (uint32_t)p.nstB) break;
-          issueB(pc, issuedB++);
+          issueB(pc);
+          ++issuedB;
         }
         pending = false;
       }
@@ -344,21 +397,27 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
         // ---- first term of the star: all tiles of the S block accumulate straight into T
         run_ahead();
         const bool has_op = !kind && hasop[first] != 0;   // an A-star keeps the raw product
-        const int slot = itA % p.nstA;
-        S3F_WAIT(0, bA + slot * 8, (itA / p.nstA) & 1);
+        const int slot = cA_slot;
+        S3F_WAIT(0, bA + slot * 8, cA_par);
 #pragma unroll
         for (int j = 0; j < NT; ++j) T[j].zero();
-        s3f_first<NT>(T, 0, L, ringA + slot * p.slotA_bytes);
+        s3f_first<NT, NA, NP>(T, 0, L, ringA + slot * p.slotA_bytes);
         if (has_op) {
 #pragma unroll
           for (int j = 0; j < NT; ++j) {
-            const CTile U = T[j];
-            T[j].zero();
-            s3f_apply_op(T[j], U, ops + first * DP * DP);
+            if (NA == 0 || j < NA) {
+              const CTile U = T[j];
+              T[j].zero();
+              s3f_apply_op(T[j], U, ops + first * DP * DP);
+            }
           }
         }
         __syncwarp();
         ++itA;
+        if (++cA_slot == p.nstA) {
+          cA_slot = 0;
+          cA_par ^= 1;
+        }
       }
       if (!kind) {
         for (int jt = 1; jt < cnt; ++jt) {
@@ -366,38 +425,48 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
           // ---- a further term of a B-star: T += O (A_x v); without a site operator the DMMA chains simply continue
           const int term = first + jt;
           const bool has_op = hasop[term] != 0;
-          const int slot = itA % p.nstA;
-          S3F_WAIT(1, bA + slot * 8, (itA / p.nstA) & 1);
+          const int slot = cA_slot;
+          S3F_WAIT(1, bA + slot * 8, cA_par);
           const uint32_t aslot = ringA + slot * p.slotA_bytes;
           if (!has_op) {
-            s3f_first<NT>(T, 0, L, aslot);
+            s3f_first<NT, NA, NP>(T, 0, L, aslot);
           } else {
 #pragma unroll
             for (int j0 = 0; j0 < NT; j0 += UW) {
-              CTile U[UW];
+              if (NA == 0 || j0 < NA) {
+                CTile U[UW];
 #pragma unroll
-              for (int jj = 0; jj < UW; ++jj) U[jj].zero();
-              s3f_first<UW>(U, j0, L, aslot);
+                for (int jj = 0; jj < UW; ++jj) U[jj].zero();
+                s3f_first<UW, NA, NP>(U, j0, L, aslot);
 #pragma unroll
-              for (int jj = 0; jj < UW; ++jj)
-                if (j0 + jj < NT) s3f_apply_op(T[j0 + jj], U[jj], ops + term * DP * DP);
+                for (int jj = 0; jj < UW; ++jj)
+                  if (j0 + jj < NT && (NA == 0 || j0 + jj < NA)) s3f_apply_op(T[j0 + jj], U[jj], ops + term * DP * DP);
+              }
             }
           }
           __syncwarp();
           ++itA;
+          if (++cA_slot == p.nstA) {
+            cA_slot = 0;
+            cA_par ^= 1;
+          }
         }
         run_ahead();
         // ---- second product of the star: acc += T * B_x^T
         {
-          const int slot = itB % p.nstB;
-          S3F_WAIT(2, bB + (2 * slot) * 8, (itB / p.nstB) & 1);
+          const int slot = cB_slot;
+          S3F_WAIT(2, bB + (2 * slot) * 8, cB_par);
           const uint32_t b_base = ringB + slot * p.slotB_bytes + b_lane_off;
 #pragma unroll
           for (int j = 0; j < NT; ++j)
-            if (j < L.ntv) s3f_second<NRT>(acc, T[j], j, b_base, rt_stride);
+            if (s3f_active<NA>(j, L)) s3f_second<NRT>(acc, T[j], j, b_base, rt_stride);
           __syncwarp();
           if (lane == 0) mbar_arrive(bB + (2 * slot + 1) * 8);
           ++itB;
+          if (++cB_slot == p.nstB) {
+            cB_slot = 0;
+            cB_par ^= 1;
+          }
         }
       } else {
         // ---- A-star: T holds A_x v once; every term applies its own site operator and multiplies with its own B_x
@@ -405,12 +474,12 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
           run_ahead();
           const int term = first + jt;
           const bool has_op = hasop[term] != 0;
-          const int slot = itB % p.nstB;
-          S3F_WAIT(2, bB + (2 * slot) * 8, (itB / p.nstB) & 1);
+          const int slot = cB_slot;
+          S3F_WAIT(2, bB + (2 * slot) * 8, cB_par);
           const uint32_t b_base = ringB + slot * p.slotB_bytes + b_lane_off;
 #pragma unroll
           for (int j = 0; j < NT; ++j) {
-            if (j < L.ntv) {
+            if (s3f_active<NA>(j, L)) {
               CTile W;
               if (has_op) {
                 W.zero();
@@ -424,12 +493,16 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
           __syncwarp();
           if (lane == 0) mbar_arrive(bB + (2 * slot + 1) * 8);
           ++itB;
+          if (++cB_slot == p.nstB) {
+            cB_slot = 0;
+            cB_par ^= 1;
+          }
         }
       }
     }
 #ifdef S3F_PROFILE
-    if (lane == 0 && blockIdx.x < 148 && warp < 12) {
-      unsigned long long* o = s3f_prof + ((int)blockIdx.x * 12 + warp) * 4;
+    if (lane == 0 && cta < 148 && warp < 12) {
+      unsigned long long* o = s3f_prof + (cta * 12 + warp) * 4;
       o[0] = prof_wait[0];
       o[1] = prof_wait[1];
       o[2] = prof_wait[2];
@@ -437,7 +510,7 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
     }
 #endif
     // ---- partial result of this (CTA, group)
-    cplx* part = p.partial + ((int64_t)blockIdx.x * p.G + g) * ((int64_t)p.P * p.R * DP);
+    cplx* part = p.partial + ((int64_t)cta * p.G + g) * ((int64_t)p.P * p.R * DP);
     const int row = wg * 8 + r;
     if (row < p.P) {
 #pragma unroll
@@ -460,18 +533,89 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
   }
 }
 
-template <int NRT>
-int s3f_launch(const S3FParams& p, int ctas, int threads, cudaStream_t stream) {
+template <int NRT, int NA, int NP>
+int s3f_launch_np(const S3FParams& p, int ctas, int threads, cudaStream_t stream) {
   static bool configured[16] = {false};
   int dev = 0;
   CARC_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev < 16 && !configured[dev]) {
-    CARC_CHECK_CUDA(cudaFuncSetAttribute(stage3f_kernel<NRT, s3f_tiles(NRT)>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         S3F_SMEM_LIMIT));
+    CARC_CHECK_CUDA(cudaFuncSetAttribute(stage3f_kernel<NRT, s3f_tiles(NRT), NA, NP>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, S3F_SMEM_LIMIT));
     configured[dev] = true;
   }
-  stage3f_kernel<NRT, s3f_tiles(NRT)><<<ctas, threads, p.smem_total, stream>>>(p);
+  stage3f_kernel<NRT, s3f_tiles(NRT), NA, NP><<<ctas, threads, p.smem_total, stream>>>(p);
   CARC_CHECK_CUDA(cudaGetLastError());
+  return CARC_OK;
+}
+
+// Paired k-steps of the first product at the uniform bond dimension whose R = D^2 gives NRT row tiles (Q = D^2 as well):
+// D = 8: 8, D = 7: 6, D = 6: 4, D = 5: 3, D = 4: 2; 0 = no such D (those shapes keep the run-time loop).
+constexpr int s3f_uniform_pairs(int nrt) { return nrt == 8 ? 8 : nrt == 7 ? 6 : nrt == 5 ? 4 : nrt == 4 ? 3 : nrt == 2 ? 2 : 0; }
+
+template <int NRT, int NA>
+int s3f_launch_one(const S3FParams& p, int ctas, int threads, cudaStream_t stream) {
+  constexpr int NP = s3f_uniform_pairs(NRT);
+  static const bool unrolled = !(getenv("CARC_S3F_NP") && atoi(getenv("CARC_S3F_NP")) == 0);   // experiments
+  if (unrolled && NP > 0 && (p.Q4 >> 1) == NP) return s3f_launch_np<NRT, NA, NP>(p, ctas, threads, stream);
+  return s3f_launch_np<NRT, NA, 0>(p, ctas, threads, stream);
+}
+
+// A second stream per device, so that the launches of one apply (one per S-block width, together one CTA per SM) run
+// side by side: fork from the caller's stream, join back into it.
+struct S3FSideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+int s3f_side_stream(S3FSideStream** out) {
+  static S3FSideStream side[16];
+  int dev = 0;
+  CARC_CHECK_CUDA(cudaGetDevice(&dev));
+  CARC_REQUIRE(dev < 16, CARC_ERR_VALUE, "device index %d not supported", dev);
+  S3FSideStream& s = side[dev];
+  if (!s.stream) {
+    CARC_CHECK_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CARC_CHECK_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    CARC_CHECK_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+  }
+  *out = &s;
+  return CARC_OK;
+}
+
+// One launch per S-block width: the CTAs whose block holds `tiles` tiles run the kernel instantiated for that count.
+// The widest blocks go to the caller's stream, the others (an uneven split of S has two widths) to the side stream.
+template <int NRT>
+int s3f_launch(S3FParams& p, const Stage3FConfig& k, cudaStream_t stream) {
+  constexpr int NT = s3f_tiles(NRT);
+  int widths[S3F_MAX_SB + 1], nw = 0;
+  for (int i = 0; i < k.NSB; ++i) {
+    const int tiles = k.sb_tile0[i + 1] - k.sb_tile0[i];
+    bool seen = false;
+    for (int j = 0; j < nw; ++j) seen = seen || widths[j] == tiles;
+    if (!seen) widths[nw++] = tiles;
+  }
+  S3FSideStream* side = nullptr;
+  if (nw > 1) {
+    int rc = s3f_side_stream(&side);
+    if (rc) return rc;
+    CARC_CHECK_CUDA(cudaEventRecord(side->fork, stream));
+    CARC_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+  }
+  for (int w = nw - 1; w >= 0; --w) {       // side-stream launches first, the caller's stream last
+    const int tiles = widths[w];
+    cudaStream_t st = w == 0 ? stream : side->stream;
+    int n = 0;
+    for (int c = 0; c < k.ctas; ++c)
+      if (k.sb_tile0[k.cta_sb[c] + 1] - k.sb_tile0[k.cta_sb[c]] == tiles) p.cta_map[n++] = (unsigned char)c;
+    int rc;
+    if (tiles == NT) rc = s3f_launch_one<NRT, NT>(p, n, k.threads, st);
+    else if (NT > 1 && tiles == NT - 1) rc = s3f_launch_one<NRT, (NT > 1 ? NT - 1 : NT)>(p, n, k.threads, st);
+    else rc = s3f_launch_one<NRT, 0>(p, n, k.threads, st);
+    if (rc) return rc;
+  }
+  if (nw > 1) {
+    CARC_CHECK_CUDA(cudaEventRecord(side->join, side->stream));
+    CARC_CHECK_CUDA(cudaStreamWaitEvent(stream, side->join, 0));
+  }
   return CARC_OK;
 }
 
@@ -603,6 +747,15 @@ int stage3f_launch(const Stage3Plan* plan, const Stage3FConfig& k, int P, int Q,
   p.P = P; p.Q = Q; p.R = R; p.S = S;
   p.Q4 = k.Q4; p.NPT = k.NPT; p.G = k.G; p.NSB = k.NSB; p.nstA = k.nstA; p.nstB = k.nstB; p.QS = k.QS; p.BSTR = k.BSTR;
   p.b_whole = k.b_whole;
+  {
+    // one op of a warp is NT * Q4 complex k-steps = 4 NT Q4 DMMAs of 16 pipe cycles; with n warps per sub-partition an op
+    // takes n times that, and the i-th of them starts i / n of it late
+    const int per_sp = (k.threads / 32 + 3) / 4;
+    const int nt = k.sb_tile0[1] - k.sb_tile0[0];
+    static const char* env = getenv("CARC_S3F_SKEW");     // experiments: 0 disables, other values scale (percent)
+    const int pct = env ? atoi(env) : 100;
+    p.skew_cycles = per_sp > 1 ? (int)((int64_t)4 * nt * k.Q4 * 16 * pct / 100) : 0;
+  }
   for (int i = 0; i <= S3F_MAX_SB; ++i) {
     p.sb_cta0[i] = i <= k.NSB ? k.sb_cta0[i] : 0;
     p.sb_tile0[i] = i <= k.NSB ? k.sb_tile0[i] : 0;
@@ -616,15 +769,16 @@ int stage3f_launch(const Stage3Plan* plan, const Stage3FConfig& k, int P, int Q,
   p.smem_total = k.total;
   p.v = v;
   p.partial = partial;
+  for (int c = 0; c < 160; ++c) p.cta_map[c] = 0;
   switch (k.NRT) {
-    case 1: return s3f_launch<1>(p, k.ctas, k.threads, stream);
-    case 2: return s3f_launch<2>(p, k.ctas, k.threads, stream);
-    case 3: return s3f_launch<3>(p, k.ctas, k.threads, stream);
-    case 4: return s3f_launch<4>(p, k.ctas, k.threads, stream);
-    case 5: return s3f_launch<5>(p, k.ctas, k.threads, stream);
-    case 6: return s3f_launch<6>(p, k.ctas, k.threads, stream);
-    case 7: return s3f_launch<7>(p, k.ctas, k.threads, stream);
-    default: return s3f_launch<8>(p, k.ctas, k.threads, stream);
+    case 1: return s3f_launch<1>(p, k, stream);
+    case 2: return s3f_launch<2>(p, k, stream);
+    case 3: return s3f_launch<3>(p, k, stream);
+    case 4: return s3f_launch<4>(p, k, stream);
+    case 5: return s3f_launch<5>(p, k, stream);
+    case 6: return s3f_launch<6>(p, k, stream);
+    case 7: return s3f_launch<7>(p, k, stream);
+    default: return s3f_launch<8>(p, k, stream);
   }
 }
 

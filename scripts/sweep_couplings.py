@@ -61,7 +61,9 @@ def run_point(model, J, args):
         counts = {}
         energy, seconds, bond, sweeps = _drivers.run_tfim_chain(J, seed=args.seed, sweep_tol=args.sweep_tol,
                                                                  run_tol=args.run_tol, counts=counts)
-        exact = float(_drivers.tfim_infinite_chain_energy(J))
+        # _drivers.tfim_infinite_chain_energy keeps the reference script's convention (computeTIinfinite.py:6-12: its
+        # argument is twice the XX coupling, lam = J / 2); the run's Hamiltonian is -sum Z - J sum X X
+        exact = float(_drivers.tfim_infinite_chain_energy(2.0 * J))
         return {"J": J, "energy_per_site": energy, "exact": exact, "error": abs(energy - exact), "bond": bond,
                 "sweeps": sweeps, "iterations": counts.get("iterations"), "seconds": seconds}
     energies, seconds, bond, sweeps, note = _drivers.run_tfim_plane(J, args.chi, args.max_bandwidth, seed=args.seed)

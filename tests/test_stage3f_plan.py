@@ -92,13 +92,13 @@ def test_block_shares_follow_the_tile_counts():
 
 
 def test_which_tiling_runs():
-    """The measured choice: the folded tiling wherever it issues fewer DMMA steps and, at equal
-    work, where an A_x tile is large; the original tiling at D = 4; unfused GEMMs outside both envelopes."""
+    """The measured choice: the folded tiling wherever it issues no more DMMA steps than the
+    original one (every uniform D since round 2: 25.8 vs 23.1 TFLOP/s at D = 4); unfused GEMMs outside both envelopes."""
     def path(D, d=2, X=65536, force=0, P=None):
         n = P if P is not None else D * D
         return _lib.lib.carc_stage3_path(9, n, n, n, n, d, X, force)
 
-    assert [path(D) for D in (2, 3, 4, 5, 6, 7, 8)] == [3, 3, 1, 3, 3, 3, 3]
+    assert [path(D) for D in (2, 3, 4, 5, 6, 7, 8)] == [3, 3, 3, 3, 3, 3, 3]
     assert path(4, force=3) == 3 and path(8, force=1) == 1 and path(6, force=2) == 2
     assert path(3, d=3) == 2                      # both fused kernels are specific to d = 2
     assert path(9) == 2                           # 81 rows: more than 8 row tiles
