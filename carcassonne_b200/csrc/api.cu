@@ -249,9 +249,17 @@ int carc_operator_create_dense(carc_operator** op, const void* matrix_dev, int64
 
 int64_t carc_operator_dimension(const carc_operator* op) { return op ? op->n : -1; }
 
+int carc_operator_path(const carc_operator* op);
 double carc_operator_executed_flops(const carc_operator* op) {
   if (!op || op->kind != 0 || !op->plan) return -1.0;
-  return carc::stage3_executed_flops(op->plan, op->P, op->Q, op->R, op->S, op->d);
+  int column_blocks = 1;
+  if (carc_operator_path(op) == 3) {
+    int64_t Xmax = 0;
+    for (const auto& t : op->terms) Xmax = std::max<int64_t>(Xmax, t.X);
+    carc::Stage3FConfig k;
+    if (carc::stage3f_configure((int)op->terms.size(), op->P, op->Q, op->R, op->S, op->d, Xmax, &k)) column_blocks = k.RB;
+  }
+  return carc::stage3_executed_flops(op->plan, op->P, op->Q, op->R, op->S, op->d, column_blocks);
 }
 int carc_operator_path(const carc_operator* op) {
   if (!op || op->kind != 0 || !op->finalized) return -1;
@@ -302,6 +310,10 @@ int carc_stage3f_describe(int nterms, int P, int Q, int R, int S, int d, int64_t
   for (int i = 0; i < 17; ++i) out[o++] = i <= k.NSB ? k.sb_cta0[i] : -1;
   for (int i = 0; i < 160; ++i) out[o++] = i < k.ctas ? k.cta_sb[i] : -1;
   for (int i = 0; i < 160; ++i) out[o++] = i < k.ctas ? k.cta_sl[i] : -1;
+  if (out_len >= o + 2) {     // row / column blocks of the output (NPT, NRT above are those of the largest block)
+    out[o++] = k.PB;
+    out[o++] = k.RB;
+  }
   return CARC_OK;
 }
 int carc_operator_num_groups(const carc_operator* op) { return (op && op->plan) ? (int)op->plan->groups.size() : -1; }

@@ -82,7 +82,7 @@ struct Stage3Plan {
 int stage3_plan_create(const Stage3Term* terms, int nterms, Stage3Plan** out);
 void stage3_plan_host(const Stage3Term* terms, int nterms, Stage3Plan* plan);
 void stage3_plan_destroy(Stage3Plan* plan);
-double stage3_executed_flops(const Stage3Plan* plan, int P, int Q, int R, int S, int d);
+double stage3_executed_flops(const Stage3Plan* plan, int P, int Q, int R, int S, int d, int column_blocks = 1);
 int stage3_apply(const Stage3Plan* plan, int P, int Q, int R, int S, int d, const cplx* v, cplx* out, cplx* workspace,
                  int64_t workspace_elems, int force_path, cudaStream_t stream, Comm* comm = nullptr);
 int64_t stage3_workspace_elems(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax);
@@ -91,6 +91,7 @@ int stage3_path(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, int
 // stage3f.cu: the folded tiling of the fused kernel (spin index folded into the columns of the first product)
 struct Stage3FConfig {
   int NPT, NRT, Q4, NSB, G, nstA, nstB, QS, BSTR, b_whole;
+  int PB = 1, RB = 1;   // row / column blocks of the output (P > 64 or R > 64); NPT, NRT are those of the largest block
   int sb_cta0[17], sb_tile0[17];
   unsigned char cta_sb[160], cta_sl[160];
   uint32_t slotA, slotB, ops_off, hasop_off, tab_off, vt_off, vtail_off, ring_off, total;
@@ -99,6 +100,7 @@ struct Stage3FConfig {
 };
 int stage3f_profile_read(unsigned long long* host);
 bool stage3f_configure(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, Stage3FConfig* cfg);
+bool stage3f_configure_block(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, Stage3FConfig* cfg);
 int stage3f_launch(const Stage3Plan* plan, const Stage3FConfig& k, int P, int Q, int R, int S, const cplx* v, cplx* partial,
                    cudaStream_t stream);
 

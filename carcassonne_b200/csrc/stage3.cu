@@ -578,6 +578,9 @@ void s3_choose(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, int 
                bool* can_fuse, bool* can_fold) {
   *can_fuse = force_path != 2 && force_path != 3 && Xmax > 0 && s3_configure(nterms, P, Q, R, S, d, Xmax, k);
   *can_fold = force_path != 2 && force_path != 1 && Xmax > 0 && stage3f_configure(nterms, P, Q, R, S, d, Xmax, kf);
+  // three column blocks (R > 128) repeat every first product three times: measured slower than the unfused GEMMs
+  // (D = 12: 107 vs 82 ms), so the automatic choice stops at two; force_path = 3 still runs it
+  if (*can_fold && force_path == 0 && kf->RB > 2) *can_fold = false;
   if (*can_fuse && *can_fold) {
     // Both tilings fit.  Take the one that issues fewer DMMA steps for this shape (complex 8x8x4 steps per x and product
     // pair).  At equal work (P, Q, S multiples of 8 / 16: D = 4, 8) the measured winner depends on the work per op: the
@@ -694,10 +697,11 @@ void stage3_plan_destroy(Stage3Plan* plan) {
 
 // FP64 flops the fused kernel actually issues on the tensor pipe (first products: one per term; second products:
 // one per group), for the roofline; the reference-equivalent count is 8 x cost_of_multiply.
-double stage3_executed_flops(const Stage3Plan* plan, int P, int Q, int R, int S, int d) {
+double stage3_executed_flops(const Stage3Plan* plan, int P, int Q, int R, int S, int d, int column_blocks) {
   double f = 0.0;
   for (const auto& gr : plan->groups) {
-    const double first = gr.kind ? 1.0 : (double)gr.count, second = gr.kind ? (double)gr.count : 1.0;
+    // every column block of the output (R > 64: stage3f.cu) repeats the first products
+    const double first = (gr.kind ? 1.0 : (double)gr.count) * column_blocks, second = gr.kind ? (double)gr.count : 1.0;
     f += 8.0 * (double)gr.X * (first * P * Q * S * d + second * P * R * S * d);
   }
   return f;

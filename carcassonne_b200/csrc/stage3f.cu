@@ -41,10 +41,10 @@ struct S3FParams {
   const Stage3Term* terms;  // device copy, sorted by group
   const Stage3Group* groups;
   int nterms, ngroups;
-  int P, Q, R, S;
+  int P, Q, R, S;                 // P, R: extents of the (row block, column block) of the output this launch computes
+  int Pfull, Rfull, p0, r0;       // the whole output is Pfull x Rfull; the block starts at row p0, column r0
   int Q4, NPT, G, NSB, nstA, nstB, QS, BSTR;
   int b_whole;                    // one S block: B_x is one contiguous copy, issued by the warps in turn
-  int skew_cycles;                // start-up delay per co-resident warp of an SM sub-partition (see the kernel)
   int sb_cta0[S3F_MAX_SB + 1];    // S block i has sb_cta0[i+1] - sb_cta0[i] CTAs (one X slab each)
   unsigned char cta_sb[160], cta_sl[160];   // CTA -> (S block, X slab): CTAs sharing a stretch of X are neighbours
   unsigned char cta_map[160];               // blockIdx.x of this launch -> CTA (launches are per S-block width)
@@ -110,19 +110,14 @@ __device__ __forceinline__ void s3f_first_step(CTile (&T)[NJ], int jbase, const 
   }
 }
 
-// T[jj] += A_x (8 rows of this warp) * Vt (tile jbase + jj), for the active tiles.  NP > 0: the number of paired k-steps
-// is known at compile time (NP = Q / 8 for the uniform bond dimensions) and the k loop is unrolled completely -- no loop
-// branch, and every operand load of the op is free to move ahead of the DMMAs before it.
-template <int NJ, int NA, int NP>
+// T[jj] += A_x (8 rows of this warp) * Vt (tile jbase + jj), for the active tiles.  (Measured and not adopted: a k loop
+// unrolled completely for the uniform bond dimensions -- ptxas hoists more loads than the register file holds and spills:
+// 27.98 vs 30.14 TFLOP/s at D = 8, 17.99 vs 19.46 at D = 7.)
+template <int NJ, int NA>
 __device__ __forceinline__ void s3f_first(CTile (&T)[NJ], int jbase, const S3FLane& L, uint32_t slot) {
   const uint32_t a_base = slot + L.a_pair;
-  if (NP > 0) {
-#pragma unroll
-    for (int kp = 0; kp < NP; ++kp) s3f_first_step<NJ, NA>(T, jbase, L, a_base, kp);
-  } else {
 #pragma unroll 2
-    for (int kp = 0; kp < L.npairs; ++kp) s3f_first_step<NJ, NA>(T, jbase, L, a_base, kp);
-  }
+  for (int kp = 0; kp < L.npairs; ++kp) s3f_first_step<NJ, NA>(T, jbase, L, a_base, kp);
   if (L.tail) {
     const cplx a = lds_c(slot + L.a_tail);
 #pragma unroll
@@ -175,8 +170,7 @@ __device__ __forceinline__ void s3f_second(CTile (&acc)[NRT][2], const CTile& W,
 
 // NA: number of tiles the S blocks of THIS launch hold (NT or NT - 1: an uneven split of S gives blocks of both widths
 // and one launch per width), or 0 for "read it at run time" (see s3f_active).
-// NP: number of paired k-steps of the first product when it is a compile-time constant for this launch, else 0.
-template <int NRT, int NT, int NA, int NP>
+template <int NRT, int NT, int NA>
 __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const S3FParams p) {
   const int cta = p.cta_map[blockIdx.x];   // position in the whole job's CTA table (slab, S block, partial slot)
   constexpr int DP = 2;
@@ -321,7 +315,7 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
         // the slot was read by this warp's own lanes (all past the __syncwarp that follows every first product)
         fence_proxy_async();
         mbar_arrive_expect_tx(bA + sa * 8, a_bytes);
-        bulk_g2s(ringA + sa * p.slotA_bytes, A + ((int64_t)cu.x * p.P + 8 * wg) * p.Q, a_bytes, bA + sa * 8);
+        bulk_g2s(ringA + sa * p.slotA_bytes, A + ((int64_t)cu.x * p.Pfull + p.p0 + 8 * wg) * p.Q, a_bytes, bA + sa * 8);
       }
     };
     auto issueB = [&](const Cursor& cu) {
@@ -341,7 +335,7 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
         if (my_turn && lane == 0) {
           mbar_wait(fullB + 8, empty_parity);
           mbar_arrive_expect_tx(fullB, (uint32_t)(p.R * p.S * 16));
-          bulk_g2s(dst, B + (int64_t)cu.x * p.R * p.S, (uint32_t)(p.R * p.S * 16), fullB);
+          bulk_g2s(dst, B + ((int64_t)cu.x * p.Rfull + p.r0) * p.S, (uint32_t)(p.R * p.S * 16), fullB);
         }
         return;
       }
@@ -351,7 +345,7 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
         else mbar_arrive(fullB);
       }
       __syncwarp();
-      const cplx* src = B + ((int64_t)cu.x * p.R) * p.S + S0;
+      const cplx* src = B + ((int64_t)cu.x * p.Rfull + p.r0) * p.S + S0;
       for (int rr = wg + p.NPT * lane; rr < p.R; rr += 32 * p.NPT)
         bulk_g2s(dst + rr * BSTR * 16, src + (int64_t)rr * p.S, b_row_bytes, fullB);
     };
@@ -359,16 +353,9 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
     Cursor cc = {-1, 0, 0, 0}, pc = {-1, 0, 0, 0};
     uint32_t issuedA = 0, issuedB = 0, itA = 0, itB = 0;
     bool more = true, pending = false;
-    // Warps w, w + 4, w + 8 share an SM sub-partition and with it one DMMA pipe.  They run the same op sequence, and
-    // started together they stay phase-locked: both reach the stretch between two ops (cursor, copies, site operator,
-    // accumulator shuffling -- no DMMA for ~1500 cycles) at the same time and the pipe idles.  Starting each co-resident
-    // warp a fraction of an op later keeps one warp's bookkeeping under the other's DMMAs; the offset is stable because
-    // a warp that has the pipe to itself runs at twice the shared rate for exactly the other's bookkeeping time.
-    if (p.skew_cycles > 0 && (warp >> 2) > 0) {
-      const long long t_skew = clock64() + (long long)(warp >> 2) * p.skew_cycles;
-      while (clock64() < t_skew) {
-      }
-    }
+    // (Measured and not adopted: starting the warps that share an SM sub-partition a fraction of an op apart, so that one
+    // warp's bookkeeping between two ops falls under the other's DMMAs -- no change at D = 4, 6, 8, before and after the
+    // tile loops lost their predicates: the idle DMMA slots are not a phase-locking effect.)
     auto run_ahead = [&]() {
       while (more) {
         if (!pending) {
@@ -401,7 +388,7 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
         S3F_WAIT(0, bA + slot * 8, cA_par);
 #pragma unroll
         for (int j = 0; j < NT; ++j) T[j].zero();
-        s3f_first<NT, NA, NP>(T, 0, L, ringA + slot * p.slotA_bytes);
+        s3f_first<NT, NA>(T, 0, L, ringA + slot * p.slotA_bytes);
         if (has_op) {
 #pragma unroll
           for (int j = 0; j < NT; ++j) {
@@ -429,7 +416,7 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
           S3F_WAIT(1, bA + slot * 8, cA_par);
           const uint32_t aslot = ringA + slot * p.slotA_bytes;
           if (!has_op) {
-            s3f_first<NT, NA, NP>(T, 0, L, aslot);
+            s3f_first<NT, NA>(T, 0, L, aslot);
           } else {
 #pragma unroll
             for (int j0 = 0; j0 < NT; j0 += UW) {
@@ -437,7 +424,7 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
                 CTile U[UW];
 #pragma unroll
                 for (int jj = 0; jj < UW; ++jj) U[jj].zero();
-                s3f_first<UW, NA, NP>(U, j0, L, aslot);
+                s3f_first<UW, NA>(U, j0, L, aslot);
 #pragma unroll
                 for (int jj = 0; jj < UW; ++jj)
                   if (j0 + jj < NT && (NA == 0 || j0 + jj < NA)) s3f_apply_op(T[j0 + jj], U[jj], ops + term * DP * DP);
@@ -510,7 +497,7 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
     }
 #endif
     // ---- partial result of this (CTA, group)
-    cplx* part = p.partial + ((int64_t)cta * p.G + g) * ((int64_t)p.P * p.R * DP);
+    cplx* part = p.partial + ((int64_t)cta * p.G + g) * ((int64_t)p.Pfull * p.Rfull * DP);
     const int row = wg * 8 + r;
     if (row < p.P) {
 #pragma unroll
@@ -524,7 +511,7 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
               cplx val;
               val.x = h ? acc[rt][s].re1 : acc[rt][s].re0;
               val.y = h ? acc[rt][s].im1 : acc[rt][s].im0;
-              part[((int64_t)row * p.R + col) * DP + s] = val;
+              part[((int64_t)(p.p0 + row) * p.Rfull + p.r0 + col) * DP + s] = val;
             }
           }
         }
@@ -533,31 +520,19 @@ __global__ void __launch_bounds__(s3f_max_threads(NRT), 1) stage3f_kernel(const 
   }
 }
 
-template <int NRT, int NA, int NP>
-int s3f_launch_np(const S3FParams& p, int ctas, int threads, cudaStream_t stream) {
+template <int NRT, int NA>
+int s3f_launch_one(const S3FParams& p, int ctas, int threads, cudaStream_t stream) {
   static bool configured[16] = {false};
   int dev = 0;
   CARC_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev < 16 && !configured[dev]) {
-    CARC_CHECK_CUDA(cudaFuncSetAttribute(stage3f_kernel<NRT, s3f_tiles(NRT), NA, NP>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, S3F_SMEM_LIMIT));
+    CARC_CHECK_CUDA(cudaFuncSetAttribute(stage3f_kernel<NRT, s3f_tiles(NRT), NA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         S3F_SMEM_LIMIT));
     configured[dev] = true;
   }
-  stage3f_kernel<NRT, s3f_tiles(NRT), NA, NP><<<ctas, threads, p.smem_total, stream>>>(p);
+  stage3f_kernel<NRT, s3f_tiles(NRT), NA><<<ctas, threads, p.smem_total, stream>>>(p);
   CARC_CHECK_CUDA(cudaGetLastError());
   return CARC_OK;
-}
-
-// Paired k-steps of the first product at the uniform bond dimension whose R = D^2 gives NRT row tiles (Q = D^2 as well):
-// D = 8: 8, D = 7: 6, D = 6: 4, D = 5: 3, D = 4: 2; 0 = no such D (those shapes keep the run-time loop).
-constexpr int s3f_uniform_pairs(int nrt) { return nrt == 8 ? 8 : nrt == 7 ? 6 : nrt == 5 ? 4 : nrt == 4 ? 3 : nrt == 2 ? 2 : 0; }
-
-template <int NRT, int NA>
-int s3f_launch_one(const S3FParams& p, int ctas, int threads, cudaStream_t stream) {
-  constexpr int NP = s3f_uniform_pairs(NRT);
-  static const bool unrolled = !(getenv("CARC_S3F_NP") && atoi(getenv("CARC_S3F_NP")) == 0);   // experiments
-  if (unrolled && NP > 0 && (p.Q4 >> 1) == NP) return s3f_launch_np<NRT, NA, NP>(p, ctas, threads, stream);
-  return s3f_launch_np<NRT, NA, 0>(p, ctas, threads, stream);
 }
 
 // A second stream per device, so that the launches of one apply (one per S-block width, together one CTA per SM) run
@@ -639,10 +614,57 @@ int stage3f_profile_read(unsigned long long* host) {
 bool stage3f_configure(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, Stage3FConfig* cfg) {
   if (d != 2) return false;
   if (Xmax >= (1ll << 31) || Xmax < 1) return false;
-  if (P > 64 || R > 64 || P < 1 || R < 1 || Q < 1 || S < 1) return false;
-  Stage3FConfig k;
-  k.NPT = (P + 7) / 8;
-  k.NRT = (R + 7) / 8;
+  if (P < 1 || R < 1 || Q < 1 || S < 1) return false;
+  // Outputs wider than the 64 columns a warp can accumulate (8 row tiles x 2 spins of register tiles) or taller than the
+  // CTA's warps and shared memory can stage are computed block by block: RB column blocks x PB row blocks, one set of
+  // launches each, all writing their part of the same partial-sum slots.  Row blocks cost nothing extra in arithmetic
+  // (rows are independent; B_x is streamed once per row block); every column block repeats the first products.
+  // Among the row-block counts that fit, take the one that loads the four DMMA pipes of an SM most evenly: a block of
+  // NPT_b row tiles runs as G groups of NPT_b warps, warp w on sub-partition w % 4, so per environment index the busiest
+  // sub-partition issues ceil(G NPT_b / 4) / G tile-ops.  (D = 6: one block of 5 row tiles = 10 warps as 3 + 3 + 2 + 2
+  // -> 1.5; blocks of 3 + 2 row tiles = 12 and 8 warps, both even -> 1.25: 18.3 -> 19.6 TFLOP/s.)  Each extra block
+  // re-streams B_x once more.
+  const int rt_all = (R + 7) / 8, pt_all = (P + 7) / 8;
+  static const int forced_pb = getenv("CARC_S3F_PB") ? atoi(getenv("CARC_S3F_PB")) : 0;     // experiments
+  for (int RB = (rt_all + 7) / 8; RB <= rt_all && RB <= 4; ++RB) {
+    bool found = false;
+    double best = 0.0;
+    int feasible = 0;
+    for (int PB = 1; PB <= pt_all && PB <= 8 && feasible < 3; ++PB) {
+      Stage3FConfig k;
+      k.RB = RB;
+      k.PB = PB;
+      if (!stage3f_configure_block(nterms, P, Q, R, S, d, Xmax, &k)) continue;
+      ++feasible;
+      // per block: warps on the busiest sub-partition / G, divided by how well that many co-resident warps keep the pipe
+      // fed (measured: one warp alone ~0.6, two ~0.85, three ~0.95 of what the pipe can take)
+      static const double fed[4] = {1.0, 0.6, 0.85, 0.95};
+      double cost = 0.03 * PB;
+      for (int pb = 0; pb < PB; ++pb) {
+        const int tiles = std::min(k.NPT, pt_all - pb * k.NPT);
+        if (tiles <= 0) continue;
+        const int busiest = (k.G * tiles + 3) / 4;
+        cost += (double)busiest / fed[std::min(busiest, 3)] / k.G;
+      }
+      if (forced_pb > 0) cost = PB == forced_pb ? 0.0 : 1e9 + PB;
+      if (!found || cost < best - 1e-9) {
+        found = true;
+        best = cost;
+        *cfg = k;
+      }
+    }
+    if (found) return true;
+  }
+  return false;
+}
+
+// Launch geometry for the block counts k->PB, k->RB; false when a block does not fit the kernel.
+bool stage3f_configure_block(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, Stage3FConfig* cfg) {
+  Stage3FConfig k = *cfg;
+  const int rt_all = (R + 7) / 8, pt_all = (P + 7) / 8;
+  k.NPT = (pt_all + k.PB - 1) / k.PB;      // row tiles of the tallest block
+  k.NRT = (rt_all + k.RB - 1) / k.RB;      // column tiles of the widest block
+  if (k.NRT > 8) return false;
   k.Q4 = (Q + 3) / 4;
   const int ntt = (S + 3) / 4;
   const int ntmax = s3f_tiles(k.NRT);
@@ -728,7 +750,7 @@ bool stage3f_configure(int nterms, int P, int Q, int R, int S, int d, int64_t Xm
           }
         }
         // DMMA work per x and product pair, in complex 8x8x4 steps, for the choice between the two kernels
-        k.padded_work = (double)k.NPT * ntt * ((double)k.Q4 + 2.0 * k.NRT);
+        k.padded_work = (double)k.NPT * k.PB * ntt * ((double)k.Q4 * k.RB + 2.0 * k.NRT * k.RB);
         *cfg = k;
         return true;
       }
@@ -745,17 +767,9 @@ int stage3f_launch(const Stage3Plan* plan, const Stage3FConfig& k, int P, int Q,
   p.nterms = (int)plan->terms.size();
   p.ngroups = (int)plan->groups.size();
   p.P = P; p.Q = Q; p.R = R; p.S = S;
+  p.Pfull = P; p.Rfull = R; p.p0 = 0; p.r0 = 0;
   p.Q4 = k.Q4; p.NPT = k.NPT; p.G = k.G; p.NSB = k.NSB; p.nstA = k.nstA; p.nstB = k.nstB; p.QS = k.QS; p.BSTR = k.BSTR;
   p.b_whole = k.b_whole;
-  {
-    // one op of a warp is NT * Q4 complex k-steps = 4 NT Q4 DMMAs of 16 pipe cycles; with n warps per sub-partition an op
-    // takes n times that, and the i-th of them starts i / n of it late
-    const int per_sp = (k.threads / 32 + 3) / 4;
-    const int nt = k.sb_tile0[1] - k.sb_tile0[0];
-    static const char* env = getenv("CARC_S3F_SKEW");     // experiments: 0 disables, other values scale (percent)
-    const int pct = env ? atoi(env) : 100;
-    p.skew_cycles = per_sp > 1 ? (int)((int64_t)4 * nt * k.Q4 * 16 * pct / 100) : 0;
-  }
   for (int i = 0; i <= S3F_MAX_SB; ++i) {
     p.sb_cta0[i] = i <= k.NSB ? k.sb_cta0[i] : 0;
     p.sb_tile0[i] = i <= k.NSB ? k.sb_tile0[i] : 0;
@@ -770,16 +784,32 @@ int stage3f_launch(const Stage3Plan* plan, const Stage3FConfig& k, int P, int Q,
   p.v = v;
   p.partial = partial;
   for (int c = 0; c < 160; ++c) p.cta_map[c] = 0;
-  switch (k.NRT) {
-    case 1: return s3f_launch<1>(p, k, stream);
-    case 2: return s3f_launch<2>(p, k, stream);
-    case 3: return s3f_launch<3>(p, k, stream);
-    case 4: return s3f_launch<4>(p, k, stream);
-    case 5: return s3f_launch<5>(p, k, stream);
-    case 6: return s3f_launch<6>(p, k, stream);
-    case 7: return s3f_launch<7>(p, k, stream);
-    default: return s3f_launch<8>(p, k, stream);
+  for (int pb = 0; pb < k.PB; ++pb) {
+    for (int rb = 0; rb < k.RB; ++rb) {
+      p.p0 = pb * 8 * k.NPT;
+      p.r0 = rb * 8 * k.NRT;
+      p.P = std::min(8 * k.NPT, P - p.p0);
+      p.R = std::min(8 * k.NRT, R - p.r0);
+      if (p.P <= 0 || p.R <= 0) continue;
+      Stage3FConfig kb = k;            // same groups, S blocks, slabs and rings; only the warps of this block's row tiles
+      kb.NPT = (p.P + 7) / 8;
+      kb.threads = k.G * kb.NPT * 32;
+      p.NPT = kb.NPT;
+      int rc;
+      switch (k.NRT) {
+        case 1: rc = s3f_launch<1>(p, kb, stream); break;
+        case 2: rc = s3f_launch<2>(p, kb, stream); break;
+        case 3: rc = s3f_launch<3>(p, kb, stream); break;
+        case 4: rc = s3f_launch<4>(p, kb, stream); break;
+        case 5: rc = s3f_launch<5>(p, kb, stream); break;
+        case 6: rc = s3f_launch<6>(p, kb, stream); break;
+        case 7: rc = s3f_launch<7>(p, kb, stream); break;
+        default: rc = s3f_launch<8>(p, kb, stream); break;
+      }
+      if (rc) return rc;
+    }
   }
+  return CARC_OK;
 }
 
 }  // namespace carc

@@ -137,8 +137,9 @@ int carc_operator_path(const carc_operator* op);
 int carc_stage3f_profile_read(unsigned long long* host);
 /* Host-side launch plan of the folded fused kernel for one shape (no device call): out = {NPT, NRT, Q4, NSB, G, nstA,
  * nstB, QS, BSTR, b_whole, threads, ctas, slots, smem bytes, A slot bytes, B slot bytes}, then sb_tile0[17], sb_cta0[17],
- * cta_sb[160], cta_sl[160] (-1 beyond the used entries); CARC_ERR_UNSUPPORTED outside the kernel's envelope.  What the
- * CPU test suite checks the work partition with. */
+ * cta_sb[160], cta_sl[160] (-1 beyond the used entries) and, when out_len >= 372, {PB, RB}: the output is computed in
+ * PB row blocks x RB column blocks (P or R > 64; NPT / NRT / threads are then those of the largest block);
+ * CARC_ERR_UNSUPPORTED outside the kernel's envelope.  What the CPU test suite checks the work partition with. */
 /* Which device path a stage-3 operator of this shape takes (host-side decision, no device call): 1 fused kernel,
  * 3 fused kernel with the folded tiling, 2 unfused GEMMs; force_path as in carc_operator_set_path. */
 int carc_stage3_path(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, int force_path);

@@ -220,6 +220,30 @@ def test_stage3_operator(dd, chi2, D, terms, path):
     assert relerr(out2, (2 + 1j) * ref) < MATVEC_TOL
 
 
+@pytest.mark.parametrize("chi2,dims,terms", [(2, (9, 9, 9, 9), 2), (2, (10, 10, 10, 10), 3), (2, (11, 11, 11, 11), 1),
+                                             (2, (12, 12, 12, 12), 2), (3, (9, 8, 5, 11), 2), (2, (3, 30, 2, 40), 2),
+                                             (3, (12, 12, 4, 4), 2), (2, (5, 5, 10, 13), 3)])
+@pytest.mark.parametrize("path", [0, 2, 3])
+def test_stage3_large_bond_dimensions(dd, chi2, dims, terms, path):
+    """Outputs beyond the 64 x 64 a single launch of the fused kernel covers (D = 9 .. 12, ragged bonds): computed in
+    row / column blocks of the output; the reference's recipe (tensors/_2d/dense.py:115-160) has no such limit.  The
+    automatic choice must be the fused kernel."""
+    from carcassonne_b200.operator import Stage3Operator, prejoin_halves
+    rng = np.random.default_rng(chi2 * 1000 + sum(dims) * 10 + terms)
+    s2_0, s2_1, ops, v, ref = _stage3_case(rng, chi2, None, terms=terms, dims=dims)
+    op = Stage3Operator(v.shape)
+    for a, b, o in zip(s2_0, s2_1, ops):
+        A, B = prejoin_halves(dd.fromArray(a), dd.fromArray(b))
+        op.add_term(A, B, o)
+    op.finalize().set_path(path)
+    if path == 0:      # fused up to two column blocks of the output (R <= 128); beyond, the unfused GEMMs are faster
+        assert op.path == (3 if dims[2] * dims[3] <= 128 else 2)
+    out = op(dd.fromArray(v)).toArray()
+    assert relerr(out, ref) < MATVEC_TOL
+    out2 = op(dd.fromArray((2 + 1j) * v)).toArray()
+    assert relerr(out2, (2 + 1j) * ref) < MATVEC_TOL
+
+
 @pytest.mark.parametrize("dims,d", [((2, 3, 3, 2), 2), ((1, 1, 1, 1), 2), ((3, 2, 2, 4), 3), ((2, 2, 2, 2), 1),
                                      ((4, 4, 2, 2), 2), ((2, 2, 8, 8), 2), ((3, 5, 7, 1), 2), ((7, 7, 5, 3), 2),
                                      ((1, 5, 6, 6), 2)])

@@ -12,7 +12,7 @@ SMEM_LIMIT = 227 * 1024
 
 
 def describe(P, Q, R, S, X, nterms=9):
-    buf = np.full(16 + 17 + 17 + 160 + 160, -7, dtype=np.int32)
+    buf = np.full(16 + 17 + 17 + 160 + 160 + 2, -7, dtype=np.int32)
     rc = _lib.lib.carc_stage3f_describe(nterms, P, Q, R, S, 2, X, buf.ctypes.data, len(buf))
     if rc == _lib.ERR_UNSUPPORTED:
         return None
@@ -24,6 +24,7 @@ def describe(P, Q, R, S, X, nterms=9):
     k["sb_cta0"] = buf[33:50]
     k["cta_sb"] = buf[50:210]
     k["cta_sl"] = buf[210:370]
+    k["PB"], k["RB"] = int(buf[370]), int(buf[371])
     return k
 
 
@@ -34,7 +35,9 @@ def check_plan(P, Q, R, S, X):
     assert 1 <= k["ctas"] <= 148 and k["slots"] == k["ctas"] * k["G"]
     assert k["threads"] == 32 * k["G"] * k["NPT"] and k["threads"] <= (256 if k["NRT"] >= 7 else 384)
     assert k["smem"] <= SMEM_LIMIT
-    assert k["NPT"] == -(-P // 8) and k["NRT"] == -(-R // 8) and k["Q4"] == -(-Q // 4)
+    # the output in PB x RB blocks of at most NPT x NRT tiles (one block when P, R <= 64)
+    assert k["NPT"] == -(-(-(-P // 8)) // k["PB"]) and k["NRT"] == -(-(-(-R // 8)) // k["RB"]) and k["Q4"] == -(-Q // 4)
+    assert k["NRT"] <= 8 and (k["PB"], k["RB"]) == (1, 1) or P > 64 or R > 64 or k["PB"] >= 1
     # strides that keep the fragment loads conflict-free, and room for the copies
     assert k["QS"] % 8 == 1 and k["QS"] >= 8 * (k["Q4"] // 2)
     nsb = k["NSB"]
@@ -76,8 +79,13 @@ def test_ragged_shapes_and_envelope():
         P, R = int(rng.integers(1, 65)), int(rng.integers(1, 65))
         X = int(rng.integers(1, 5000))
         check_plan(P, P, R, R, X)
-    assert describe(65, 65, 8, 8, 100) is None        # more than 8 row tiles: the unfused path takes over
-    assert describe(8, 8, 72, 72, 100) is None
+    # beyond 64 rows / columns the output is computed in blocks (round 2); the plan of every block obeys the same rules
+    for P, R in ((65, 8), (8, 72), (81, 81), (100, 100), (121, 121), (144, 144), (90, 80), (72, 55)):
+        k = check_plan(P, P, R, R, 700)
+        assert k["PB"] * 8 * k["NPT"] >= P and k["RB"] * 8 * k["NRT"] >= R
+        assert k["RB"] > 1 or R <= 64
+        assert k["PB"] > 1 or P <= 96                  # up to 12 warps (96 rows) fit one block when R is narrow
+    assert describe(8, 8, 8, 8, 100, nterms=9)["PB"] == 1
 
 
 def test_block_shares_follow_the_tile_counts():
@@ -101,5 +109,6 @@ def test_which_tiling_runs():
     assert [path(D) for D in (2, 3, 4, 5, 6, 7, 8)] == [3, 3, 3, 3, 3, 3, 3]
     assert path(4, force=3) == 3 and path(8, force=1) == 1 and path(6, force=2) == 2
     assert path(3, d=3) == 2                      # both fused kernels are specific to d = 2
-    assert path(9) == 2                           # 81 rows: more than 8 row tiles
+    # row / column blocks of the output (round 2); beyond two column blocks the unfused GEMMs are faster (measured)
+    assert [path(D, X=4096) for D in (9, 10, 11, 12)] == [3, 3, 3, 2] and path(12, X=4096, force=3) == 3
     assert path(5, X=1) == 3
