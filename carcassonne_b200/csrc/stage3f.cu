@@ -750,7 +750,7 @@ bool stage3f_configure_block(int nterms, int P, int Q, int R, int S, int d, int6
           }
         }
         // DMMA work per x and product pair, in complex 8x8x4 steps, for the choice between the two kernels
-        k.padded_work = (double)k.NPT * k.PB * ntt * ((double)k.Q4 * k.RB + 2.0 * k.NRT * k.RB);
+        k.padded_work = (double)pt_all * ntt * ((double)k.Q4 * k.RB + 2.0 * k.NRT * k.RB);
         *cfg = k;
         return true;
       }
