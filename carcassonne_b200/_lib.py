@@ -82,6 +82,14 @@ SIGNATURES = {
     "carc_stage3_path": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_i64, c_int]),
     "carc_stage3_describe_stars": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "carc_stage3f_describe": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_i64, c_vp, c_int]),
+    "carc_absorb_side_into_corner": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp]),
+    "carc_double_layer_center": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "carc_absorb_center_into_side": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "carc_form_stage1": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "carc_form_stage2": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp]),
+    "carc_normalize_axis": (c_int, [c_vp, c_vp, c_int, c_int, c_int, C.c_double, c_vp, c_vp, c_vp, c_vp]),
+    "carc_product_compressor": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_int, C.c_double, c_vp, c_vp, c_vp,
+                                        c_vp]),
     "carc_operator_num_terms": (c_int, [c_vp]),
     "carc_operator_cost_of_multiply": (c_i64, [c_vp]),
     "carc_operator_destroy": (c_int, [c_vp]),

@@ -21,6 +21,11 @@ from .data import DeviceData, _empty, _ptr, _stream, gemm, gemm_hermitian, gemm_
 from .utils import LUFactors, SolverDidNotConverge, _DenseOperator
 
 
+# True: run the Gram-form ALS round by round from Python (the pre-round-2 path, kept as the cross-check of
+# carc_product_compressor in tests/test_gpu_system.py)
+_PYTHON_ALS = False
+
+
 def _gmres_dense(matrix, rhs, rtol=1e-5, restart=20, maxiter=None):
     """x = matrix^-1 rhs by GMRES from x0 = 0 (scipy.sparse.linalg.gmres defaults)."""
     n = matrix.shape[0]
@@ -189,12 +194,20 @@ def computeProductCompressor(L, R, new_dimension, initial=None, sweeps=4, regula
     old_dimension = L.shape[1]
     if initial is None:
         initial = DeviceData.newRandom(old_dimension, new_dimension)
-    compressor = initial.unitize()
     if new_dimension == old_dimension:
         # every unitary preserves the product exactly: the starting point already is a global minimiser of the
         # ALS objective (the reference still runs its four rounds and lands on some other unitary)
-        return compressor.transpose()
+        return initial.unitize().transpose()
     m = old_dimension * new_dimension
+    if L.shape[3] == 1 and new_dimension <= 80 and not _PYTHON_ALS:
+        # the whole fit in one library call (csrc/recipes.cu: carc_product_compressor): Gram form, no host round trip
+        out = _empty((new_dimension, old_dimension))
+        check(lib.carc_product_compressor(
+            _ptr(L._t), L.shape[0], _ptr(R._t), R.shape[3], old_dimension, new_dimension, _ptr(initial._t), int(sweeps),
+            float(regularization), _ptr(left_gram._t) if left_gram is not None else None,
+            _ptr(right_gram._t) if right_gram is not None else None, _ptr(out), _stream()))
+        return DeviceData(out)
+    compressor = initial.unitize()
     if L.shape[3] == 1:
         form = _GramForm(L, R, left_gram, right_gram)
     else:

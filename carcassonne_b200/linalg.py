@@ -98,23 +98,20 @@ def normalize_axis(t, axis, sqrt_svals=False, dont_recip_under=1e-14):
             n = np.sqrt(n)
             return DeviceData.fromArray(np.array([[1 / n]])), DeviceData.fromArray(np.array([[n]]))
         return t * (1.0 / n), DeviceData.fromArray(np.array([[1 / n]])), DeviceData.fromArray(np.array([[n]]))
-    others = [i for i in range(t.ndim) if i != axis]
-    M = t.join(others, axis)
-    m, n = M.shape
+    n = t.shape[axis]
+    m = t.size() // n
     if m < n:
         raise ValueError("the total number of degrees of freedom in all other axes ({}) are not enough to normalize "
                          "axis ({}) with dimension ({})".format(m, axis, n))
-    Q, U_R, S, Vh = _svd_tall(M)
-    polar, nrm, den, nrm_sqrt, den_sqrt = _normalizer_pieces(U_R, S, Vh, n, dont_recip_under)
+    if n > MAX_SMALL:
+        raise NotImplementedError("device SVD supports at most {} columns (got {})".format(MAX_SMALL, n))
+    # one library call: permute to [(others), axis], Householder QR, Jacobi SVD of R, normaliser pieces and the isometric
+    # tensor Q (U V^H) written with the normalised axis already back in place (csrc/recipes.cu: carc_normalize_axis)
+    shape = (C.c_int64 * t.ndim)(*t.shape)
+    nrm, den = _empty((n, n)), _empty((n, n))
+    iso = None if sqrt_svals else _empty(t.shape)
+    check(lib.carc_normalize_axis(_ptr(t._t), shape, t.ndim, axis, int(bool(sqrt_svals)), float(dont_recip_under or 0.0),
+                                  _ptr(iso) if iso is not None else None, _ptr(nrm), _ptr(den), _stream()))
     if sqrt_svals:
-        return DeviceData(nrm_sqrt), DeviceData(den_sqrt)
-    # isometric tensor = Q . polar, written with the normalised axis already back in place
-    shape = t.shape
-    post = 1
-    for s in shape[axis + 1:]:
-        post *= s
-    pre = m // post if post else 0
-    iso = _empty(shape)
-    # rows of M are (pre, post); column j goes to position `axis`:  offset = pre*(n*post) + j*post + post_idx
-    gemm(_lib.OP_N, _lib.OP_N, m, n, n, Q, n, polar, n, iso, out_map=(max(post, 1), n * post, 1, n, 0, post))
+        return DeviceData(nrm), DeviceData(den)
     return DeviceData(iso), DeviceData(nrm), DeviceData(den)

@@ -89,6 +89,10 @@ class CompressionPolicy(Policy):
 
 class ConstantStateCompressionPolicy(CompressionPolicy):
     def __init__(self, new_dimension):
+        from .linalg import MAX_SMALL
+        if new_dimension > MAX_SMALL:     # the polar projection of the compressor is a device SVD of `new` columns
+            raise NotImplementedError("state compression to {} exceeds the device SVD limit of {} columns".format(
+                new_dimension, MAX_SMALL))
         self.new_dimension = new_dimension
 
     def apply(self):

@@ -124,6 +124,12 @@ class BaseSystem:
                 raise ValueError("New dimension must be less than the physical dimension times the old dimension "
                                  "({} > {}*{}).".format(new_dimension, physical_dimension, old_dimension))
             new_dimension = limit
+        # fail BEFORE anything is mutated: the device SVD behind normalizeAxis handles bonds up to linalg.MAX_SMALL
+        from ..linalg import MAX_SMALL
+        if new_dimension > MAX_SMALL:
+            raise NotImplementedError(
+                "bond dimension {} exceeds the device SVD limit of {} columns (carc_svd_small); the system has not been "
+                "changed".format(new_dimension, MAX_SMALL))
 
         towards_opposite = center.normalizeAxis(opposite)[0]
         towards_axis = center.normalizeAxis(axis)[0]

@@ -14,8 +14,11 @@ from math import prod
 
 import numpy as np
 
+import ctypes as C
+
 from ... import _lib as _la
-from ...data import DeviceData, _empty, gemm, gemm_scatter
+from ..._lib import check, lib
+from ...data import DeviceData, _empty, _ptr, _stream, gemm, gemm_scatter
 from ...utils import DimensionMismatchError, L, Multiplier, O, R, UnexpectedTensorRankError
 
 OP_N, OP_T, OP_C, OP_J = _la.OP_N, _la.OP_T, _la.OP_C, _la.OP_J
@@ -41,6 +44,12 @@ def _target(shape, accumulate_into):
     return accumulate_into._t, 1.0
 
 
+def _shape(t):
+    """int64[] of a tensor's shape for the one-call-per-recipe entry points of the C ABI."""
+    shape = t if isinstance(t, (tuple, list)) else t.shape
+    return (C.c_int64 * len(shape))(*shape)
+
+
 def _row_major_strides(dims):
     strides, acc = [], 1
     for d in reversed(dims):
@@ -56,14 +65,12 @@ def absorbDenseSideIntoCornerFromLeft(corner, side, accumulate_into=None):
     for a in range(3):
         _check_bond(0, a, corner, 1, 3 + a, side)
     c, s = corner.shape, side.shape
-    K = c[0] * c[1] * c[2]
     out_shape = (s[0], s[1], s[2], c[3] * s[6], c[4] * s[7], c[5])
     out, beta = _target(out_shape, accumulate_into)
-    # per leading side index b = (s0 s1 s2):  C_b[(c3 c4 c5), (s6 s7)] = corner[K, (c3 c4 c5)]^T . side_b[K, (s6 s7)]
-    st = _row_major_strides((c[3], s[6], c[4], s[7], c[5]))
-    gemm_scatter(OP_T, OP_N, c[3] * c[4] * c[5], s[6] * s[7], K, corner._t, c[3] * c[4] * c[5], side._t, s[6] * s[7],
-                 out, ((c[3], st[0]), (c[4], st[2]), (c[5], st[4])), ((s[6], st[1]), (s[7], st[3])), beta=beta,
-                 batch=s[0] * s[1] * s[2], strideB=K * s[6] * s[7], strideC=prod(out_shape[3:]))
+    # per leading side index b = (s0 s1 s2):  C_b[(c3 c4 c5), (s6 s7)] = corner[K, (c3 c4 c5)]^T . side_b[K, (s6 s7)],
+    # scattered into the joined layout by the GEMM epilogue (csrc/recipes.cu)
+    check(lib.carc_absorb_side_into_corner(_ptr(corner._t), _shape(corner), _ptr(side._t), _shape(side), 1, _ptr(out),
+                                           int(beta != 0.0), _stream()))
     return accumulate_into if accumulate_into is not None else DeviceData(out)
 
 
@@ -73,13 +80,10 @@ def absorbDenseSideIntoCornerFromRight(corner, side, accumulate_into=None):
     for a in range(3):
         _check_bond(0, 3 + a, corner, 1, a, side)
     c, s = corner.shape, side.shape
-    K = c[3] * c[4] * c[5]
-    t345 = s[3] * s[4] * s[5]
     out_shape = (c[0] * s[6], c[1] * s[7], c[2], s[3], s[4], s[5])
     out, beta = _target(out_shape, accumulate_into)
-    st = _row_major_strides((c[0], s[6], c[1], s[7], c[2], t345))
-    gemm_scatter(OP_N, OP_N, c[0] * c[1] * c[2], t345 * s[6] * s[7], K, corner._t, K, side._t, t345 * s[6] * s[7], out,
-                 ((c[0], st[0]), (c[1], st[2]), (c[2], st[4])), ((t345, st[5]), (s[6], st[1]), (s[7], st[3])), beta=beta)
+    check(lib.carc_absorb_side_into_corner(_ptr(corner._t), _shape(corner), _ptr(side._t), _shape(side), 0, _ptr(out),
+                                           int(beta != 0.0), _stream()))
     return accumulate_into if accumulate_into is not None else DeviceData(out)
 
 
@@ -93,22 +97,18 @@ def _double_layer(direction, center, center_conj, operator):
     if n[4] != m[4]:
         raise DimensionMismatchError(1, 4, n[4], 2, 4, m[4])
     d = n[4]
-    v = center
     if operator is not None:
         if operator.ndim != 2:
             raise UnexpectedTensorRankError(3, 2, operator.ndim)
         if operator.shape != (d, d):
             raise DimensionMismatchError(3, 1, operator.shape[1], 1, 4, d)
-        vo = _empty(n)
-        gemm(OP_N, OP_T, prod(n[:4]), d, d, center._t, d, operator._t, d, vo)     # vo[.., z] = sum_s v[.., s] O[z, s]
-        v = DeviceData(vo)
     i, l, r, o = direction, L(direction), R(direction), O(direction)
     dims = (n[i], m[i], n[l], m[l], n[r], m[r], n[o], m[o])
-    st = _row_major_strides(dims)
-    role = {i: 0, l: 2, r: 4, o: 6}
     E = _empty((n[i] * m[i], prod(dims[2:])))
-    gemm_scatter(OP_N, OP_T, prod(n[:4]), prod(m[:4]), d, v._t, d, center_conj._t, d, E,
-                 tuple((n[a], st[role[a]]) for a in range(4)), tuple((m[a], st[role[a] + 1]) for a in range(4)))
+    # vo[.., z] = sum_s v[.., s] O[z, s], then a K = d product scattered into [(g h), (vL wL vR wR vO wO)]: one call
+    check(lib.carc_double_layer_center(direction, _ptr(center._t), _shape(center), _ptr(center_conj._t),
+                                       _shape(center_conj), _ptr(operator._t) if operator is not None else None, _ptr(E),
+                                       _stream()))
     return E, dims
 
 
@@ -120,14 +120,10 @@ def _absorb_center(direction, side, E, dims, accumulate_into):
     if s[7] != dims[1]:
         raise DimensionMismatchError(0, 7, s[7], 2, direction, dims[1])
     nl, ml, nr, mr, no, mo = dims[2:]
-    out_dims = (s[0], nl, s[1], ml, s[2], s[3], nr, s[4], mr, s[5], no * mo)
     out_shape = (s[0] * nl, s[1] * ml, s[2], s[3] * nr, s[4] * mr, s[5], no, mo)
     out, beta = _target(out_shape, accumulate_into)
-    st = _row_major_strides(out_dims)
-    K = s[6] * s[7]
-    gemm_scatter(OP_N, OP_N, prod(s[:6]), prod(dims[2:]), K, side._t, K, E, prod(dims[2:]), out,
-                 ((s[0], st[0]), (s[1], st[2]), (s[2], st[4]), (s[3], st[5]), (s[4], st[7]), (s[5], st[9])),
-                 ((nl, st[1]), (ml, st[3]), (nr, st[6]), (mr, st[8]), (no * mo, st[10])), beta=beta)
+    check(lib.carc_absorb_center_into_side(_ptr(side._t), _shape(side), _ptr(E), _shape(dims), _ptr(out), int(beta != 0.0),
+                                           _stream()))
     if accumulate_into is not None:
         return accumulate_into
     result = DeviceData(out)
@@ -163,11 +159,10 @@ def formNormalizationStage1(corner, side, accumulate_into=None):
     for a in range(3):
         _check_bond(0, 3 + a, corner, 1, a, side)
     c, s = corner.shape, side.shape
-    K = c[3] * c[4] * c[5]
-    M, Nn = c[0] * c[1] * c[2], prod(s[3:])
-    out_shape = (M, s[3] * s[4] * s[5], s[6], s[7])
+    out_shape = (c[0] * c[1] * c[2], s[3] * s[4] * s[5], s[6], s[7])
     out, beta = _target(out_shape, accumulate_into)
-    gemm(OP_N, OP_N, M, Nn, K, corner._t, K, side._t, Nn, out, beta=beta)
+    check(lib.carc_form_stage1(_ptr(corner._t), _shape(corner), _ptr(side._t), _shape(side), _ptr(out), int(beta != 0.0),
+                               _stream()))
     return accumulate_into if accumulate_into is not None else DeviceData(out)
 
 
@@ -215,11 +210,12 @@ def formNormalizationStage2(stage1_a, stage1_b, accumulate_into=None, half=None,
     front of every matvec disappears.  ``slab`` = (rank, world): only this rank's slab of X is built (multi-GPU)."""
     _check_ranks((stage1_a, 4), (stage1_b, 4))
     _check_bond(0, 0, stage1_a, 1, 1, stage1_b)
-    p = stage2SlabPlan(stage1_a.shape, stage1_b.shape, half, slab)
+    p = stage2SlabPlan(stage1_a.shape, stage1_b.shape, half, slab)      # the plan carc_form_stage2 executes (shapes here)
     out, beta = _target(p["out_shape"], accumulate_into)
-    gemm_scatter(OP_T, OP_N, p["M"], p["N"], p["K"], stage1_a._t, p["lda"], stage1_b._t, p["ldb"], out, p["rows"],
-                 p["cols"], beta=beta, batch=p["batch"], strideB=p["strideB"], strideC=p["strideC"],
-                 a_offset=p["a_offset"], b_offset=p["b_offset"])
+    rank, world = slab if slab is not None else (0, 1)
+    check(lib.carc_form_stage2(_ptr(stage1_a._t), _shape(stage1_a), _ptr(stage1_b._t), _shape(stage1_b),
+                               -1 if half is None else int(half), int(rank), int(world), _ptr(out), int(beta != 0.0),
+                               _stream()))
     return accumulate_into if accumulate_into is not None else DeviceData(out)
 
 

@@ -252,6 +252,49 @@ int carc_normalizer_matrices(const void* U, const void* S, const void* Vh, int n
                              void* polar, void* normalizer, void* denormalizer, void* normalizer_sqrt,
                              void* denormalizer_sqrt, void* stream);
 
+/* ---- one call per recipe -------------------------------------------------------------------
+ * The boundary algebra of tensors/_2d/dense.py and the two solver-side helpers of the sweep, each as ONE entry point on
+ * plain device pointers and int64 shapes (corner [c0 c1 c2 | c3 c4 c5], side [s0 s1 s2 | s3 s4 s5 | s6 s7], center
+ * [right, up, left, down, physical]).  `accumulate` != 0 adds into `out` (the `result[tag] += ...` of
+ * contractSparseTensors, sparse.py:236).  All asynchronous on `stream`. */
+/* absorbDenseSideIntoCornerFromLeft / FromRight (dense.py:11-21): out [s0,s1,s2,c3 s6,c4 s7,c5] / [c0 s6,c1 s7,c2,s3,s4,s5] */
+int carc_absorb_side_into_corner(const void* corner, const int64_t* corner_shape, const void* side, const int64_t* side_shape,
+                                 int from_left, void* out, int accumulate, void* stream);
+/* absorbDenseCenterSS/SOSIntoSide (dense.py:23-81) in two steps, so that the double-layer center of one site operator is
+ * shared by every sparse tag pair: E[(g h), (vL wL vR wR vO wO)] = sum_{s z} center[.., s] O[z, s] conj[.., z] (operator_dev
+ * NULL = identity; g / h the center / conjugate legs facing side `direction`), then
+ * out [s0 vL, s1 wL, s2, s3 vR, s4 wR, s5, vO, wO] = sum_{g h} side[.., g, h] E[(g h), ..];
+ * dims = {n_i, m_i, n_l, m_l, n_r, m_r, n_o, m_o} for center_shape n, conj_shape m and i = direction, l / r / o its
+ * left / right / opposite legs. */
+int carc_double_layer_center(int direction, const void* center, const int64_t* center_shape, const void* center_conj,
+                             const int64_t* conj_shape, const void* operator_dev, void* E, void* stream);
+int carc_absorb_center_into_side(const void* side, const int64_t* side_shape, const void* E, const int64_t* dims, void* out,
+                                 int accumulate, void* stream);
+/* formNormalizationStage1 / Stage2 (dense.py:96-112): the two stages of the environment build.  half = -1: the
+ * reference's layout [B0,A1,A2,B2,A3,B3]; half = 0 / 1: the layout the center-site operator streams, [(B0 A1),A3,B3,A2,B2] /
+ * [(A1 B0),A3,B3,A2,B2] (the pre-joins of dense.py:130-131).  slab_world > 1 builds only rank slab_rank's slab of the joined
+ * environment bond (contiguous in its slow factor; both halves of a ring use the same index range), which is how the
+ * environment is sharded over GPUs. */
+int carc_form_stage1(const void* corner, const int64_t* corner_shape, const void* side, const int64_t* side_shape, void* out,
+                     int accumulate, void* stream);
+int carc_form_stage2(const void* stage1_a, const int64_t* a_shape, const void* stage1_b, const int64_t* b_shape, int half,
+                     int slab_rank, int slab_world, void* out, int accumulate, void* stream);
+/* NDArrayData.normalizeAxis (data/__init__.py:263-301) for shape[axis] in 2..80: normalized (same shape as t) =
+ * Q (U V^H) of the SVD of [(other axes), axis]; normalizer = conj(V S^-1 V^H), denormalizer = V S V^H, n x n
+ * (S^-1 skipped where S <= dont_recip_under); sqrt_svals != 0 returns the square-root variants and no tensor.  Output
+ * pointers may be NULL. */
+int carc_normalize_axis(const void* t, const int64_t* shape, int ndim, int axis, int sqrt_svals, double dont_recip_under,
+                        void* normalized, void* normalizer, void* denormalizer, void* stream);
+/* computeProductCompressor (compression.py:26-45), operator bond 1: L [l, old, old, 1], R [old, old, 1, r]; `initial` the
+ * random [old, new] draw (the host RNG stays with the caller so that seeded runs consume the reference's stream);
+ * `sweeps` alternating-least-squares rounds (reference: 4) in Gram form -- the (l r) x (old new) matrix of the reference is
+ * never formed -- each solved by the device LU after a relative diagonal shift `regularization` (1e-10) and followed
+ * by the polar projection; left_gram / right_gram: optional L^H L / R R^H over the outer legs, [(old old), (old old)].
+ * compressor_out [new, old].  No host round trip between rounds. */
+int carc_product_compressor(const void* L, int64_t l, const void* R, int64_t r, int64_t old_dim, int64_t new_dim,
+                            const void* initial, int sweeps, double regularization, const void* left_gram,
+                            const void* right_gram, void* compressor_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

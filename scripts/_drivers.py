@@ -149,7 +149,20 @@ def _seed(seed):
     random.seed(seed)
 
 
-def run_tfim_chain(J, seed=0, sweep_tol=1e-5, run_tol=1e-7, increment=2, counts=None):
+def _bond_capped(policy_class, max_bond):
+    """The run-convergence policy with a ceiling on the state bond: near the critical coupling the energy keeps creeping
+    with every bandwidth increase and an uncapped run does not end in any useful time."""
+    class Capped(policy_class):
+        def converged(self):
+            done = policy_class.converged(self)
+            if max_bond and max(self.system.state_center_data.shape[:4]) >= max_bond and self.last is not None:
+                return True
+            return done
+    return Capped
+
+
+def run_tfim_chain(J, seed=0, sweep_tol=1e-5, run_tol=1e-7, increment=2, counts=None, max_bond=None,
+                   max_iterations_per_sweep=None):
     """Infinite transverse-Ising chain through the 2D system driven along one axis (reference
     tests/test_simulator_2d_in_1d.py:36-47 with the coupling as a parameter).  Returns (energy per site, seconds,
     final bond dimension, sweeps)."""
@@ -159,8 +172,12 @@ def run_tfim_chain(J, seed=0, sweep_tol=1e-5, run_tol=1e-7, increment=2, counts=
     _init_constants()
     _seed(seed)
     system = System.newTrivialWithSimpleSparseOperator(O=-DeviceData.Z, OO_LR=[DeviceData.X, -J * DeviceData.X])
-    system.setPolicy("sweep convergence", pol.RelativeStateDifferenceThresholdConvergencePolicy(sweep_tol))
-    system.setPolicy("run convergence", pol.RelativeOneSiteExpectationDifferenceThresholdConvergencePolicy(run_tol))
+    sweep = pol.RelativeStateDifferenceThresholdConvergencePolicy(sweep_tol)
+    if max_iterations_per_sweep:
+        sweep = pol.BoundedConvergencePolicy(sweep, max_iterations_per_sweep)
+    system.setPolicy("sweep convergence", sweep)
+    system.setPolicy("run convergence",
+                     _bond_capped(pol.RelativeOneSiteExpectationDifferenceThresholdConvergencePolicy, max_bond)(run_tol))
     system.setPolicy("bandwidth increase", pol.OneDirectionIncrementBandwidthIncreasePolicy(0, increment))
     system.setPolicy("contraction", pol.RepeatPatternContractionPolicy([0, 2]))
     t0 = time.perf_counter()

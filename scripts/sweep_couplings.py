@@ -10,7 +10,7 @@ over a gloo group and prints ONE JSON line with every point (energy per site, cl
 seconds), the job's wall time (max over ranks) and the aggregate throughput in sweep iterations per second.
 
     python scripts/sweep_couplings.py --J 0.02,0.1,0.3,0.5,0.8,1.0,1.4,2.0
-    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 scripts/sweep_couplings.py --J-grid 0.05:2.0:32
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 scripts/sweep_couplings.py --J-grid 0.05:0.8:32
 
 ``--model plane`` sweeps the infinite square lattice instead (bounded full-2D runs, see _drivers.run_tfim_plane).
 """
@@ -60,7 +60,8 @@ def run_point(model, J, args):
     if model == "chain":
         counts = {}
         energy, seconds, bond, sweeps = _drivers.run_tfim_chain(J, seed=args.seed, sweep_tol=args.sweep_tol,
-                                                                 run_tol=args.run_tol, counts=counts)
+                                                                 run_tol=args.run_tol, counts=counts, max_bond=args.max_bond,
+                                                                 max_iterations_per_sweep=args.max_iterations_per_sweep)
         # _drivers.tfim_infinite_chain_energy keeps the reference script's convention (computeTIinfinite.py:6-12: its
         # argument is twice the XX coupling, lam = J / 2); the run's Hamiltonian is -sum Z - J sum X X
         exact = float(_drivers.tfim_infinite_chain_energy(2.0 * J))
@@ -80,6 +81,9 @@ def main():
     ap.add_argument("--sweep-tol", type=float, default=1e-5)
     ap.add_argument("--run-tol", type=float, default=1e-7)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--max-bond", type=int, default=12,
+                    help="chain runs stop growing the state bond here (the critical point J = 1 never converges otherwise)")
+    ap.add_argument("--max-iterations-per-sweep", type=int, default=200)
     args = ap.parse_args()
     grid = parse_grid(args)
     rank = int(os.environ.get("RANK", "0"))

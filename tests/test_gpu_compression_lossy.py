@@ -59,3 +59,41 @@ def test_lossy_compressor_against_reference_run(case):
     tol = 1e-6 if case < 3 else 2e-3
     assert np.linalg.norm(c.conj().T @ c - want.conj().T @ want) / np.sqrt(new) < tol
     assert abs(device_error - product_error(Lt, Rt, want)) < tol
+
+
+@pytest.mark.parametrize("shape", [(6, 6, 3, 20), (5, 8, 4, 12), (12, 8, 4, 9), (4, 5, 5, 4), (9, 6, 1, 9)])
+def test_one_call_compressor_matches_the_stepwise_path(shape):
+    """carc_product_compressor (the whole Gram-form ALS in one library call, csrc/recipes.cu) against the same rounds
+    issued step by step from Python (compression._PYTHON_ALS), from the same random start, with and without the
+    precomputed Gram factors.  (Shapes with at least as many equations l r as unknowns old new: below that the normal
+    equations are rank deficient by construction and the two paths' triangular solves -- plain and block-inverse -- part
+    ways at the 1e-3 level in the null-space directions the shift leaves undetermined.)"""
+    from carcassonne_b200 import compression
+    from carcassonne_b200.data import DeviceData
+    l, old, new, r = shape
+    rng = np.random.default_rng(sum(shape))
+
+    def crand(*s):
+        return rng.uniform(-1, 1, s) + 1j * rng.uniform(-1, 1, s)
+
+    Lt = crand(l, old, old, 1)
+    Lt = Lt + Lt.transpose(0, 2, 1, 3).conj()
+    Rt = crand(old, old, 1, r)
+    Rt = Rt + Rt.transpose(1, 0, 2, 3).conj()
+    init = crand(old, new)
+    L, R, c0 = DeviceData.fromArray(Lt), DeviceData.fromArray(Rt), DeviceData.fromArray(init)
+    one = compression.computeProductCompressor(L, R, new, initial=c0).toArray()
+    compression._PYTHON_ALS = True
+    try:
+        steps = compression.computeProductCompressor(L, R, new, initial=c0).toArray()
+    finally:
+        compression._PYTHON_ALS = False
+    assert one.shape == steps.shape == (new, old)
+    assert np.linalg.norm(one @ one.conj().T - np.eye(new)) < 1e-12
+    assert np.linalg.norm(one.conj().T @ one - steps.conj().T @ steps) < 1e-9
+    # precomputed Gram factors (what compressCornerStateTowards passes after a center absorption)
+    LL = np.einsum("lab,lcd->abcd", Lt[..., 0].conj(), Lt[..., 0]).reshape(old * old, old * old)
+    RR = np.einsum("abr,cdr->abcd", Rt[:, :, 0, :].conj(), Rt[:, :, 0, :]).reshape(old * old, old * old)
+    given = compression.computeProductCompressor(L, R, new, initial=c0, left_gram=DeviceData.fromArray(LL),
+                                                 right_gram=DeviceData.fromArray(RR)).toArray()
+    assert np.linalg.norm(given.conj().T @ given - one.conj().T @ one) < 1e-9

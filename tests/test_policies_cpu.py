@@ -159,3 +159,10 @@ def test_hook_policy_accepts_a_bound_method_callback():
     assert binding.apply() == "called"
     assert spy.seen == [system]
     assert binding.callback.__self__ is spy
+
+
+def test_compression_policy_rejects_bonds_beyond_the_device_svd_up_front():
+    from carcassonne_b200.linalg import MAX_SMALL
+    pol.ConstantStateCompressionPolicy(MAX_SMALL)
+    with pytest.raises(NotImplementedError):
+        pol.ConstantStateCompressionPolicy(MAX_SMALL + 1)
