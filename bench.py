@@ -491,7 +491,7 @@ def matvec_section(job, model, D, chi, d, steps, warmup, mode="xslab", gate=True
     out = torch.empty_like(v)
     if job.world > 1:
         dist.broadcast(v, 0)
-    parity = parity_gate(job, env, D, d, v) if gate else None
+    parity = parity_gate(job, env, D, d, v) if gate and not job.args.no_parity else None
     comm = job.peer_comm(n)
     cd.shard_operator(op, comm)
     use_nccl = job.world > 1 and comm is None
@@ -827,6 +827,9 @@ def main():
                     help="run the (D, chi) = (8, 32) capacity section (default: only at 8 GPUs)")
     ap.add_argument("--no-capacity", action="store_true")
     ap.add_argument("--no-capacity-relax", action="store_true")
+    ap.add_argument("--no-parity", action="store_true",
+                    help="skip the in-job parity gate (ONLY for ncu launch lists: its unfused full-size check is ~500 "
+                         "launches that would drown the timed steps)")
     ap.add_argument("--path", type=int, default=0, choices=[0, 1, 2, 3],
                     help="device path of the matvec: 0 automatic, 1 fused kernel, 3 fused kernel with the folded "
                          "tiling, 2 unfused GEMMs (kernel comparisons; the default is what the library picks)")

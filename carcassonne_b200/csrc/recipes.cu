@@ -163,6 +163,141 @@ __global__ void __launch_bounds__(256) diagonal_shift_kernel(cplx* G, int n, dou
   for (int i = threadIdx.x; i < n; i += blockDim.x) G[(int64_t)i * n + i].x += shift;
 }
 
+// x <- A^-1 x for a small system (n <= 118: the matrix, padded to an odd row stride, and the right-hand side fit the
+// shared memory of one SM): LU with partial pivoting (LAPACK's rule: largest |re| + |im|, first on ties) and both
+// substitutions in ONE launch of one CTA.  The normal equations of a state-bond compression at small bond dimension are
+// this size (old new = 108 at chi = 6, D = 3), four per compression and eight compressions per sweep iteration; the
+// blocked device LU spends ~0.4 ms per factorisation on grid barriers there (two cooperative panel launches), this kernel
+// a few dozen microseconds.  A is left untouched.
+constexpr int SMALL_LU_MAX = 118;
+__global__ void __launch_bounds__(1024, 1) small_lu_solve_kernel(const cplx* __restrict__ A, int n, cplx* __restrict__ x) {
+  extern __shared__ __align__(16) unsigned char small_lu_raw[];
+  const int ld = n + 1;
+  cplx* M = reinterpret_cast<cplx*>(small_lu_raw);
+  cplx* rhs = M + (size_t)n * ld;
+  __shared__ double wval[32];
+  __shared__ int widx[32];
+  __shared__ int prow;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int e = tid; e < n * n; e += blockDim.x) M[(e / n) * ld + e % n] = A[e];
+  for (int i = tid; i < n; i += blockDim.x) rhs[i] = x[i];
+  __syncthreads();
+  for (int k = 0; k < n; ++k) {
+    // pivot search in column k
+    double best = -1.0;
+    int arg = n;
+    for (int i = k + tid; i < n; i += blockDim.x) {
+      const cplx v = M[i * ld + k];
+      const double a = fabs(v.x) + fabs(v.y);
+      if (a > best) {
+        best = a;
+        arg = i;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (ob > best || (ob == best && oa < arg)) {
+        best = ob;
+        arg = oa;
+      }
+    }
+    if (lane == 0) {
+      wval[warp] = best;
+      widx[warp] = arg;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      best = lane < (int)(blockDim.x >> 5) ? wval[lane] : -1.0;
+      arg = lane < (int)(blockDim.x >> 5) ? widx[lane] : n;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (ob > best || (ob == best && oa < arg)) {
+          best = ob;
+          arg = oa;
+        }
+      }
+      if (lane == 0) prow = arg < n ? arg : k;
+    }
+    __syncthreads();
+    const int p = prow;
+    if (p != k) {
+      for (int j = tid; j < n; j += blockDim.x) {
+        const cplx t = M[k * ld + j];
+        M[k * ld + j] = M[p * ld + j];
+        M[p * ld + j] = t;
+      }
+      if (tid == 0) {
+        const cplx t = rhs[k];
+        rhs[k] = rhs[p];
+        rhs[p] = t;
+      }
+      __syncthreads();
+    }
+    const cplx piv = M[k * ld + k];
+    const double den = piv.x * piv.x + piv.y * piv.y;
+    if (den > 0.0) {
+      const cplx inv = make_double2(piv.x / den, -piv.y / den);
+      for (int i = k + 1 + tid; i < n; i += blockDim.x) {
+        const cplx v = M[i * ld + k];
+        M[i * ld + k] = make_double2(v.x * inv.x - v.y * inv.y, v.x * inv.y + v.y * inv.x);
+      }
+    }
+    __syncthreads();
+    // trailing update and the forward substitution of the right-hand side
+    for (int i = k + 1 + warp; i < n; i += (int)(blockDim.x >> 5)) {
+      const cplx l = M[i * ld + k];
+      for (int j = k + 1 + lane; j < n; j += 32) {
+        const cplx u = M[k * ld + j];
+        cplx c = M[i * ld + j];
+        c.x -= l.x * u.x - l.y * u.y;
+        c.y -= l.x * u.y + l.y * u.x;
+        M[i * ld + j] = c;
+      }
+      if (lane == 0) {
+        const cplx u = rhs[k];
+        rhs[i].x -= l.x * u.x - l.y * u.y;
+        rhs[i].y -= l.x * u.y + l.y * u.x;
+      }
+    }
+    __syncthreads();
+  }
+  // back substitution with U
+  for (int k = n - 1; k >= 0; --k) {
+    if (tid == 0) {
+      const cplx piv = M[k * ld + k], b = rhs[k];
+      const double den = piv.x * piv.x + piv.y * piv.y;
+      rhs[k] = make_double2((b.x * piv.x + b.y * piv.y) / den, (b.y * piv.x - b.x * piv.y) / den);
+    }
+    __syncthreads();
+    const cplx xk = rhs[k];
+    for (int i = tid; i < k; i += blockDim.x) {
+      const cplx u = M[i * ld + k];
+      rhs[i].x -= u.x * xk.x - u.y * xk.y;
+      rhs[i].y -= u.x * xk.y + u.y * xk.x;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += blockDim.x) x[i] = rhs[i];
+}
+
+int small_lu_solve(const cplx* A, int n, cplx* x, cudaStream_t stream) {
+  const size_t smem = sizeof(cplx) * ((size_t)n * (n + 1) + n);
+  static bool configured[16] = {false};
+  int dev = 0;
+  CARC_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 16 && !configured[dev]) {
+    CARC_CHECK_CUDA(cudaFuncSetAttribute(small_lu_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    configured[dev] = true;
+  }
+  small_lu_solve_kernel<<<1, 1024, smem, stream>>>(A, n, x);
+  CARC_CHECK_CUDA(cudaGetLastError());
+  return CARC_OK;
+}
+
 inline int L4(int i) { return (i + 1) % 4; }
 inline int R4(int i) { return (i + 3) % 4; }
 inline int O4(int i) { return (i + 2) % 4; }
@@ -437,8 +572,12 @@ int carc_product_compressor(const void* L, int64_t l, const void* R, int64_t r, 
     // x = (G + eps mean(diag G) I)^-1 rhs
     diagonal_shift_kernel<<<1, 256, 0, st>>>(gram, (int)m, regularization);
     CARC_CHECK_CUDA(cudaGetLastError());
-    CARC_TRY(lu_factor(gram, (int)m, piv, singular_dev, scratch_lu, st));
-    CARC_TRY(lu_solve(gram, (int)m, piv, rhs, st));
+    if (m <= SMALL_LU_MAX) {
+      CARC_TRY(small_lu_solve(gram, (int)m, rhs, st));
+    } else {
+      CARC_TRY(lu_factor(gram, (int)m, piv, singular_dev, scratch_lu, st));
+      CARC_TRY(lu_solve(gram, (int)m, piv, rhs, st));
+    }
     CARC_TRY(unitize_tall(rhs, old, (int)nw, c, s));
   }
   return permute(c, (cplx*)compressor_out, 2, shape_c, transpose, 0, 0, st);
