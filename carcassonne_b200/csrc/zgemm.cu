@@ -43,6 +43,8 @@ struct GemmParams {
   const int64_t* coloff;
   int hermitian;              // 1: C = C^H (M == N): tiles strictly below the diagonal are skipped and mirrored
   unsigned tiles_m;           // number of M tiles (the tile grid is linearised on blockIdx.x)
+  unsigned tiles_n, group_m;  // the linear order walks `group_m` M tiles at a time through all N tiles, so that the ~148 CTAs
+                              // running together cover a compact block of the output and share operand tiles in L2
   int splitk;                 // > 1: blockIdx.z is a K split; raw partial products go to C = workspace[split][M][N]
   int64_t kt_per_split;       // K tiles per split
 };
@@ -59,7 +61,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) zgemm_kernel(GemmParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1;       // 4 x 2 warps
   const int r = lane >> 2, c = lane & 3;
-  const int64_t m0 = (int64_t)(blockIdx.x % p.tiles_m) * BM, n0 = (int64_t)(blockIdx.x / p.tiles_m) * BN;  // 1-D tile grid
+  // 1-D tile grid in grouped order (a wave of CTAs reads ~2 sqrt(148) distinct operand tiles per k-step instead of
+  // tiles_m + 148 / tiles_m: the Gram products of the compression re-read their 4.3 GB operand 20 x from DRAM before)
+  const unsigned width = p.group_m * p.tiles_n, grp = blockIdx.x / width, first_m = grp * p.group_m;
+  const unsigned gsz = min(p.tiles_m - first_m, p.group_m), within = blockIdx.x - grp * width;
+  const int64_t m0 = (int64_t)(first_m + within % gsz) * BM, n0 = (int64_t)(within / gsz) * BN;
   if (p.hermitian == 1 && n0 + BN - 1 < m0) return;   // strictly lower tile: filled by the mirror of its transpose
   if (p.hermitian == 2 && n0 > m0 + BM - 1) return;   // lower-triangle update: tiles strictly above the diagonal skipped
   const bool split = p.splitk > 1;
@@ -460,6 +466,8 @@ int zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, cplx alpha, const c
   CARC_REQUIRE(batch < 65536 && gx * gy < (1ll << 31), CARC_ERR_VALUE, "zgemm: grid too large (%lld tiles, batch %lld)",
                (long long)(gx * gy), (long long)batch);
   p.tiles_m = (unsigned)gy;
+  p.tiles_n = (unsigned)gx;
+  p.group_m = (unsigned)std::min<int64_t>(gy, 12);
   p.splitk = 1;
   p.kt_per_split = 0;
   const int64_t tiles = gx * gy, KT = (K + BK - 1) / BK;
