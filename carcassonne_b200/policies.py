@@ -103,17 +103,29 @@ class ConstantStateCompressionPolicy(CompressionPolicy):
 
 
 class ConstantOperatorCompressionPolicy(CompressionPolicy):
-    """Fills the reference's empty "operator compression" slot (system/base.py:49): folds the partnered two-site
-    halves of every corner into a compressed operator bond of at most ``new_dimension``.
-    One application leaves <H> and <N> unchanged at full rank; applying it repeatedly between absorptions is only exact
-    while both ends of each side keep the same channel basis (not guaranteed by the reference's tag scheme), so the
-    policy is offered for experiments, not enabled anywhere by default."""
+    """Fills the reference's empty "operator compression" slot (system/base.py:49): folds the two-site halves of every
+    edge of the ring into compressed operator bonds of at most ``new_dimension``, which
+    bounds the number of stage-3 terms -- otherwise it grows with every absorption round.
 
-    def __init__(self, new_dimension, normalize=False):
+    ``per_edge`` (default): ``System.compressEdgeTwoSiteOperators`` -- one channel basis per edge, applied to the four
+    tensors whose operator bonds face each other across that edge, so that <H> and <N> stay invariant (at full rank)
+    under any number of absorb + compress rounds (tests/test_gpu_two_site.py: 20 rounds, 1e-9).  ``per_edge=False`` is
+    the reference's per-junction routine (``compressCornerTwoSiteOperatorTowards``, system/_2d.py:229-363), exact for
+    ONE application only: the two ends of a side are rotated at different junctions by different unitaries and stop
+    matching once a corner has absorbed the side."""
+
+    def __init__(self, new_dimension, normalize=False, per_edge=True):
         self.new_dimension = new_dimension
         self.normalize = normalize
+        self.per_edge = per_edge
 
     def apply(self):
+        if self.per_edge:
+            for edge in range(4):
+                old_dimension = self.system.edgeTwoSiteOperatorBondDimension(edge)
+                if old_dimension:
+                    self.system.compressEdgeTwoSiteOperators(edge, min(self.new_dimension, old_dimension), self.normalize)
+            return
         for corner_id in range(4):
             for direction in range(2):
                 old_dimension = self.system.twoSiteOperatorBondDimension(corner_id, direction)

@@ -460,6 +460,114 @@ class System(BaseSystem):
                                                                        side_compressed, side_multiplier)
         self.sides[side_id] = kept_side
 
+    # -- operator-bond compression that survives absorption (no counterpart in the reference) ----
+    def _edge_members(self, edge):
+        """The four tensors whose operator bonds face each other across the translation of side ``edge``:
+        (container, index, direction, right_facing).  corner_e and side_e carry the bond on their RIGHT end (axis 5),
+        side_e and corner_{R(e)} on their LEFT end (axis 2); after any absorption every right-facing bond of the edge
+        meets a left-facing one (corner_e | side_e, side_e | side_e -- the next copy --, side_e | corner_{R(e)})."""
+        return ((self.corners, edge, 1, True), (self.sides, edge, 1, True),
+                (self.sides, edge, 0, False), (self.corners, R(edge), 0, False))
+
+    def edgeTwoSiteOperatorBondDimension(self, edge):
+        """Channels ``compressEdgeTwoSiteOperators`` would fold: two-site halves present, with the same (id, position),
+        on all four tensors of the edge, plus the extent of an existing compressed bond."""
+        keys, compressed = None, 0
+        for container, index, direction, _ in self._edge_members(edge):
+            mine = {(t.id, t.position) for t in container[index] if isinstance(t, TwoSiteOperator) and t.direction == direction}
+            keys = mine if keys is None else keys & mine
+            for t, data in container[index].items():
+                if isinstance(t, TwoSiteOperatorCompressed) and t.direction == direction:
+                    compressed = data.shape[3 * direction + 2]
+        return len(keys) + compressed
+
+    def compressEdgeTwoSiteOperators(self, edge, new_dimension, normalize=False):
+        """Fold the two-site halves of one edge of the ring into a compressed operator bond of ``new_dimension`` with
+        ONE channel basis for the whole edge: the right-facing tensors (corner ``edge`` and side ``edge``, bond 5) are
+        rotated by the compressor, the left-facing ones (side ``edge`` and corner ``R(edge)``, bond 2) by its conjugate.
+
+        The reference's per-junction routine (``compressCornerTwoSiteOperatorTowards``, system/_2d.py:229-363) rotates
+        one corner-side junction at a time; when the corner later absorbs the side, the side's OTHER end -- rotated
+        at another junction by another unitary -- becomes the corner's bond and no longer matches the side it faces.
+        With one basis per edge every right-facing bond keeps meeting a left-facing one in the conjugate basis, whatever
+        is absorbed into whatever, so <H> and <N> are invariant under any number of absorb + compress rounds at full
+        rank, and the number of stage-3 terms stops growing (the growing family of (TwoSite, TwoSite, Identity) cross
+        terms becomes one (Compressed, Compressed, Identity) term per cut).  The compressor keeps the dominant
+        eigenvectors of the summed Gram matrix of the flattened halves (conjugated for the left-facing tensors)."""
+        members = self._edge_members(edge)
+        gathered, keys, have_compressed = [], None, []
+        for container, index, direction, _ in members:
+            halves, compressed, kept = {}, None, {}
+            for tag, data in container[index].items():
+                if isinstance(tag, TwoSiteOperator) and tag.direction == direction:
+                    halves[tag.id, tag.position] = (tag, data)
+                elif isinstance(tag, TwoSiteOperatorCompressed) and tag.direction == direction:
+                    assert compressed is None
+                    compressed = data
+                else:
+                    kept[tag] = data
+            gathered.append((halves, compressed, kept))
+            keys = set(halves) if keys is None else keys & set(halves)
+            have_compressed.append(compressed is not None)
+        if any(have_compressed) and not all(have_compressed):
+            raise ValueError("edge {} carries a compressed operator bond on some of its tensors only".format(edge))
+        keys = sorted(keys, key=repr)
+        n_sparse = len(keys)
+        k_old = gathered[0][1].shape[5] if have_compressed[0] else 0
+        old_dimension = n_sparse + k_old
+        if old_dimension == 0:
+            return None
+        gram = np.zeros((old_dimension,) * 2, dtype=np.complex128)
+        stacks = []
+        for (container, index, direction, right_facing), (halves, compressed, kept) in zip(members, gathered):
+            axis = 3 * direction + 2
+            stacked = DeviceData.newCollected([halves[key][1].ravel() for key in keys]) if n_sparse else None
+            stacks.append(stacked)
+            block = np.zeros_like(gram)
+            if n_sparse:
+                block[:n_sparse, :n_sparse] = stacked.conj().contractWith(stacked, (1,), (1,)).toArray()
+            if compressed is not None:
+                if compressed.shape[axis] != k_old:
+                    raise ValueError("compressed operator bonds of edge {} differ in extent".format(edge))
+                folded = compressed.fold(axis)
+                block[n_sparse:, n_sparse:] = folded.conj().contractWith(folded, (1,), (1,)).toArray()
+            gram += block if right_facing else block.conj()
+        right_multiplier, left_multiplier_conj = computeCompressor(
+            old_dimension, min(new_dimension, old_dimension),
+            Multiplier((old_dimension,) * 2, lambda v: gram @ v, gram.size, lambda: gram, 0), np.complex128, normalize)
+        left_multiplier = left_multiplier_conj.conj()
+        for (container, index, direction, right_facing), (halves, compressed, kept), stacked in zip(members, gathered, stacks):
+            axis = 3 * direction + 2
+            multiplier = right_multiplier if right_facing else left_multiplier
+            reference_shape = container[index][Identity()].shape
+            result = None
+            if stacked is not None:
+                shape = list(reference_shape)
+                del shape[axis]
+                order = list(range(1, len(reference_shape)))
+                order.insert(axis, 0)
+                mixed = stacked.split(n_sparse, *shape).absorbMatrixAt(0, DeviceData.fromArray(multiplier[:, :n_sparse]))
+                result = mixed.transpose(order)
+            if compressed is not None:
+                term = compressed.absorbMatrixAt(axis, DeviceData.fromArray(multiplier[:, n_sparse:]))
+                if result is None:
+                    result = term
+                else:
+                    result = result.copy()
+                    result += term
+            # rebuilt from the tensor as it is NOW: side `edge` is a member twice (its right end and its left end)
+            folded_keys = set(keys)
+            new = {}
+            for tag, data in container[index].items():
+                if isinstance(tag, TwoSiteOperatorCompressed) and tag.direction == direction:
+                    continue
+                if isinstance(tag, TwoSiteOperator) and tag.direction == direction and (tag.id, tag.position) in folded_keys:
+                    continue                              # folded; halves not present on all four tensors stay ordinary tags
+                new[tag] = data
+            new[TwoSiteOperatorCompressed(direction)] = result
+            container[index] = new
+        return right_multiplier
+
     # -- gauge normalisation of the environment (reference system/_2d.py:503-549) ----------------------------------------
     def normalize(self):
         for corner_id in range(4):
