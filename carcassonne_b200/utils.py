@@ -276,45 +276,52 @@ def relaxOver(initial, expectation_multiplier, normalization_multiplier=None, ma
 
 
 # -- compressors (reference utils.py:268-321) ----------------------------------------------------------------------
-def computeCompressor(old_dimension, new_dimension, multiplier, dtype=np.complex128, normalize=False):
-    """Top-``new_dimension`` eigenpairs of a small Hermitian PSD matrix (size = number of operator terms): host
-    LAPACK, as SURVEY.md section 2 (K17) prescribes -- the matrix is a handful of numbers."""
+def _dominant_eigenpairs(multiplier, size, count, dtype):
+    """(eigenvalues ascending, eigenvectors as columns) of the ``count`` dominant eigenpairs of a Hermitian positive
+    semi-definite operator of dimension ``size``.  Dense LAPACK when at least about half the spectrum is wanted -- the
+    reference's switch-over, new >= old // 2 (utils.py:279) -- otherwise ARPACK on the matvec, as the reference does."""
     from scipy.linalg import eigh
     from scipy.sparse.linalg import LinearOperator, eigsh
+    if count < size // 2:
+        return eigsh(LinearOperator(shape=(size, size), matvec=multiplier, dtype=dtype), k=count)
+    matrix = multiplier.formMatrix()
+    matrix = matrix.toArray() if hasattr(matrix, "toArray") else np.asarray(matrix)
+    if matrix.shape != (size, size):
+        raise ValueError("Multiplier matrix has shape {} but the old dimension is {}.".format(matrix.shape, size))
+    values, vectors = eigh(matrix)
+    return values[size - count:], vectors[:, size - count:]
+
+
+def computeCompressor(old_dimension, new_dimension, multiplier, dtype=np.complex128, normalize=False):
+    """Compressor pair for an operator bond (same contract as the reference's ``computeCompressor``, utils.py:268-303;
+    a #terms x #terms problem, kept on the host as SURVEY.md section 2 (K17) prescribes): the rows of both returned
+    [new, old] matrices are the dominant eigenvectors (transposed, not conjugated) of the Gram operator ``multiplier``;
+    with ``normalize`` the first is scaled by the square roots of the eigenvalues and the second by their inverses, so
+    that the pair still multiplies to the projector.  Raises ``ValueError`` for an inconsistent dimension and when every
+    retained eigenvalue is numerically zero."""
     if new_dimension < 0:
         raise ValueError("New dimension ({}) must be non-negative.".format(new_dimension))
     if new_dimension > old_dimension:
         raise ValueError("New dimension ({}) must be less than or equal to the old dimension ({}).".format(
             new_dimension, old_dimension))
     if new_dimension == 0:
-        return (np.zeros((new_dimension, old_dimension), dtype=dtype),) * 2
-    if new_dimension >= old_dimension // 2:
-        matrix = multiplier.formMatrix()
-        matrix = matrix.toArray() if hasattr(matrix, "toArray") else np.asarray(matrix)
-        if tuple(matrix.shape) != (old_dimension,) * 2:
-            raise ValueError("Multiplier matrix has shape {} but the old dimension is {}.".format(matrix.shape,
-                                                                                                old_dimension))
-        evals, evecs = eigh(matrix)
-        evals, evecs = evals[-new_dimension:], evecs[:, -new_dimension:]
-    else:
-        evals, evecs = eigsh(LinearOperator(shape=(old_dimension,) * 2, matvec=multiplier, dtype=dtype), k=new_dimension)
-    evecs = evecs.transpose()
-    while new_dimension > 0 and abs(evals[new_dimension - 1]) < 1e-15:
-        new_dimension -= 1
-    if new_dimension == 0:
+        empty = np.zeros((0, old_dimension), dtype=dtype)
+        return empty, empty
+    values, vectors = _dominant_eigenpairs(multiplier, old_dimension, new_dimension, dtype)
+    if not np.any(np.abs(values) >= 1e-15):
         raise ValueError("Input is filled with near-zero elements.")
-    if normalize:
-        evals = np.sqrt(evals).reshape(new_dimension, 1)
-        return evecs * evals, evecs / evals
-    return evecs, evecs
+    rows = vectors.T
+    if not normalize:
+        return rows, rows
+    weights = np.sqrt(values)[:, None]
+    return rows * weights, rows / weights
 
 
 def computeCompressorForMatrixTimesItsDagger(old_dimension, new_dimension, matrix, normalize=False):
-    other_dimension = matrix.shape[0]
-    matrix_dagger = matrix.transpose().conj()
-    return computeCompressor(
-        old_dimension, new_dimension,
-        Multiplier((old_dimension,) * 2, lambda v: np.dot(matrix_dagger, np.dot(matrix, v)),
-                   2 * old_dimension * other_dimension, lambda: np.dot(matrix_dagger, matrix),
-                   old_dimension ** 2 * other_dimension),
-        matrix.dtype, normalize)
+    """Compressor of the Gram operator M^H M of a [other, old] matrix, applied without forming it when ARPACK is used
+    (reference utils.py:305-321)."""
+    adjoint = matrix.conj().T
+    rows = matrix.shape[0]
+    gram = Multiplier((old_dimension, old_dimension), lambda v: adjoint @ (matrix @ v), 2 * old_dimension * rows,
+                      lambda: adjoint @ matrix, old_dimension * old_dimension * rows)
+    return computeCompressor(old_dimension, new_dimension, gram, matrix.dtype, normalize)
