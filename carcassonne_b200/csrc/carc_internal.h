@@ -91,7 +91,7 @@ int stage3_path(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, int
 // stage3f.cu: the folded tiling of the fused kernel (spin index folded into the columns of the first product)
 struct Stage3FConfig {
   int NPT, NRT, Q4, NSB, G, nstA, nstB, QS, BSTR, b_whole;
-  int ws_barriers = 0;  // barrier area sized for the warp-specialised instantiation (8 row tiles, one group)
+  int ws = 0;           // consumer-warp slots of the warp-specialised kernel (8 or 12), 0 = the symmetric kernel
   int PB = 1, RB = 1;   // row / column blocks of the output (P > 64 or R > 64); NPT, NRT are those of the largest block
   int sb_cta0[17], sb_tile0[17];
   unsigned char cta_sb[160], cta_sl[160];

@@ -170,13 +170,18 @@ __device__ __forceinline__ void s3f_second(CTile (&acc)[NRT][2], const CTile& W,
 
 // NA: number of tiles the S blocks of THIS launch hold (NT or NT - 1: an uneven split of S gives blocks of both widths
 // and one launch per width), or 0 for "read it at run time" (see s3f_active).
-// WS ("warp specialised", only for one group of exactly 8 row tiles -- P in 57..64, the D = 8 shape): the CTA gets a third
-// warpgroup, warps 8..11, that runs the op cursor and issues every TMA copy, and the eight consumer warps do nothing but
+// WS > 0 ("warp specialised"): the CTA has WS consumer-warp slots (8 or 12: two or three warpgroups) and one more
+// warpgroup of producers that runs the op cursor and issues every TMA copy, so that the consumer warps do nothing but
 // wait -> DMMA -> release.  `setmaxnreg` moves the registers to where the accumulators are: the kernel is launched with
-// 384 threads (168 registers each), the producer warpgroup drops to 40 and the two consumer warpgroups rise to 232
-// (8 x 32 x 232 + 4 x 32 x 40 = 64 512 of the 65 536).  A slots then need empty barriers (consumer -> producer).
-template <int NRT, int NT, int NA, bool WS>
-__global__ void __launch_bounds__(WS ? 384 : s3f_max_threads(NRT), 1) stage3f_kernel(const S3FParams p) {
+// (WS + 4) warps (168 / 128 registers each), the producer warpgroup drops to 40 and the consumer warpgroups rise to
+// 232 / 152 (8 x 32 x 232 + 4 x 32 x 40 = 64 512, 12 x 32 x 152 + 4 x 32 x 40 = 63 488 of the 65 536).  A slots then need
+// empty barriers (consumer -> producer).  The 4 producer warps are shared out between the G <= 4 groups: 4 / G warps per
+// group, each issuing the A copies of every (4 / G)-th consumer warp and every (4 / G)-th row of the B blocks.
+// WS == 0: the symmetric kernel -- every warp is consumer and producer of its own rows (kept for CARC_S3F_WS=0).
+__host__ __device__ constexpr int s3f_ws_consumer_registers(int ws) { return ws == 8 ? 232 : 152; }
+__host__ __device__ constexpr int s3f_producers_per_group(int G) { return G == 1 ? 4 : G == 2 ? 2 : 1; }
+template <int NRT, int NT, int NA, int WS>
+__global__ void __launch_bounds__(WS ? (WS + 4) * 32 : s3f_max_threads(NRT), 1) stage3f_kernel(const S3FParams p) {
   const int cta = p.cta_map[blockIdx.x];   // position in the whole job's CTA table (slab, S block, partial slot)
   constexpr int DP = 2;
   constexpr int UW = NT < 2 ? NT : 2;   // tiles per pass of a later term's first product (register budget)
@@ -204,12 +209,12 @@ __global__ void __launch_bounds__(WS ? 384 : s3f_max_threads(NRT), 1) stage3f_ke
       for (int i = 0; i < p.NPT * p.nstA; ++i) mbar_init(b + i * 8, 1);   // full A, private to one warp
       for (int i = 0; i < p.nstB; ++i) {
         // full B: every warp that copies rows announces its share (WS: the four producer warps)
-        mbar_init(b + (p.NPT * p.nstA + 2 * i) * 8, p.b_whole ? 1 : (WS ? 4 : p.NPT));
+        mbar_init(b + (p.NPT * p.nstA + 2 * i) * 8, p.b_whole ? 1 : (WS ? s3f_producers_per_group(p.G) : p.NPT));
         mbar_init(b + (p.NPT * p.nstA + 2 * i + 1) * 8, p.NPT);   // empty B
       }
     }
     if (WS)   // empty A, one per (consumer warp, stage), behind the other barriers
-      for (int i = 0; i < p.NPT * p.nstA; ++i) mbar_init(bars + (p.G * nbar_g + i) * 8, 1);
+      for (int i = 0; i < ncw * p.nstA; ++i) mbar_init(bars + (p.G * nbar_g + i) * 8, 1);
     fence_barrier_init();
   }
   __syncthreads();
@@ -251,15 +256,21 @@ __global__ void __launch_bounds__(WS ? 384 : s3f_max_threads(NRT), 1) stage3f_ke
   fence_proxy_async();
   __syncthreads();
 
-  if (WS && warp >= ncw) {
-    // ---- producer warpgroup: the flattened op sequence of this CTA's slab, every copy of it
+  if (WS && warp >= WS) {
+    // ---- producer warpgroup: the flattened op sequence of one group's share of this CTA's slab, every copy of it
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
-    const int pw = warp - ncw;                                          // 0..3; serves consumer warps 2 pw, 2 pw + 1
-    const uint32_t ring0 = smem_u32(smem + p.ring_off);
-    const uint32_t ringB = ring0 + p.NPT * p.nstA * p.slotA_bytes;
-    const uint32_t bB = bars + (p.NPT * p.nstA) * 8, bEA = bars + nbar_g * 8;
+    const int ppg = s3f_producers_per_group(p.G);
+    const int g = (warp - WS) / ppg, pl = (warp - WS) % ppg;            // group served; which of its ppg producers
+    if (g >= p.G) return;
+    const uint32_t barsG = bars + g * nbar_g * 8;                       // the group's full-A barriers [warp][stage]
+    const uint32_t ringA = smem_u32(smem + p.ring_off) + g * group_bytes;
+    const uint32_t ringB = ringA + p.NPT * p.nstA * p.slotA_bytes;
+    const uint32_t bB = barsG + (p.NPT * p.nstA) * 8;
+    const uint32_t bEA = bars + (p.G * nbar_g + g * p.NPT * p.nstA) * 8;
     const uint32_t b_row_bytes = (uint32_t)(SBv * 16);
-    const int my_rows = p.R > pw ? (p.R - pw + 3) / 4 : 0;              // rows pw, pw + 4, ... of every B block
+    const int my_rows = p.R > pl ? (p.R - pl + ppg - 1) / ppg : 0;      // rows pl, pl + ppg, ... of every B block
+    // lane l issues the A copies of consumer warp l of the group (if that warp is this producer's)
+    const int a_rows = (lane < p.NPT && lane % ppg == pl) ? min(8, p.P - 8 * lane) : 0;
     int gi = -1, j = 0, x = 0, x_hi = 0;
     int slotA = 0, parA = 1, slotB = 0, parB = 1, turn = 0;
     for (;;) {
@@ -268,7 +279,7 @@ __global__ void __launch_bounds__(WS ? 384 : s3f_max_threads(NRT), 1) stage3f_ke
         ++j;
       } else {
         j = 0;
-        ++x;
+        x += p.G;
         bool done = false;
         while (gi < 0 || x >= x_hi) {
           if (++gi >= p.ngroups) {
@@ -276,7 +287,7 @@ __global__ void __launch_bounds__(WS ? 384 : s3f_max_threads(NRT), 1) stage3f_ke
             break;
           }
           const int64_t X = groupX[gi];
-          x = (int)(X * sl / NSL);
+          x = (int)(X * sl / NSL) + g;
           x_hi = (int)(X * (sl + 1) / NSL);
         }
         if (done) break;
@@ -284,16 +295,13 @@ __global__ void __launch_bounds__(WS ? 384 : s3f_max_threads(NRT), 1) stage3f_ke
       const int kind = groupKind[gi], first = groupFirst[gi];
       if (kind ? (j == 0) : (j < groupCount[gi])) {
         const cplx* A = kind ? groupCenter[gi] : termA[first + j];
-        if (lane < 2) {
-          const int cw = 2 * pw + lane;
-          const int rows = min(8, p.P - 8 * cw);
-          if (rows > 0) {
-            const uint32_t full = bars + (cw * p.nstA + slotA) * 8, bytes = (uint32_t)(rows * p.Q * 16);
-            mbar_wait(bEA + (cw * p.nstA + slotA) * 8, (uint32_t)parA);
-            mbar_arrive_expect_tx(full, bytes);
-            bulk_g2s(ring0 + (cw * p.nstA + slotA) * p.slotA_bytes, A + ((int64_t)x * p.Pfull + p.p0 + 8 * cw) * p.Q, bytes, full);
-          }
+        if (a_rows > 0) {
+          const uint32_t full = barsG + (lane * p.nstA + slotA) * 8, bytes = (uint32_t)(a_rows * p.Q * 16);
+          mbar_wait(bEA + (lane * p.nstA + slotA) * 8, (uint32_t)parA);
+          mbar_arrive_expect_tx(full, bytes);
+          bulk_g2s(ringA + (lane * p.nstA + slotA) * p.slotA_bytes, A + ((int64_t)x * p.Pfull + p.p0 + 8 * lane) * p.Q, bytes, full);
         }
+        __syncwarp();
         if (++slotA == p.nstA) {
           slotA = 0;
           parA ^= 1;
@@ -302,7 +310,7 @@ __global__ void __launch_bounds__(WS ? 384 : s3f_max_threads(NRT), 1) stage3f_ke
         const cplx* B = kind ? termB[first + j - 1] : groupCenter[gi];
         const uint32_t fullB = bB + (2 * slotB) * 8, dst = ringB + slotB * p.slotB_bytes;
         if (p.b_whole) {
-          if (turn == pw && lane == 0) {
+          if (turn == pl && lane == 0) {
             mbar_wait(fullB + 8, (uint32_t)parB);
             mbar_arrive_expect_tx(fullB, (uint32_t)(p.R * p.S * 16));
             bulk_g2s(dst, B + ((int64_t)x * p.Rfull + p.r0) * p.S, (uint32_t)(p.R * p.S * 16), fullB);
@@ -315,19 +323,19 @@ __global__ void __launch_bounds__(WS ? 384 : s3f_max_threads(NRT), 1) stage3f_ke
           }
           __syncwarp();
           const cplx* src = B + ((int64_t)x * p.Rfull + p.r0) * p.S + S0;
-          for (int rr = pw + 4 * lane; rr < p.R; rr += 128) bulk_g2s(dst + rr * BSTR * 16, src + (int64_t)rr * p.S, b_row_bytes, fullB);
+          for (int rr = pl + ppg * lane; rr < p.R; rr += 32 * ppg) bulk_g2s(dst + rr * BSTR * 16, src + (int64_t)rr * p.S, b_row_bytes, fullB);
         }
         if (++slotB == p.nstB) {
           slotB = 0;
           parB ^= 1;
         }
-        turn = (turn + 1) & 3;
+        if (++turn == ppg) turn = 0;
       }
     }
     return;
   }
+  if (WS) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(s3f_ws_consumer_registers(WS)));
   if (warp >= ncw) return;
-  if (WS) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
   {
     const int g = warp / p.NPT, wg = warp % p.NPT;
     const uint32_t bA = bars + (g * nbar_g + wg * p.nstA) * 8;          // this warp's full-A barriers
@@ -440,7 +448,7 @@ __global__ void __launch_bounds__(WS ? 384 : s3f_max_threads(NRT), 1) stage3f_ke
     // (Measured and not adopted: starting the warps that share an SM sub-partition a fraction of an op apart, so that one
     // warp's bookkeeping between two ops falls under the other's DMMAs -- no change at D = 4, 6, 8, before and after the
     // tile loops lost their predicates: the idle DMMA slots are not a phase-locking effect.)
-    const uint32_t bEA = bars + (p.G * nbar_g + wg * p.nstA) * 8;     // WS: this warp's empty-A barriers
+    const uint32_t bEA = bars + (p.G * nbar_g + (g * p.NPT + wg) * p.nstA) * 8;     // WS: this warp's empty-A barriers
     auto run_ahead = [&]() {
       if (WS) return;                   // the producer warpgroup issues the copies
       while (more) {
@@ -608,35 +616,28 @@ __global__ void __launch_bounds__(WS ? 384 : s3f_max_threads(NRT), 1) stage3f_ke
   }
 }
 
-template <int NRT, int NA>
+template <int NRT, int NA, int WS>
 int s3f_launch_one(const S3FParams& p, int ctas, int threads, cudaStream_t stream) {
   static bool configured[16] = {false};
   int dev = 0;
   CARC_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev < 16 && !configured[dev]) {
-    CARC_CHECK_CUDA(cudaFuncSetAttribute(stage3f_kernel<NRT, s3f_tiles(NRT), NA, false>,
+    CARC_CHECK_CUDA(cudaFuncSetAttribute(stage3f_kernel<NRT, s3f_tiles(NRT), NA, WS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, S3F_SMEM_LIMIT));
     configured[dev] = true;
   }
-  stage3f_kernel<NRT, s3f_tiles(NRT), NA, false><<<ctas, threads, p.smem_total, stream>>>(p);
+  stage3f_kernel<NRT, s3f_tiles(NRT), NA, WS><<<ctas, WS ? (WS + 4) * 32 : threads, p.smem_total, stream>>>(p);
   CARC_CHECK_CUDA(cudaGetLastError());
   return CARC_OK;
 }
 
-// the warp-specialised instantiation (8 consumer warps + the producer warpgroup), full-width S blocks only
-template <int NRT>
-int s3f_launch_ws(const S3FParams& p, int ctas, cudaStream_t stream) {
-  static bool configured[16] = {false};
-  int dev = 0;
-  CARC_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev < 16 && !configured[dev]) {
-    CARC_CHECK_CUDA(cudaFuncSetAttribute(stage3f_kernel<NRT, s3f_tiles(NRT), s3f_tiles(NRT), true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, S3F_SMEM_LIMIT));
-    configured[dev] = true;
-  }
-  stage3f_kernel<NRT, s3f_tiles(NRT), s3f_tiles(NRT), true><<<ctas, 384, p.smem_total, stream>>>(p);
-  CARC_CHECK_CUDA(cudaGetLastError());
-  return CARC_OK;
+// the instantiation for a launch whose S blocks hold `tiles` tiles
+template <int NRT, int WS>
+int s3f_launch_width(const S3FParams& p, int tiles, int ctas, int threads, cudaStream_t stream) {
+  constexpr int NT = s3f_tiles(NRT);
+  if (tiles == NT) return s3f_launch_one<NRT, NT, WS>(p, ctas, threads, stream);
+  if (NT > 1 && tiles == NT - 1) return s3f_launch_one<NRT, (NT > 1 ? NT - 1 : NT), WS>(p, ctas, threads, stream);
+  return s3f_launch_one<NRT, 0, WS>(p, ctas, threads, stream);
 }
 
 // A second stream per device, so that the launches of one apply (one per S-block width, together one CTA per SM) run
@@ -664,7 +665,6 @@ int s3f_side_stream(S3FSideStream** out) {
 // The widest blocks go to the caller's stream, the others (an uneven split of S has two widths) to the side stream.
 template <int NRT>
 int s3f_launch(S3FParams& p, const Stage3FConfig& k, cudaStream_t stream) {
-  constexpr int NT = s3f_tiles(NRT);
   int widths[S3F_MAX_SB + 1], nw = 0;
   for (int i = 0; i < k.NSB; ++i) {
     const int tiles = k.sb_tile0[i + 1] - k.sb_tile0[i];
@@ -685,14 +685,8 @@ int s3f_launch(S3FParams& p, const Stage3FConfig& k, cudaStream_t stream) {
     int n = 0;
     for (int c = 0; c < k.ctas; ++c)
       if (k.sb_tile0[k.cta_sb[c] + 1] - k.sb_tile0[k.cta_sb[c]] == tiles) p.cta_map[n++] = (unsigned char)c;
-    int rc;
-    static const bool ws_off = getenv("CARC_S3F_WS") && atoi(getenv("CARC_S3F_WS")) == 0;     // experiments
-    if (NRT >= 7 && !ws_off && tiles == NT && k.NPT == 8 && k.G == 1 && k.ws_barriers) {
-      if constexpr (NRT >= 7) rc = s3f_launch_ws<NRT>(p, n, st);
-      else rc = CARC_ERR_UNSUPPORTED;
-    } else if (tiles == NT) rc = s3f_launch_one<NRT, NT>(p, n, k.threads, st);
-    else if (NT > 1 && tiles == NT - 1) rc = s3f_launch_one<NRT, (NT > 1 ? NT - 1 : NT)>(p, n, k.threads, st);
-    else rc = s3f_launch_one<NRT, 0>(p, n, k.threads, st);
+    const int rc = k.ws ? s3f_launch_width<NRT, s3f_max_threads(NRT) / 32>(p, tiles, n, k.threads, st)
+                        : s3f_launch_width<NRT, 0>(p, tiles, n, k.threads, st);
     if (rc) return rc;
   }
   if (nw > 1) {
@@ -798,14 +792,17 @@ bool stage3f_configure_block(int nterms, int P, int Q, int R, int S, int d, int6
   const uint32_t vbytes = (uint32_t)(8 * nt_block * k.QS * 16);
   const uint32_t vtail_bytes = (uint32_t)(8 * nt_block * 4 * 16);
   const uint32_t obytes = (uint32_t)(nterms * d * d * 16);
-  int G = std::min(8, maxwarps / k.NPT);
+  // CARC_S3F_WS (experiments): 0 = symmetric kernels only, 8 = warp-specialised only where a warp holds 7 or 8 column
+  // tiles, otherwise (default) warp-specialised everywhere; its four producer warps serve at most four groups
+  static const int ws_env = getenv("CARC_S3F_WS") ? atoi(getenv("CARC_S3F_WS")) : 1;
+  k.ws = ws_env == 0 ? 0 : (ws_env == 8 && maxwarps != 8) ? 0 : maxwarps;
+  int G = std::min(k.ws ? 4 : 8, maxwarps / k.NPT);
   if (Xmax < G) G = (int)std::max<int64_t>(1, Xmax);
   for (; G >= 1; --G) {
     for (int nstA = 3; nstA >= 2; --nstA) {
       for (int nstB = 4; nstB >= nstA; --nstB) {
-        const bool ws = k.NPT == 8 && G == 1;      // room for the warp-specialised kernel's empty-A barriers
-        const uint32_t bar_bytes = (uint32_t)((((G * (k.NPT * nstA + 2 * nstB) + (ws ? k.NPT * nstA : 0)) * 8) + 127) / 128 * 128);
-        k.ws_barriers = ws ? 1 : 0;
+        // (the warp-specialised kernel has an empty barrier per A slot as well)
+        const uint32_t bar_bytes = (uint32_t)(((G * (k.NPT * nstA * (k.ws ? 2 : 1) + 2 * nstB) * 8) + 127) / 128 * 128);
         const uint32_t ops_off = bar_bytes;
         const uint32_t hasop_off = ops_off + obytes;
         const uint32_t tab_off = (hasop_off + (uint32_t)nterms * 4 + 15) / 16 * 16;
