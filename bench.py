@@ -537,7 +537,8 @@ def matvec_section(job, model, D, chi, d, steps, warmup, mode="xslab", gate=True
 
 
 KERNEL_NAMES = {1: "stage3_kernel (fused A.v -> O -> B^T, DMMA.8x8x4)",
-                3: "stage3f_kernel (fused A.v -> O -> B^T, spin index folded into the tile columns, DMMA.8x8x4)",
+                3: "stage3f_kernel (fused A.v -> O -> B^T, spin index folded into the tile columns, DMMA.8x8x4; TMA producer "
+                   "warpgroup + consumer warpgroups with setmaxnreg)",
                 2: "zgemm_kernel x 3 per term (unfused DMMA GEMMs)"}
 
 
@@ -737,10 +738,9 @@ def run_device(args, rank, world, local_rank):
                 "vendor_note": "torch.matmul complex128 (cuBLAS ZGEMM) and this library's zgemm_kernel on the same "
                                "4096^3 product, measured in this process: the vendor library's FP64 rate beside the "
                                "DMMA issue-rate peak and beside the fused kernel",
-                "peak_distinct_operands": 31.4,
-                "peak_note": "peak = DMMA.8x8x4 issue rate with register-resident operands; with a fresh A/B fragment "
-                             "per instruction (what any GEMM inner loop needs) the same microbenchmark tops out at "
-                             "31.4 TFLOP/s on this part (scripts/dmma_rate.py, 8 warps/SM)",
+                "peak_note": "peak = DMMA.8x8x4 issue rate (one DMMA per SM sub-partition every 16 cycles) with "
+                             "register-resident operands; the kernel's two inner loops alone, operands in shared memory, "
+                             "reach the same rate (scripts/dmma_loops.cu, profiles/r2_dmma_loops.txt)",
                 "peak_source": "DMMA.8x8x4 issue-rate microbenchmark run in this process (carc_dmma_peak); "
                                "MEASURED_PEAKS.json has no FP64 figure",
                 "algorithmic_bytes": main["bytes_local"],
