@@ -128,6 +128,10 @@ int lu_solve(const cplx* LU, int n, const int* piv, cplx* x, cudaStream_t stream
 int lu_invert_diagonal_blocks(const cplx* LU, int n, cplx* inv, cudaStream_t stream);
 int64_t lu_inverse_blocks_elems(int n);
 // *timed_out = 1 when a wavefront solve on these inverse blocks gave up waiting (sticky); synchronises the device word
+// lu_panel.cu: one 64-column panel of lu_factor by a thread-block cluster + the interchanges on all other columns;
+// CARC_ERR_UNSUPPORTED (nothing launched) when the panel is taller than a cluster holds in registers
+int lu_panel_cluster(cplx* A, int n, int j0, int nb, int* piv, int* singular, cudaStream_t stream);
+int lu_trsm_unit_lower(cplx* A, int n, int j0, int nb, int c_first, int ncols, cudaStream_t stream);
 int lu_solve_status(const cplx* inv, int n, int* timed_out);
 int lu_solve_fast(const cplx* LU, int n, const int* piv, const cplx* inv, cplx* x, cplx* tmp, cudaStream_t stream);
 int gmres(const LinOp& A, const cplx* b, cplx* x, int64_t n, double rtol, int restart, int maxiter, cplx* work,

@@ -12,6 +12,8 @@
 #include <cooperative_groups.h>
 #include <math.h>
 
+#include <cstdlib>
+
 #include <atomic>
 #include <vector>
 
@@ -363,19 +365,6 @@ __global__ void __launch_bounds__(SB) tri_invert_kernel(const cplx* __restrict__
   }
 }
 
-// inverse of the unit-lower nb x nb block at (j0, j0) into a dense [nb][nb] buffer (one thread per column)
-__global__ void __launch_bounds__(64) unit_lower_inverse_kernel(const cplx* __restrict__ A, int n, int j0, int nb,
-                                                                cplx* __restrict__ out) {
-  const int j = threadIdx.x;
-  if (j >= nb) return;
-  for (int i = 0; i < nb; ++i) out[i * nb + j] = make_double2(0.0, 0.0);
-  for (int i = j; i < nb; ++i) {
-    cplx acc = make_double2(i == j ? 1.0 : 0.0, 0.0);
-    for (int k = j; k < i; ++k) acc = csub(acc, cmul(A[(int64_t)(j0 + i) * n + j0 + k], out[k * nb + j]));
-    out[i * nb + j] = acc;
-  }
-}
-
 // one block step: solved[j0 ..] = inv_kk rhs[j0 ..]; rhs[r] -= sum_j A[r][j0 + j] solved[j0 + j] for r in [r0, r1)
 __global__ void __launch_bounds__(256) tri_step_kernel(const cplx* __restrict__ A, int n, int j0, int nb,
                                                        const cplx* __restrict__ inv_kk, cplx* __restrict__ rhs,
@@ -630,6 +619,242 @@ __device__ void small_eig_min_real(int k, const cplx* Min /* k x k row-major */,
   for (int i = 0; i < k; ++i) vec_out[i] = x[i];
 }
 
+// The same algorithm, same operations in the same order, for a compile-time dimension K <= 4 (the Krylov dimension of
+// relaxOver is 3): every loop has static bounds and run-time ranges are predicates, so that H, the rotations and the
+// elimination tableau live in registers instead of dynamically indexed local memory.  The generic routine above takes
+// ~60 us at k = 3 (a few hundred dependent local-memory round trips), which made ritz_kernel the longest kernel of a
+// restart at small bond dimensions.
+template <int K>
+__device__ void small_eig_min_real_fixed(const cplx* Min /* K x K row-major */, cplx* lambda_out, cplx* vec_out) {
+  cplx H[K][K];
+#pragma unroll
+  for (int i = 0; i < K; ++i)
+#pragma unroll
+    for (int j = 0; j < K; ++j) H[i][j] = Min[i * K + j];
+#pragma unroll
+  for (int col = 0; col + 2 < K; ++col)
+#pragma unroll
+    for (int row = K - 1; row > col + 1; --row) {
+      const cplx a = H[row - 1][col], b = H[row][col];
+      const double nb2 = cabs2(b);
+      if (nb2 != 0.0) {
+        const double r = sqrt(cabs2(a) + nb2);
+        const cplx c = cscale(a, 1.0 / r), s = cscale(b, 1.0 / r);
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          const cplx x = H[row - 1][j], y = H[row][j];
+          H[row - 1][j] = cadd(cmulc(c, x), cmulc(s, y));
+          H[row][j] = csub(cmul(c, y), cmul(s, x));
+        }
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          const cplx x = H[i][row - 1], y = H[i][row];
+          H[i][row - 1] = cadd(cmul(x, c), cmul(y, s));
+          H[i][row] = csub(cmulc(c, y), cmulc(s, x));
+        }
+      }
+    }
+  cplx ev[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) ev[i] = make_double2(0.0, 0.0);
+  int hi = K - 1;
+  int iter = 0;
+  double hnorm = 0.0;
+#pragma unroll
+  for (int i = 0; i < K; ++i)
+#pragma unroll
+    for (int j = 0; j < K; ++j) hnorm += cabs2(H[i][j]);
+  hnorm = sqrt(hnorm);
+  while (hi >= 1 && iter < 500) {
+    // deflation check: the largest l <= hi whose sub-diagonal entry is negligible (0 if none)
+    int l = 0;
+    bool found = false;
+#pragma unroll
+    for (int t = K - 1; t >= 1; --t) {
+      if (t <= hi && !found) {
+        const double sc = sqrt(cabs2(H[t - 1][t - 1])) + sqrt(cabs2(H[t][t]));
+        if (sqrt(cabs2(H[t][t - 1])) <= 2.3e-16 * (sc > 0.0 ? sc : hnorm)) {
+          H[t][t - 1] = make_double2(0.0, 0.0);
+          l = t;
+          found = true;
+        }
+      }
+    }
+    if (l == hi) {
+#pragma unroll
+      for (int t = 1; t < K; ++t)
+        if (t == hi) ev[t] = H[t][t];
+      --hi;
+      iter = 0;
+      continue;
+    }
+    cplx a = make_double2(0.0, 0.0), b = a, c = a, d = a;
+#pragma unroll
+    for (int t = 1; t < K; ++t)
+      if (t == hi) {
+        a = H[t - 1][t - 1];
+        b = H[t - 1][t];
+        c = H[t][t - 1];
+        d = H[t][t];
+      }
+    const cplx tr = cadd(a, d), det = csub(cmul(a, d), cmul(b, c));
+    const cplx disc = csub(cmul(cscale(tr, 0.5), cscale(tr, 0.5)), det);
+    const double dm = sqrt(sqrt(cabs2(disc)));
+    const double ang = 0.5 * atan2(disc.y, disc.x);
+    const cplx sq = make_double2(dm * cos(ang), dm * sin(ang));
+    const cplx e1 = cadd(cscale(tr, 0.5), sq), e2 = csub(cscale(tr, 0.5), sq);
+    cplx mu = cabs2(csub(e1, d)) < cabs2(csub(e2, d)) ? e1 : e2;
+    if (iter == 10 || iter == 20) mu = cadd(mu, make_double2(sqrt(cabs2(c)), 0.0));
+    cplx cs[K], sn[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      cs[i] = make_double2(1.0, 0.0);
+      sn[i] = make_double2(0.0, 0.0);
+      if (i >= l && i <= hi) H[i][i] = csub(H[i][i], mu);
+    }
+#pragma unroll
+    for (int i = 0; i + 1 < K; ++i) {
+      if (i >= l && i < hi) {
+        const cplx x = H[i][i], y = H[i + 1][i];
+        const double r = sqrt(cabs2(x) + cabs2(y));
+        if (r != 0.0) {
+          cs[i] = cscale(x, 1.0 / r);
+          sn[i] = cscale(y, 1.0 / r);
+#pragma unroll
+          for (int j = 0; j < K; ++j) {
+            const cplx u = H[i][j], v = H[i + 1][j];
+            H[i][j] = cadd(cmulc(cs[i], u), cmulc(sn[i], v));
+            H[i + 1][j] = csub(cmul(cs[i], v), cmul(sn[i], u));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i + 1 < K; ++i) {
+      if (i >= l && i < hi) {
+#pragma unroll
+        for (int r2 = 0; r2 < K; ++r2) {
+          const cplx u = H[r2][i], v = H[r2][i + 1];
+          H[r2][i] = cadd(cmul(u, cs[i]), cmul(v, sn[i]));
+          H[r2][i + 1] = csub(cmulc(cs[i], v), cmulc(sn[i], u));
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+      if (i >= l && i <= hi) H[i][i] = cadd(H[i][i], mu);
+    ++iter;
+  }
+  if (iter >= 500) {
+#pragma unroll
+    for (int t = K - 1; t >= 1; --t)
+      if (t <= hi) ev[t] = H[t][t];
+  }
+  ev[0] = H[0][0];
+  int best = 0;
+  cplx lam = ev[0];
+#pragma unroll
+  for (int i = 1; i < K; ++i)
+    if (ev[i].x < lam.x) {
+      best = i;
+      lam = ev[i];
+    }
+  (void)best;
+  *lambda_out = lam;
+  double mnorm = 0.0;
+#pragma unroll
+  for (int i = 0; i < K * K; ++i) mnorm += cabs2(Min[i]);
+  mnorm = sqrt(mnorm);
+  const cplx shift = cadd(lam, make_double2(1e-10 * (mnorm > 0.0 ? mnorm : 1.0), 0.0));
+  cplx x[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) x[i] = make_double2(1.0 / (1.0 + i), 0.3 / (2.0 + i));
+  for (int it = 0; it < 3; ++it) {
+    cplx M[K][K + 1];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) M[i][j] = Min[i * K + j];
+      M[i][i] = csub(M[i][i], shift);
+      M[i][K] = x[i];
+    }
+#pragma unroll
+    for (int col = 0; col < K; ++col) {
+      int pr = col;
+      double pv = cabs2(M[col][col]);
+#pragma unroll
+      for (int r = col + 1; r < K; ++r)
+        if (cabs2(M[r][col]) > pv) {
+          pr = r;
+          pv = cabs2(M[r][col]);
+        }
+#pragma unroll
+      for (int r = col + 1; r < K; ++r)
+        if (r == pr) {
+#pragma unroll
+          for (int j = 0; j <= K; ++j) {
+            const cplx t = M[col][j];
+            M[col][j] = M[r][j];
+            M[r][j] = t;
+          }
+        }
+      if (cabs2(M[col][col]) < 1e-300) M[col][col] = make_double2(1e-150, 0.0);
+#pragma unroll
+      for (int r = col + 1; r < K; ++r) {
+        const cplx f = cdiv(M[r][col], M[col][col]);
+#pragma unroll
+        for (int j = col; j <= K; ++j) M[r][j] = csub(M[r][j], cmul(f, M[col][j]));
+      }
+    }
+#pragma unroll
+    for (int r = K - 1; r >= 0; --r) {
+      cplx acc = M[r][K];
+#pragma unroll
+      for (int j = r + 1; j < K; ++j) acc = csub(acc, cmul(M[r][j], x[j]));
+      x[r] = cdiv(acc, M[r][r]);
+    }
+    double nx = 0.0;
+#pragma unroll
+    for (int i = 0; i < K; ++i) nx += cabs2(x[i]);
+    nx = 1.0 / sqrt(nx);
+#pragma unroll
+    for (int i = 0; i < K; ++i) x[i] = cscale(x[i], nx);
+  }
+  int big = 0;
+  double bigv = cabs2(x[0]);
+#pragma unroll
+  for (int i = 1; i < K; ++i)
+    if (cabs2(x[i]) > bigv) {
+      big = i;
+      bigv = cabs2(x[i]);
+    }
+  const double mod = sqrt(bigv);
+  if (mod > 0.0) {
+    cplx xb = x[0];
+#pragma unroll
+    for (int i = 1; i < K; ++i)
+      if (i == big) xb = x[i];
+    const cplx ph = make_double2(xb.x / mod, -xb.y / mod);
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      x[i] = cmul(x[i], ph);
+      if (i == big) x[i].y = 0.0;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < K; ++i) vec_out[i] = x[i];
+}
+
+__device__ void small_eig_dispatch(int k, const cplx* Min, cplx* lambda_out, cplx* vec_out) {
+  switch (k) {
+    case 1: small_eig_min_real_fixed<1>(Min, lambda_out, vec_out); break;
+    case 2: small_eig_min_real_fixed<2>(Min, lambda_out, vec_out); break;
+    case 3: small_eig_min_real_fixed<3>(Min, lambda_out, vec_out); break;
+    case 4: small_eig_min_real_fixed<4>(Min, lambda_out, vec_out); break;
+    default: small_eig_min_real(k, Min, lambda_out, vec_out); break;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Arnoldi state shared by the kernels below (device memory)
 struct RelaxState {
@@ -702,8 +927,10 @@ __global__ void __launch_bounds__(VT) arnoldi_step_kernel(cplx* __restrict__ V, 
 }
 
 // projected matrix (utils.py:862), its lowest-real-part eigenpair (863-866), and the normalised Ritz vector
-// written to `next` (869-870 / 875-876).
-__global__ void __launch_bounds__(VT) ritz_kernel(const cplx* __restrict__ V, const cplx* __restrict__ MV, int64_t n,
+// written to `next` (869-870 / 875-876) and to row 0 of V, with the basis count reset: the start of the next restart.
+// (256 threads: thread 0's register-resident eigen-solver needs more than the 64 registers a 1024-thread CTA allows)
+constexpr int RITZ_THREADS = 256;
+__global__ void __launch_bounds__(RITZ_THREADS) ritz_kernel(cplx* __restrict__ V, const cplx* __restrict__ MV, int64_t n,
                                                   int kmax, cplx* __restrict__ next, RelaxState* __restrict__ st) {
   __shared__ cplx sh[32 * KMAX];
   __shared__ cplx small[KMAX * KMAX];
@@ -713,7 +940,7 @@ __global__ void __launch_bounds__(VT) ritz_kernel(const cplx* __restrict__ V, co
     cplx c[KMAX];
 #pragma unroll
     for (int j = 0; j < KMAX; ++j) c[j] = make_double2(0.0, 0.0);
-    for (int64_t e = threadIdx.x; e < n; e += VT) {
+    for (int64_t e = threadIdx.x; e < n; e += RITZ_THREADS) {
       const cplx va = V[(int64_t)a * n + e];
 #pragma unroll
       for (int j = 0; j < KMAX; ++j)
@@ -727,13 +954,13 @@ __global__ void __launch_bounds__(VT) ritz_kernel(const cplx* __restrict__ V, co
   if (threadIdx.x == 0) {
     cplx lam;
     cplx vec[KMAX];
-    small_eig_min_real(kk, small, &lam, vec);
+    small_eig_dispatch(kk, small, &lam, vec);
     st->ritz = lam;
     for (int j = 0; j < kk; ++j) y[j] = vec[j];
   }
   __syncthreads();
   cplx nrm[1] = {make_double2(0.0, 0.0)};
-  for (int64_t e = threadIdx.x; e < n; e += VT) {
+  for (int64_t e = threadIdx.x; e < n; e += RITZ_THREADS) {
     cplx acc = make_double2(0.0, 0.0);
     for (int j = 0; j < kk; ++j) acc = cadd(acc, cmul(y[j], V[(int64_t)j * n + e]));
     next[e] = acc;
@@ -741,7 +968,12 @@ __global__ void __launch_bounds__(VT) ritz_kernel(const cplx* __restrict__ V, co
   }
   block_csum<1>(nrm, sh);
   const double inv = 1.0 / sqrt(nrm[0].x);
-  for (int64_t e = threadIdx.x; e < n; e += VT) next[e] = cscale(next[e], inv);
+  for (int64_t e = threadIdx.x; e < n; e += RITZ_THREADS) {
+    const cplx val = cscale(next[e], inv);
+    next[e] = val;
+    V[e] = val;   // (this thread read V[j * n + e] for every j in the loop above)
+  }
+  if (threadIdx.x == 0) st->kk = 1;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -928,58 +1160,75 @@ static int g_coop_ctas = 0;
 
 size_t lu_scratch_bytes() { return sizeof(LuCand); }
 
+// Two-level blocking: panels of 64 columns (the width the panel kernels factorise) inside outer blocks of 256 or 512.
+// After a panel only the remaining columns of its outer block are updated (K = 64 products on few columns); the rest of
+// the matrix sees ONE product per outer block with K = 256 / 512, where zgemm_kernel runs at its large-K rate -- with K = 64
+// trailing updates it spent 146 of the 230 ms at n = 8192 re-reading and re-writing the trailing matrix (10 TFLOP/s).
+// The U block rows are triangular solves with the unit-lower diagonal blocks (lu_trsm_unit_lower).
 int lu_factor(cplx* A, int n, int* piv, int* singular_dev, cplx* scratch, cudaStream_t stream) {
-  if (g_coop_ctas == 0) {
-    int dev = 0, sms = 0, per_sm = 0;
-    CARC_CHECK_CUDA(cudaGetDevice(&dev));
-    CARC_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    CARC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lu_panel_coop_kernel, 256, 0));
-    g_coop_ctas = per_sm > 0 ? sms : 0;   // one CTA per SM (fewer, larger CTAs measured slower)
-    CARC_REQUIRE(g_coop_ctas > 0, CARC_ERR_UNSUPPORTED, "lu_factor: cooperative launch unavailable");
-  }
   CARC_REQUIRE(n >= 1, CARC_ERR_VALUE, "lu_factor: n must be positive");
   const int NB = 64;
+  static const int outer_env = getenv("CARC_LU_OUTER") ? atoi(getenv("CARC_LU_OUTER")) : 0;   // experiments
+  const int OB = outer_env >= NB ? outer_env / NB * NB : n >= 6144 ? 512 : 256;   // n = 8192: 173 / 156 / 149 ms at 128 / 256 / 512
   const cplx minus_one = make_double2(-1.0, 0.0), one = make_double2(1.0, 0.0);
   CARC_CHECK_CUDA(cudaMemsetAsync(singular_dev, 0, sizeof(int), stream));
-  cplx* linv = nullptr;
-  CARC_CHECK_CUDA(cudaMallocAsync((void**)&linv, sizeof(cplx) * 64 * 64, stream));
-  for (int j0 = 0; j0 < n; j0 += NB) {
-    const int nb = n - j0 < NB ? n - j0 : NB;
-    const int pe = j0 + nb;
-    {
-      // one cooperative launch per panel (falls back to the per-column kernels if the device refuses)
-      LuCand* cand = reinterpret_cast<LuCand*>(scratch);
-      int rows = n - j0;
-      int ctas = (rows + 7) / 8;   // (the rank-w update uses one warp per row, 8 warps per CTA)
-      if (ctas > g_coop_ctas) ctas = g_coop_ctas;
-      if (ctas < 1) ctas = 1;
-      int nn = n, jj = j0, nbb = nb;
-      void* args[] = {(void*)&A, (void*)&nn, (void*)&jj, (void*)&nbb, (void*)&piv, (void*)&singular_dev, (void*)&cand};
-      CARC_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)lu_panel_coop_kernel, dim3(ctas), dim3(256), args, 0, stream));
-    }
-    if (pe < n) {
-      const int cols = n - pe;
-      // U12 = L11^-1 A12 as a DMMA GEMM with the explicitly inverted 64 x 64 unit-lower block (in place: each CTA
-      // reads all K rows of its own columns before its epilogue writes them; M = nb <= 128 is a single row tile)
-      unit_lower_inverse_kernel<<<1, 64, 0, stream>>>(A, n, j0, nb, linv);
-      {
-        GemmOut ou;
-        ou.m_div = n; ou.m_s1 = 0; ou.m_s0 = n;
-        ou.n_div = n; ou.n_s1 = 0; ou.n_s0 = 1;
-        int rc2 = zgemm(OP_N, OP_N, nb, cols, nb, one, linv, nb, A + (int64_t)j0 * n + pe, n, make_double2(0.0, 0.0),
-                        A + (int64_t)j0 * n + pe, &ou, nullptr, 1, 0, 0, 0, stream);
-        if (rc2) return rc2;
+  // C[r0 : r0 + M, c0 : c0 + N] -= A[r0 : r0 + M, k0 : k0 + K] A[k0 : k0 + K, c0 : c0 + N], all blocks of the same matrix
+  auto update = [&](int r0, int M, int c0, int N, int k0, int K) -> int {
+    if (M <= 0 || N <= 0 || K <= 0) return CARC_OK;
+    GemmOut o;
+    o.m_div = n; o.m_s1 = 0; o.m_s0 = n;
+    o.n_div = n; o.n_s1 = 0; o.n_s0 = 1;
+    return zgemm(OP_N, OP_N, M, N, K, minus_one, A + (int64_t)r0 * n + k0, n, A + (int64_t)k0 * n + c0, n, one,
+                 A + (int64_t)r0 * n + c0, &o, nullptr, 1, 0, 0, 0, stream);
+  };
+  for (int o0 = 0; o0 < n; o0 += OB) {
+    const int o1 = n - o0 < OB ? n : o0 + OB;
+    for (int j0 = o0; j0 < o1; j0 += NB) {
+      const int nb = o1 - j0 < NB ? o1 - j0 : NB;
+      const int pe = j0 + nb;
+      // the panel: one thread-block cluster with the sub-panel in registers (lu_panel.cu); panels taller than a cluster
+      // holds (n - j0 > 20480) take the cooperative kernel with grid-wide barriers
+      const int prc = lu_panel_cluster(A, n, j0, nb, piv, singular_dev, stream);
+      if (prc != CARC_OK && prc != CARC_ERR_UNSUPPORTED) return prc;
+      if (prc == CARC_ERR_UNSUPPORTED) {
+        if (g_coop_ctas == 0) {
+          int dev = 0, sms = 0, per_sm = 0;
+          CARC_CHECK_CUDA(cudaGetDevice(&dev));
+          CARC_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+          CARC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lu_panel_coop_kernel, 256, 0));
+          g_coop_ctas = per_sm > 0 ? sms : 0;   // one CTA per SM (fewer, larger CTAs measured slower)
+          CARC_REQUIRE(g_coop_ctas > 0, CARC_ERR_UNSUPPORTED, "lu_factor: cooperative launch unavailable");
+        }
+        LuCand* cand = reinterpret_cast<LuCand*>(scratch);
+        int rows = n - j0;
+        int ctas = (rows + 7) / 8;   // (the rank-w update uses one warp per row, 8 warps per CTA)
+        if (ctas > g_coop_ctas) ctas = g_coop_ctas;
+        if (ctas < 1) ctas = 1;
+        int nn = n, jj = j0, nbb = nb;
+        void* args[] = {(void*)&A, (void*)&nn, (void*)&jj, (void*)&nbb, (void*)&piv, (void*)&singular_dev, (void*)&cand};
+        CARC_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)lu_panel_coop_kernel, dim3(ctas), dim3(256), args, 0, stream));
       }
-      // A22 -= L21 U12
-      GemmOut o;
-      o.m_div = n; o.m_s1 = 0; o.m_s0 = n;
-      o.n_div = n; o.n_s1 = 0; o.n_s0 = 1;
-      int rc = zgemm(OP_N, OP_N, cols, cols, nb, minus_one, A + (int64_t)pe * n + j0, n, A + (int64_t)j0 * n + pe, n, one,
-                     A + (int64_t)pe * n + pe, &o, nullptr, 1, 0, 0, 0, stream);
+      if (pe < o1) {
+        // inside the outer block: U block row and rank-nb update of the block's remaining columns only
+        int rc = lu_trsm_unit_lower(A, n, j0, nb, pe, o1 - pe, stream);
+        if (rc) return rc;
+        rc = update(pe, n - pe, pe, o1 - pe, j0, nb);
+        if (rc) return rc;
+      }
+    }
+    if (o1 < n) {
+      // the outer block's U block row on the columns to the right (block forward substitution), then the trailing matrix
+      for (int j0 = o0; j0 < o1; j0 += NB) {
+        const int pe = o1 - j0 < NB ? o1 : j0 + NB;
+        int rc = lu_trsm_unit_lower(A, n, j0, pe - j0, o1, n - o1, stream);
+        if (rc) return rc;
+        rc = update(pe, o1 - pe, o1, n - o1, j0, pe - j0);
+        if (rc) return rc;
+      }
+      const int rc = update(o1, n - o1, o1, n - o1, o0, o1 - o0);
       if (rc) return rc;
     }
   }
-  CARC_CHECK_CUDA(cudaFreeAsync(linv, stream));
   CARC_CHECK_CUDA(cudaGetLastError());
   return CARC_OK;
 }
@@ -1392,9 +1641,10 @@ int relax(const LinOp& M, cplx* v, int64_t n, int max_mults, double tol, int k, 
   double last_re = 0.0, last_im = 0.0;
   bool complete = (int64_t)k == n;
   RelaxState host;
+  CARC_CHECK_CUDA(cudaMemcpyAsync(V, v, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, stream));
+  restart_kernel<<<1, 1, 0, stream>>>(st);
   for (;;) {
-    CARC_CHECK_CUDA(cudaMemcpyAsync(V, v, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, stream));
-    restart_kernel<<<1, 1, 0, stream>>>(st);
+    // (later restarts: ritz_kernel has left the Ritz vector in row 0 of V and reset the basis count)
     for (int i = 0; i < k; ++i) {
       // after a breakdown the remaining multiplications act on stale rows and are ignored by the Ritz step; the
       // reference stops multiplying at that point (utils.py:854-858) -- so do we, at the next host check below
@@ -1411,7 +1661,7 @@ int relax(const LinOp& M, cplx* v, int64_t n, int max_mults, double tol, int k, 
       }
     }
     mults += k;
-    ritz_kernel<<<1, VT, 0, stream>>>(V, MV, n, k, v, st);
+    ritz_kernel<<<1, RITZ_THREADS, 0, stream>>>(V, MV, n, k, v, st);
     CARC_CHECK_CUDA(cudaMemcpyAsync(&host, st, sizeof(RelaxState), cudaMemcpyDeviceToHost, stream));
     CARC_CHECK_CUDA(cudaStreamSynchronize(stream));
     // a timed-out peer exchange or wavefront solve hands back NaNs (comm.cu, tri_wavefront_kernel): stop here instead of

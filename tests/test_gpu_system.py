@@ -342,7 +342,8 @@ def test_relax_over_decreases_and_converges(dd, n):
     assert np.vdot(res, h @ res).real < (np.vdot(v0, h @ v0) / np.vdot(v0, v0)).real
 
 
-@pytest.mark.parametrize("n", [1, 5, 64, 65, 128, 129, 200, 513, 2100])
+# (n = 4500: panels taller than 4096 rows keep two rows per thread in the cluster panel kernel, csrc/lu_panel.cu)
+@pytest.mark.parametrize("n", [1, 5, 64, 65, 128, 129, 200, 513, 1030, 2100, 4500])
 def test_lu_and_gmres(dd, n):
     import ctypes as C
     from carcassonne_b200.compression import _gmres_dense
