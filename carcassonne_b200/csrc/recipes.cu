@@ -406,7 +406,7 @@ int carc_form_stage1(const void* corner, const int64_t* c, const void* side, con
 // `out` holds that slab (multi-GPU).
 int carc_form_stage2(const void* stage1_a, const int64_t* a, const void* stage1_b, const int64_t* b, int half, int slab_rank,
                      int slab_world, void* out, int accumulate, void* stream) {
-  CARC_REQUIRE(stage1_a && a && stage1_b && b && out && half >= -1 && half <= 1, CARC_ERR_VALUE, "form_stage2: invalid argument");
+  CARC_REQUIRE(stage1_a && a && stage1_b && b && half >= -1 && half <= 1, CARC_ERR_VALUE, "form_stage2: invalid argument");
   CARC_REQUIRE(a[0] == b[1], CARC_ERR_DIMENSION_MISMATCH,
                "tensor 0's index 0 has dimension %lld, whereas tensor 1's index 1 has dimension %lld", (long long)a[0],
                (long long)b[1]);
@@ -415,6 +415,7 @@ int carc_form_stage2(const void* stage1_a, const int64_t* a, const void* stage1_
   const cplx* A = (const cplx*)stage1_a;
   const cplx* B = (const cplx*)stage1_b;
   if (half < 0) {
+    CARC_REQUIRE(out, CARC_ERR_VALUE, "form_stage2: invalid argument (no output buffer)");
     CARC_REQUIRE(slab_world <= 1, CARC_ERR_VALUE, "form_stage2: X slabs exist only in the stage-3 layouts (half = 0 or 1)");
     const auto st = row_major_strides({a[1], a[2], b[2], a[3], b[3]});
     return gemm_scatter(OP_T, OP_N, lda, N, K, A, lda, B, N, (cplx*)out, Levels{{a[1], st[0]}, {a[2], st[1]}, {a[3], st[3]}},
@@ -429,6 +430,8 @@ int carc_form_stage2(const void* stage1_a, const int64_t* a, const void* stage1_
     lo = slow * slab_rank / slab_world;
     hi = slow * (slab_rank + 1) / slab_world;
   }
+  if (hi <= lo) return CARC_OK;   // more ranks than entries of the slow factor of X: this rank's slab (and `out`) is empty
+  CARC_REQUIRE(out, CARC_ERR_VALUE, "form_stage2: invalid argument (no output buffer)");
   const int64_t n_b0 = half == 0 ? hi - lo : b[0], n_a1 = half == 0 ? a[1] : hi - lo;
   const int64_t rest = a[3] * b[3] * a[2] * b[2];
   const auto st = row_major_strides({a[3], b[3], a[2], b[2]});

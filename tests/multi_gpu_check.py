@@ -99,8 +99,9 @@ def system_level_checks(rank, world):
         return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
     # (chi, D, absorptions before the check, force GMRES for N^-1)
+    # (chi = 1 without absorptions: the slow factor of X has ONE entry, so every rank but the last holds an EMPTY slab)
     cases = [(2, 2, (0, 1, 2, 3), False), (3, 3, (0, 1), False), (1, 2, (0, 1, 2, 3), False), (4, 4, (0, 2), False),
-             (2, 3, (0, 1, 2, 3), True), (5, 2, (1,), False)]
+             (2, 3, (0, 1, 2, 3), True), (5, 2, (1,), False), (1, 2, (), False), (1, 3, (0,), False)]
     for chi, D, walk, force_gmres in cases:
         base = synthetic.device_system(chi, D, J=0.7, seed=10 + chi + D)
         for direction in walk:
