@@ -5,16 +5,22 @@
 // here: stage-1 / stage-2 environment builds, side->corner and center->side absorption, formMatrix, the
 // compression normal equations, absorbMatrixAt.
 //
-// Layout: CTA tile 128 x 64 x 16 (complex), 8 warps as 4 (M) x 2 (N), warp tile 32 x 32 = 4 x 4 DMMA tiles with
-// separate real / imaginary accumulators (128 registers).  Operands are staged by a 3-stage cp.async pipeline
-// into K-contiguous shared tiles with an odd row stride (17 complex) so that the paired fragment loads below
-// are bank-conflict free.  A complex MMA is four real DMMAs; the sign of the imaginary operand is flipped once
+// Layout: CTA tile 128 x 64 x 16 (complex), 8 consumer warps as 4 (M) x 2 (N), warp tile 32 x 32 = 4 x 4 DMMA tiles with
+// separate real / imaginary accumulators (128 registers).  Operands are staged into K-contiguous shared tiles with an
+// odd row stride (17 complex) so that the paired fragment loads below are bank-conflict free.
+// Staging is warp-specialised (template WS = true, the default): a fourth warpgroup of 4 PRODUCER warps computes the
+// generalised source addresses and issues the cp.async copies of a k-tile (their completion arrives on the stage's
+// "full" mbarrier: cp.async.mbarrier.arrive.noinc), the 8 consumer warps wait -> DMMA -> release ("empty" mbarrier);
+// `setmaxnreg` gives the consumers 216 registers and leaves the producers 72; 4 stages.  The symmetric variant
+// (WS = false, CARC_ZGEMM_WS=0: every warp copies and multiplies, a CTA-wide barrier per k-tile, 3 stages) is what round 1
+// measured at 27.0 TFLOP/s on 4096^3.  A complex MMA is four real DMMAs; the sign of the imaginary operand is flipped once
 // per fragment load (integer XOR on the sign bit), which is also how conjugated operands are handled.
 //
 // Fragment mapping: one 8-wide K chunk feeds two DMMA k-steps.  k-step e in {0,1} uses the K indices
 // {2c + e : c = lane % 4}, i.e. every lane reads two adjacent complex numbers (32 contiguous bytes) per
 // operand row.  Any permutation of K is legal as long as A and B use the same one.
 #include <algorithm>
+#include <cstdlib>
 
 #include "carc_internal.h"
 #include "common.cuh"
@@ -26,6 +32,8 @@ namespace {
 constexpr int BM = 128, BN = 64, BK = 16, STAGES = 3, LDK = BK + 1;
 constexpr int NTHREADS = 256;
 constexpr int SMEM_BYTES = STAGES * (BM + BN) * LDK * (int)sizeof(cplx);
+constexpr int STAGES_WS = 4, NPRODUCERS = 128, NTHREADS_WS = NTHREADS + NPRODUCERS;
+constexpr int SMEM_BYTES_WS = STAGES_WS * (BM + BN) * LDK * (int)sizeof(cplx) + 2 * STAGES_WS * 8;
 
 struct GemmParams {
   const cplx* A;
@@ -53,10 +61,18 @@ __device__ __forceinline__ double flip(double x, uint32_t mask) {
   return __hiloint2double(__double2hiint(x) ^ (int)mask, __double2loint(x));
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) zgemm_kernel(GemmParams p) {
+__device__ __forceinline__ void cp_async_arrive_on(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+
+template <bool WS>
+__global__ void __launch_bounds__(WS ? NTHREADS_WS : NTHREADS, 1) zgemm_kernel(GemmParams p) {
+  constexpr int NST = WS ? STAGES_WS : STAGES;
+  constexpr int NLOAD = WS ? NPRODUCERS : NTHREADS;   // threads that issue the copies of a k-tile
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx* As = reinterpret_cast<cplx*>(smem_raw);
-  cplx* Bs = As + STAGES * BM * LDK;
+  cplx* Bs = As + NST * BM * LDK;
+  const uint32_t bars = smem_u32(Bs + NST * BN * LDK);   // WS: full[NST], empty[NST]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1;       // 4 x 2 warps
@@ -83,13 +99,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) zgemm_kernel(GemmParams p) {
   const int64_t kt0 = split ? (int64_t)blockIdx.z * p.kt_per_split : 0;
   const int64_t KT = split ? min(p.kt_per_split, KT_all - kt0) : KT_all;
 
+  const int ltid = WS ? tid - NTHREADS : tid;
   auto load_tile = [&](int64_t kt, int stage) {
     const int64_t k0 = (kt0 + kt) * BK;
     cplx* as = As + stage * BM * LDK;
     cplx* bs = Bs + stage * BN * LDK;
 #pragma unroll
-    for (int it = 0; it < BM * BK / NTHREADS; ++it) {
-      int e = it * NTHREADS + tid;
+    for (int it = 0; it < BM * BK / NLOAD; ++it) {
+      int e = it * NLOAD + ltid;
       int m, k;
       if (p.a_kcontig) { m = e / BK; k = e % BK; } else { k = e / BM; m = e % BM; }
       int64_t gm = m0 + m, gk = k0 + k;
@@ -99,8 +116,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) zgemm_kernel(GemmParams p) {
       cp_async16(smem_u32(as + m * LDK + k), src, ok);
     }
 #pragma unroll
-    for (int it = 0; it < BN * BK / NTHREADS; ++it) {
-      int e = it * NTHREADS + tid;
+    for (int it = 0; it < BN * BK / NLOAD; ++it) {
+      int e = it * NLOAD + ltid;
       int n, k;
       if (p.b_kcontig) { n = e / BK; k = e % BK; } else { k = e / BN; n = e % BN; }
       int64_t gn = n0 + n, gk = k0 + k;
@@ -111,21 +128,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) zgemm_kernel(GemmParams p) {
     }
   };
 
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < KT) load_tile(s, s);
-    cp_async_commit();
-  }
-
-  for (int64_t kt = 0; kt < KT; ++kt) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    {
-      int64_t nk = kt + STAGES - 1;
-      if (nk < KT) load_tile(nk, (int)(nk % STAGES));
-      cp_async_commit();
-    }
-    const int stage = (int)(kt % STAGES);
+  // one k-tile of the warp's 32 x 32 block
+  auto multiply_tile = [&](int stage) {
     const uint32_t as = smem_u32(As + stage * BM * LDK + (wm * 32 + r) * LDK + 2 * c);
     const uint32_t bs = smem_u32(Bs + stage * BN * LDK + (wn * 32 + r) * LDK + 2 * c);
 #pragma unroll
@@ -152,8 +156,63 @@ __global__ void __launch_bounds__(NTHREADS, 1) zgemm_kernel(GemmParams p) {
         }
       }
     }
+  };
+
+  if (WS) {
+    if (tid == 0) {
+      for (int s = 0; s < NST; ++s) {
+        mbar_init(bars + s * 8, NPRODUCERS);          // full: one arrival per producer thread, when its copies have landed
+        mbar_init(bars + (NST + s) * 8, NTHREADS / 32);   // empty: one arrival per consumer warp
+      }
+      fence_barrier_init();
+    }
+    __syncthreads();
+    if (warp >= NTHREADS / 32) {
+      // ---- producers (72 registers: the generalised addresses are 64-bit arithmetic)
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
+      int stage = 0, parity = 1;     // parity of the EMPTY barrier's phase that frees the stage (first round: free already)
+      for (int64_t kt = 0; kt < KT; ++kt) {
+        if (kt >= NST) mbar_wait(bars + (NST + stage) * 8, (uint32_t)parity);
+        load_tile(kt, stage);
+        cp_async_arrive_on(bars + stage * 8);
+        if (++stage == NST) {
+          stage = 0;
+          parity ^= 1;
+        }
+      }
+      cp_async_wait<0>();
+      return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;\n");
+    int stage = 0, parity = 0;
+    for (int64_t kt = 0; kt < KT; ++kt) {
+      mbar_wait(bars + stage * 8, (uint32_t)parity);
+      multiply_tile(stage);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + (NST + stage) * 8);
+      if (++stage == NST) {
+        stage = 0;
+        parity ^= 1;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < NST - 1; ++s) {
+      if (s < KT) load_tile(s, s);
+      cp_async_commit();
+    }
+    for (int64_t kt = 0; kt < KT; ++kt) {
+      cp_async_wait<NST - 2>();
+      __syncthreads();
+      {
+        int64_t nk = kt + NST - 1;
+        if (nk < KT) load_tile(nk, (int)(nk % NST));
+        cp_async_commit();
+      }
+      multiply_tile((int)(kt % NST));
+    }
+    cp_async_wait<0>();
   }
-  cp_async_wait<0>();
 
   // epilogue: C = alpha * acc + beta * C at the generalised address
   const bool use_beta = !(p.beta.x == 0.0 && p.beta.y == 0.0);
@@ -432,12 +491,18 @@ int zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, cplx alpha, const c
   CARC_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 0, CARC_ERR_VALUE, "zgemm: negative dimension");
   if (M == 0 || N == 0 || batch == 0) return CARC_OK;
   static bool configured[16] = {false};
+  static const bool ws = !(getenv("CARC_ZGEMM_WS") && atoi(getenv("CARC_ZGEMM_WS")) == 0);   // 0: the symmetric kernel
   int dev = 0;
   CARC_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev < 16 && !configured[dev]) {
-    CARC_CHECK_CUDA(cudaFuncSetAttribute(zgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    CARC_CHECK_CUDA(cudaFuncSetAttribute(zgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    CARC_CHECK_CUDA(cudaFuncSetAttribute(zgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_WS));
     configured[dev] = true;
   }
+  auto launch = [&](dim3 grid, const GemmParams& q) {
+    if (ws) zgemm_kernel<true><<<grid, NTHREADS_WS, SMEM_BYTES_WS, stream>>>(q);
+    else zgemm_kernel<false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(q);
+  };
   GemmParams p;
   p.A = A; p.B = B; p.C = C;
   p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb;
@@ -494,7 +559,7 @@ int zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, cplx alpha, const c
       q.out.m_div = M; q.out.m_s1 = 0; q.out.m_s0 = N;
       q.out.n_div = N; q.out.n_s1 = 0; q.out.n_s0 = 1;
       dim3 grid((unsigned)(gx * gy), 1, (unsigned)splits);
-      zgemm_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(q);
+      launch(grid, q);
       const int64_t total = M * N;
       splitk_reduce_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 148 * 8), 256, 0, stream>>>(ws, (int)splits, p);
       CARC_CHECK_CUDA(cudaGetLastError());
@@ -503,7 +568,7 @@ int zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, cplx alpha, const c
     }
   }
   dim3 grid((unsigned)(gx * gy), 1, (unsigned)batch);
-  zgemm_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(p);
+  launch(grid, p);
   CARC_CHECK_CUDA(cudaGetLastError());
   return CARC_OK;
 }
