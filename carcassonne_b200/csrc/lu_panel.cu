@@ -492,6 +492,7 @@ int lu_panel_cluster(cplx* A, int n, int j0, int nb, int* piv, int* singular, cu
   const int rows = n - j0;
   int rc;
   if (rows <= 8 * 512) rc = launch_panel<512, 1>(A, n, j0, nb, piv, singular, rows <= 512 ? 1 : rows <= 1024 ? 2 : rows <= 2048 ? 4 : 8, stream);
+  else if (rows <= 16 * 512 && panel_cluster_limit() >= 16) rc = launch_panel<512, 1>(A, n, j0, nb, piv, singular, 16, stream);
   else if (rows <= 8 * 512 * 2) rc = launch_panel<512, 2>(A, n, j0, nb, piv, singular, 8, stream);
   else if (rows <= 16 * 512 * 2 && panel_cluster_limit() >= 16) rc = launch_panel<512, 2>(A, n, j0, nb, piv, singular, 16, stream);
   else if (rows <= 16 * 256 * 5 && panel_cluster_limit() >= 16) rc = launch_panel<256, 5>(A, n, j0, nb, piv, singular, 16, stream);
