@@ -491,7 +491,11 @@ int lu_panel_cluster(cplx* A, int n, int j0, int nb, int* piv, int* singular, cu
   if (off || nb > PANEL) return CARC_ERR_UNSUPPORTED;
   const int rows = n - j0;
   int rc;
-  if (rows <= 8 * 512) rc = launch_panel<512, 1>(A, n, j0, nb, piv, singular, rows <= 512 ? 1 : rows <= 1024 ? 2 : rows <= 2048 ? 4 : 8, stream);
+  // up to 4096 rows: 256-thread CTAs and twice as many of them (a column step is issue-bound per SM: n = 2592 24.6 -> 22.0 ms)
+  static const bool wide = !(getenv("CARC_LU_WIDE") && atoi(getenv("CARC_LU_WIDE")) == 0);
+  if (wide && rows <= 16 * 256 && rows > 256 && panel_cluster_limit() >= 16)
+    rc = launch_panel<256, 1>(A, n, j0, nb, piv, singular, rows <= 512 ? 2 : rows <= 1024 ? 4 : rows <= 2048 ? 8 : 16, stream);
+  else if (rows <= 8 * 512) rc = launch_panel<512, 1>(A, n, j0, nb, piv, singular, rows <= 512 ? 1 : rows <= 1024 ? 2 : rows <= 2048 ? 4 : 8, stream);
   else if (rows <= 16 * 512 && panel_cluster_limit() >= 16) rc = launch_panel<512, 1>(A, n, j0, nb, piv, singular, 16, stream);
   else if (rows <= 8 * 512 * 2) rc = launch_panel<512, 2>(A, n, j0, nb, piv, singular, 8, stream);
   else if (rows <= 16 * 512 * 2 && panel_cluster_limit() >= 16) rc = launch_panel<512, 2>(A, n, j0, nb, piv, singular, 16, stream);
