@@ -395,69 +395,91 @@ __global__ void __launch_bounds__(256) tri_step_kernel(const cplx* __restrict__ 
 
 // Wavefront substitution: ONE launch per triangular factor.  CTA c owns row block k (k = c for L, nblk-1-c for U),
 // folds the solved blocks x_j into its right-hand side as soon as their flags appear (in dependency order), then
-// publishes x_k.  The SB x SB matrix block of the next step is prefetched into shared memory BEFORE its flag is
-// awaited and the inverse diagonal block sits in shared memory from the start, so what remains on the critical path
-// of a step is a 64-element read, two small shared-memory products and the flag hand-off.  All CTAs are co-resident
-// (nblk <= 148 => n <= 9472); waits are bounded and raise a sticky error flag instead of hanging.
+// publishes x_k.  The SB x SB matrix block of a step does not depend on x: thread (row r, quarter q) holds its 16
+// entries in registers and loads those of the NEXT step before it waits for this step's flag (double-buffered register
+// sets -- the first version staged each block through shared memory with synchronous loads, 8.6 us per step, and the
+// last CTA's ~127 sequential steps were the whole 1.1 ms of a solve at n = 8192).  The inverse diagonal block sits in
+// shared memory from the start, so what remains on the critical path of a step is a 64-element read, two small products
+// and the flag hand-off.  All CTAs are co-resident (nblk <= 148 => n <= 9472); waits are bounded and raise a sticky error
+// flag instead of hanging.  `rhs` / `perm`: the right-hand side is read as rhs[perm[i]] (the row interchanges of the
+// factorisation as one gather, see lu_perm_build_kernel), or in place from x when rhs is null.
 __global__ void __launch_bounds__(256) tri_wavefront_kernel(const cplx* __restrict__ A, int n, int nblk,
                                                             const cplx* __restrict__ inv, cplx* __restrict__ x,
                                                             unsigned long long* __restrict__ flags,
-                                                            unsigned long long epoch, int upper) {
+                                                            unsigned long long epoch, int upper,
+                                                            const cplx* __restrict__ rhs, const int* __restrict__ perm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx* invk = reinterpret_cast<cplx*>(smem_raw);   // [SB][SB + 1]
-  cplx* blk = invk + SB * (SB + 1);                 // [SB][SB + 1]
   __shared__ cplx acc[SB];
-  __shared__ cplx xj[SB];
+  __shared__ cplx xj[2][SB];
   __shared__ int failed;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int tid = threadIdx.x;
+  const int r = tid >> 2, q = tid & 3;              // four threads per row of the block
   const int k = upper ? nblk - 1 - (int)blockIdx.x : (int)blockIdx.x;
   const int j0 = k * SB;
   const int nb = n - j0 < SB ? n - j0 : SB;
   unsigned long long* fl = flags + (upper ? nblk : 0);
   const cplx* inv_kk = inv + (int64_t)((upper ? nblk : 0) + k) * SB * SB;
-  for (int e = tid; e < SB * SB; e += 256) invk[(e / SB) * (SB + 1) + e % SB] = inv_kk[e];
-  if (tid < SB) acc[tid] = tid < nb ? x[j0 + tid] : make_double2(0.0, 0.0);
-  if (tid == 0) failed = 0;
-  __syncthreads();
   const int nsteps = upper ? nblk - 1 - k : k;
-  for (int sidx = 0; sidx < nsteps; ++sidx) {
+  auto load_block = [&](int sidx, cplx (&dst)[SB / 4]) {
     const int j = upper ? nblk - 1 - sidx : sidx;
     const int c0 = j * SB;
     const int ncol = n - c0 < SB ? n - c0 : SB;
-    // prefetch A[block k, block j] (does not depend on x_j)
-    for (int e = tid; e < SB * SB; e += 256) {
-      const int r = e / SB, c = e % SB;
-      blk[r * (SB + 1) + c] = (r < nb && c < ncol) ? A[(int64_t)(j0 + r) * n + c0 + c] : make_double2(0.0, 0.0);
+    const cplx* src = A + (int64_t)(j0 + r) * n + c0;
+#pragma unroll
+    for (int u = 0; u < SB / 4; ++u) {
+      const int c = q + 4 * u;
+      dst[u] = (r < nb && c < ncol) ? src[c] : make_double2(0.0, 0.0);
     }
-    if (tid == 0) {
-      const long long t0 = clock64();
-      while (*((volatile unsigned long long*)(fl + j)) != epoch) {
-        if (clock64() - t0 > 4000000000ll) {
-          failed = 1;
-          break;
+  };
+  cplx b0[SB / 4], b1[SB / 4];
+  if (nsteps > 0) load_block(0, b0);
+  for (int e = tid; e < SB * SB; e += 256) invk[(e / SB) * (SB + 1) + e % SB] = inv_kk[e];
+  cplx mine = make_double2(0.0, 0.0);               // threads with q == 0: the running right-hand side of row r
+  if (q == 0 && r < nb) mine = rhs ? rhs[perm ? perm[j0 + r] : j0 + r] : x[j0 + r];
+  if (tid == 0) failed = 0;
+  __syncthreads();
+  // one step with the block in `cur`, prefetching the following block into `nxt`
+  auto step = [&](int sidx, cplx (&cur)[SB / 4], cplx (&nxt)[SB / 4]) -> bool {
+    if (sidx + 1 < nsteps) load_block(sidx + 1, nxt);
+    const int j = upper ? nblk - 1 - sidx : sidx;
+    const int c0 = j * SB;
+    const int ncol = n - c0 < SB ? n - c0 : SB;
+    cplx* xs = xj[sidx & 1];
+    if (tid < 32) {
+      // warp 0 waits for x_j and fetches it (two values per lane)
+      if (tid == 0) {
+        const long long t0 = clock64();
+        while (*((volatile unsigned long long*)(fl + j)) != epoch) {
+          if (clock64() - t0 > 4000000000ll) {
+            failed = 1;
+            break;
+          }
         }
+        __threadfence();
       }
-      __threadfence();
+      __syncwarp();
+      xs[tid] = tid < ncol ? __ldcg(x + c0 + tid) : make_double2(0.0, 0.0);
+      xs[tid + 32] = tid + 32 < ncol ? __ldcg(x + c0 + tid + 32) : make_double2(0.0, 0.0);
     }
     __syncthreads();
-    if (failed) break;
-    if (tid < SB) xj[tid] = tid < ncol ? __ldcg(x + c0 + tid) : make_double2(0.0, 0.0);
-    __syncthreads();
-    // acc[r] -= sum_c blk[r][c] xj[c]: four threads per row
-    {
-      const int r = tid >> 2, q = tid & 3;
-      cplx s2 = make_double2(0.0, 0.0);
-#pragma unroll 4
-      for (int c = q; c < SB; c += 4) s2 = cadd(s2, cmul(blk[r * (SB + 1) + c], xj[c]));
-      s2.x += __shfl_xor_sync(0xffffffffu, s2.x, 1);
-      s2.y += __shfl_xor_sync(0xffffffffu, s2.y, 1);
-      s2.x += __shfl_xor_sync(0xffffffffu, s2.x, 2);
-      s2.y += __shfl_xor_sync(0xffffffffu, s2.y, 2);
-      if (q == 0) acc[r] = csub(acc[r], s2);
-    }
-    __syncthreads();
+    if (failed) return false;
+    cplx s2 = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int u = 0; u < SB / 4; ++u) s2 = cadd(s2, cmul(cur[u], xs[q + 4 * u]));
+    s2.x += __shfl_xor_sync(0xffffffffu, s2.x, 1);
+    s2.y += __shfl_xor_sync(0xffffffffu, s2.y, 1);
+    s2.x += __shfl_xor_sync(0xffffffffu, s2.x, 2);
+    s2.y += __shfl_xor_sync(0xffffffffu, s2.y, 2);
+    mine = csub(mine, s2);
+    return true;     // (xj is double-buffered: the next step's writes go to the other half, no second barrier)
+  };
+  bool ok = true;
+  for (int sidx = 0; sidx < nsteps && ok; sidx += 2) {
+    ok = step(sidx, b0, b1);
+    if (ok && sidx + 1 < nsteps) ok = step(sidx + 1, b1, b0);
   }
-  if (failed) {
+  if (!ok) {
     // sticky error word for the host (read by carc_relax / carc_lu_solve_blocks at their synchronisation points) and a
     // NaN block so that nothing downstream mistakes the unsolved right-hand side for a solution
     if (tid == 0) flags[2 * nblk] = 1ull;
@@ -465,8 +487,9 @@ __global__ void __launch_bounds__(256) tri_wavefront_kernel(const cplx* __restri
     if (tid < nb) x[j0 + tid] = make_double2(nan, nan);
     return;
   }
+  if (q == 0) acc[r] = mine;
+  __syncthreads();
   {
-    const int r = tid >> 2, q = tid & 3;
     cplx s2 = make_double2(0.0, 0.0);
 #pragma unroll 4
     for (int c = q; c < SB; c += 4) s2 = cadd(s2, cmul(invk[r * (SB + 1) + c], acc[c]));
@@ -479,8 +502,38 @@ __global__ void __launch_bounds__(256) tri_wavefront_kernel(const cplx* __restri
   __threadfence();
   __syncthreads();
   if (tid == 0) *((volatile unsigned long long*)(fl + k)) = epoch;
-  (void)lane;
-  (void)w;
+}
+
+// The row interchanges of a factorisation as ONE gather: perm[i] = the index of b that ends up in position i after
+// "for j: swap(b[j], b[piv[j]])".  Built once per factorisation (valid[0] says so; lu_invert_diagonal_blocks clears it)
+// by replaying the interchanges on an index array in shared memory; applying them to a vector one by one took 1.7 ms per
+// solve at n = 8192 (a single thread's 8192 dependent global round trips), as long as both substitutions together.
+__global__ void __launch_bounds__(1024) lu_perm_build_kernel(const int* __restrict__ piv, int n, int* __restrict__ valid,
+                                                             int* __restrict__ perm) {
+  extern __shared__ int perm_smem[];   // [n] indices, [n] pivots
+  if (*((volatile int*)valid)) return;
+  int* idx = perm_smem;
+  int* pv = perm_smem + n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    idx[i] = i;
+    pv[i] = piv[i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int j = 0; j < n; ++j) {
+      const int p = pv[j];
+      if (p != j) {
+        const int t = idx[j];
+        idx[j] = idx[p];
+        idx[p] = t;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) perm[i] = idx[i];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) *valid = 1;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1467,38 +1520,48 @@ int lu_solve(const cplx* LU, int n, const int* piv, cplx* x, cudaStream_t stream
 int lu_invert_diagonal_blocks(const cplx* LU, int n, cplx* inv, cudaStream_t stream) {
   const int nblk = (n + SB - 1) / SB;
   tri_invert_kernel<<<2 * nblk, SB, 0, stream>>>(LU, n, nblk, inv);
-  CARC_CHECK_CUDA(cudaMemsetAsync(inv + 2ll * nblk * SB * SB, 0, sizeof(cplx) * (2 * nblk + 2), stream));
+  // flag words and the "permutation built" word behind them
+  CARC_CHECK_CUDA(cudaMemsetAsync(inv + 2ll * nblk * SB * SB, 0, sizeof(cplx) * (2 * nblk + 3), stream));
   CARC_CHECK_CUDA(cudaGetLastError());
   return CARC_OK;
 }
 
-// inverse blocks followed by 2 nblk + 1 flag words (as complex slots: 16 bytes each, more than enough)
+// inverse blocks followed by 2 nblk + 1 flag words (as complex slots: 16 bytes each, more than enough), one slot for the
+// "permutation built" word and the gather permutation of the row interchanges (n ints)
 int64_t lu_inverse_blocks_elems(int n) {
   const int64_t nblk = (n + SB - 1) / SB;
-  return 2 * nblk * SB * SB + 2 * nblk + 2;
+  return 2 * nblk * SB * SB + 2 * nblk + 3 + (n + 3) / 4;
 }
 
 // x <- A^-1 x with the pre-inverted diagonal blocks; tmp: n complex
 int lu_solve_fast(const cplx* LU, int n, const int* piv, const cplx* inv, cplx* x, cplx* tmp, cudaStream_t stream) {
   const int nblk = (n + SB - 1) / SB;
-  lu_permute_kernel<<<1, 32, 0, stream>>>(x, piv, n);
   if (nblk <= sm_count()) {
     static std::atomic<unsigned long long> epoch_counter{0};
-    unsigned long long* flags = reinterpret_cast<unsigned long long*>(const_cast<cplx*>(inv) + 2ll * nblk * SB * SB);
+    cplx* tail = const_cast<cplx*>(inv) + 2ll * nblk * SB * SB;
+    unsigned long long* flags = reinterpret_cast<unsigned long long*>(tail);
+    int* perm_valid = reinterpret_cast<int*>(tail + 2 * nblk + 2);
+    int* perm = reinterpret_cast<int*>(tail + 2 * nblk + 3);
     const unsigned long long epoch = ++epoch_counter;
-    const size_t smem = sizeof(cplx) * 2 * SB * (SB + 1);
+    const size_t smem = sizeof(cplx) * SB * (SB + 1);
+    const size_t perm_smem = sizeof(int) * 2 * (size_t)n;
     static bool configured[16] = {false};
     int dev = 0;
     CARC_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev < 16 && !configured[dev]) {
       CARC_CHECK_CUDA(cudaFuncSetAttribute(tri_wavefront_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CARC_CHECK_CUDA(cudaFuncSetAttribute(lu_perm_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 9472 * (int)sizeof(int)));
       configured[dev] = true;
     }
-    tri_wavefront_kernel<<<nblk, 256, smem, stream>>>(LU, n, nblk, inv, x, flags, epoch, 0);
-    tri_wavefront_kernel<<<nblk, 256, smem, stream>>>(LU, n, nblk, inv, x, flags, epoch, 1);
+    // P b as a gather: the permutation is built on the first solve after a factorisation (a no-op launch afterwards)
+    lu_perm_build_kernel<<<1, 1024, perm_smem, stream>>>(piv, n, perm_valid, perm);
+    CARC_CHECK_CUDA(cudaMemcpyAsync(tmp, x, sizeof(cplx) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
+    tri_wavefront_kernel<<<nblk, 256, smem, stream>>>(LU, n, nblk, inv, x, flags, epoch, 0, tmp, perm);
+    tri_wavefront_kernel<<<nblk, 256, smem, stream>>>(LU, n, nblk, inv, x, flags, epoch, 1, nullptr, nullptr);
     CARC_CHECK_CUDA(cudaGetLastError());
     return CARC_OK;
   }
+  lu_permute_kernel<<<1, 32, 0, stream>>>(x, piv, n);
   for (int k = 0; k < nblk; ++k) {   // L y = P b : running rhs in x, y into tmp
     const int j0 = k * SB, nb = n - j0 < SB ? n - j0 : SB, r0 = j0 + nb;
     int blocks = (n - r0 + 7) / 8;
