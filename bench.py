@@ -796,12 +796,16 @@ def sweep_section(no_cpu):
     for D, chi in ((3, 6), (4, 8), (6, 8), (8, 8)):
         if D <= 6:
             # first pass at a size builds its per-layout offset tables and grows the allocator pools (3x the steady-state
-            # time at D = 3); a sweep runs hundreds of iterations at one size, so time the second pass
+            # time at D = 3); a sweep runs hundreds of iterations at one size, so that pass is not timed
             sweep_bench.device_iterations(chi, D, False)
-        r = sweep_bench.device_iterations(chi, D, False)
+        # two timed passes, the faster one reported: single passes show sporadic host-side stalls of 0.2 - 1.5 s (allocator
+        # / driver, not kernels) that land in a different phase each time
+        passes = [sweep_bench.device_iterations(chi, D, False) for _ in range(2)]
+        r = min(passes, key=lambda q: q["per_iteration"])
         rows.append({"D": D, "chi": chi, "gpu_s_per_iteration": r["per_iteration"], "minimize_s": r["minimize"] / 4,
                      "contract_s": r["contract"] / 4, "compress_s": r["compress"] / 4,
-                     "matvecs_per_minimize": r["mults"]})
+                     "matvecs_per_minimize": r["mults"],
+                     "passes_s_per_iteration": [q["per_iteration"] for q in passes], "statistic": "faster of two passes"})
     out = {"unit": "s per sweep iteration (minimize + contract + 8 corner compressions)", "sizes": rows}
     if not no_cpu:
         c = sweep_bench.cpu_iterations(6, 3)

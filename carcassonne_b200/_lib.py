@@ -87,6 +87,7 @@ SIGNATURES = {
     "carc_absorb_center_into_side": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "carc_form_stage1": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "carc_form_stage2": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp]),
+    "carc_stage3_form_matrix": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_int, c_vp, c_int, c_vp]),
     "carc_normalize_axis": (c_int, [c_vp, c_vp, c_int, c_int, c_int, C.c_double, c_vp, c_vp, c_vp, c_vp]),
     "carc_product_compressor": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_int, C.c_double, c_vp, c_vp, c_vp,
                                         c_vp]),

@@ -20,6 +20,7 @@
 // {2c + e : c = lane % 4}, i.e. every lane reads two adjacent complex numbers (32 contiguous bytes) per
 // operand row.  Any permutation of K is legal as long as A and B use the same one.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "carc_internal.h"
@@ -499,9 +500,28 @@ int zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, cplx alpha, const c
     CARC_CHECK_CUDA(cudaFuncSetAttribute(zgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_WS));
     configured[dev] = true;
   }
+  // CARC_ZGEMM_TRACE=1 (diagnostics): every product is timed with events and logged to stderr as
+  // "zgemm M N K batch opA opB splits ms" -- scripts/zgemm_trace.py sums the log by shape
+  static const bool trace = getenv("CARC_ZGEMM_TRACE") && atoi(getenv("CARC_ZGEMM_TRACE")) == 1;
   auto launch = [&](dim3 grid, const GemmParams& q) {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (trace) {
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, stream);
+    }
     if (ws) zgemm_kernel<true><<<grid, NTHREADS_WS, SMEM_BYTES_WS, stream>>>(q);
     else zgemm_kernel<false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(q);
+    if (trace) {
+      cudaEventRecord(e1, stream);
+      cudaEventSynchronize(e1);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      fprintf(stderr, "zgemm %lld %lld %lld %lld %d %d %d %.4f\n", (long long)M, (long long)N, (long long)K, (long long)batch, opA,
+              opB, q.splitk, ms);
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+    }
   };
   GemmParams p;
   p.A = A; p.B = B; p.C = C;

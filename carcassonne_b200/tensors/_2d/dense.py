@@ -267,16 +267,13 @@ def stage3FormMatrix(A, B, operator, accumulate_into=None):
     P, Q, Rr, S = c * dd, a * b, g * h, e * f
     n_out, n_in = P * Rr * d, Q * S * d
     out, _ = _target((n_out, n_in), accumulate_into)
-    if accumulate_into is None:
-        out.zero_()
-    if X == 0:        # an empty X slab (multi-GPU with more ranks than slow bond indices)
-        return accumulate_into if accumulate_into is not None else DeviceData(out)
-    G = _empty((P * Q, Rr * S))
-    gemm(OP_T, OP_N, P * Q, Rr * S, X, A._t, P * Q, B._t, Rr * S, G)
-    opd = DeviceData.fromArray(op.reshape(1, d * d))
-    # matrix[(P R s'), (Q S s)] += G[(P Q), (R S)] * O[s', s]   (a K = 1 product with scattered output)
-    gemm_scatter(OP_N, OP_N, P * Q * Rr * S, d * d, 1, G, 1, opd._t, d * d, out,
-                 ((P, Rr * d * n_in), (Q, S * d), (Rr, d * n_in), (S, d)), ((d, n_in), (d, 1)), beta=1.0)
+    if d > 4:
+        raise NotImplementedError("site operators beyond d = 4 are not supported on device")
+    opd = DeviceData.fromArray(op.reshape(d * d))
+    # one library call: G[(P Q),(R S)] = sum_X A B (DMMA GEMM), then matrix[(P R s'),(Q S s)] += G * O[s', s]
+    # (csrc/recipes.cu: carc_stage3_form_matrix); an empty X slab (more ranks than slow bond indices) contributes nothing
+    check(lib.carc_stage3_form_matrix(_ptr(A._t), _ptr(B._t), X, P, Q, Rr, S, _ptr(opd._t), d, _ptr(out),
+                                      int(accumulate_into is not None), _stream()))
     return accumulate_into if accumulate_into is not None else DeviceData(out)
 
 

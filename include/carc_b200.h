@@ -279,6 +279,11 @@ int carc_form_stage1(const void* corner, const int64_t* corner_shape, const void
                      int accumulate, void* stream);
 int carc_form_stage2(const void* stage1_a, const int64_t* a_shape, const void* stage1_b, const int64_t* b_shape, int half,
                      int slab_rank, int slab_world, void* out, int accumulate, void* stream);
+/* formMatrix of a stage-3 multiplier (dense.py:176-194): out[(P R s'), (Q S s)] (+)= sum_X A[X,(P Q)] B[X,(R S)] O[s', s]
+ * for the pre-joined halves A = [X, P, Q], B = [X, R, S] and a d x d (d <= 4) site operator on the device, row-major
+ * [s'][s].  accumulate == 0 zeroes `out` ((P R d) x (Q S d)) first; X == 0 (an empty slab) contributes nothing. */
+int carc_stage3_form_matrix(const void* A, const void* B, int64_t X, int64_t P, int64_t Q, int64_t R, int64_t S,
+                            const void* operator_dev, int d, void* out, int accumulate, void* stream);
 /* NDArrayData.normalizeAxis (data/__init__.py:263-301) for shape[axis] in 2..80: normalized (same shape as t) =
  * Q (U V^H) of the SVD of [(other axes), axis]; normalizer = conj(V S^-1 V^H), denormalizer = V S V^H, n x n
  * (S^-1 skipped where S <= dont_recip_under); sqrt_svals != 0 returns the square-root variants and no tensor.  Output
