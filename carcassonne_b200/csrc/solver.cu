@@ -1550,7 +1550,8 @@ int lu_solve_fast(const cplx* LU, int n, const int* piv, const cplx* inv, cplx* 
     CARC_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev < 16 && !configured[dev]) {
       CARC_CHECK_CUDA(cudaFuncSetAttribute(tri_wavefront_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CARC_CHECK_CUDA(cudaFuncSetAttribute(lu_perm_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 9472 * (int)sizeof(int)));
+      CARC_CHECK_CUDA(cudaFuncSetAttribute(lu_perm_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           2 * sm_count() * SB * (int)sizeof(int)));   // n <= sm_count() * SB on this path
       configured[dev] = true;
     }
     // P b as a gather: the permutation is built on the first solve after a factorisation (a no-op launch afterwards)
