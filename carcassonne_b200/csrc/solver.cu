@@ -401,8 +401,9 @@ __global__ void __launch_bounds__(256) tri_step_kernel(const cplx* __restrict__ 
 // last CTA's ~127 sequential steps were the whole 1.1 ms of a solve at n = 8192).  The inverse diagonal block sits in
 // shared memory from the start, so what remains on the critical path of a step is a 64-element read, two small products
 // and the flag hand-off.  All CTAs are co-resident (nblk <= 148 => n <= 9472); waits are bounded and raise a sticky error
-// flag instead of hanging.  `rhs` / `perm`: the right-hand side is read as rhs[perm[i]] (the row interchanges of the
-// factorisation as one gather, see lu_perm_build_kernel), or in place from x when rhs is null.
+// flag instead of hanging.  Out of place: the right-hand side is read as rhs[perm[i]] (perm: the row interchanges of the
+// factorisation as one gather, see lu_perm_build_kernel; null = identity) and the solution is published in x, so the two
+// substitutions of a solve ping-pong between the caller's vector and a scratch vector without a copy.
 __global__ void __launch_bounds__(256) tri_wavefront_kernel(const cplx* __restrict__ A, int n, int nblk,
                                                             const cplx* __restrict__ inv, cplx* __restrict__ x,
                                                             unsigned long long* __restrict__ flags,
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(256) tri_wavefront_kernel(const cplx* __restri
   if (nsteps > 0) load_block(0, b0);
   for (int e = tid; e < SB * SB; e += 256) invk[(e / SB) * (SB + 1) + e % SB] = inv_kk[e];
   cplx mine = make_double2(0.0, 0.0);               // threads with q == 0: the running right-hand side of row r
-  if (q == 0 && r < nb) mine = rhs ? rhs[perm ? perm[j0 + r] : j0 + r] : x[j0 + r];
+  if (q == 0 && r < nb) mine = rhs[perm ? perm[j0 + r] : j0 + r];
   if (tid == 0) failed = 0;
   __syncthreads();
   // one step with the block in `cur`, prefetching the following block into `nxt`
@@ -1556,9 +1557,9 @@ int lu_solve_fast(const cplx* LU, int n, const int* piv, const cplx* inv, cplx* 
     }
     // P b as a gather: the permutation is built on the first solve after a factorisation (a no-op launch afterwards)
     lu_perm_build_kernel<<<1, 1024, perm_smem, stream>>>(piv, n, perm_valid, perm);
-    CARC_CHECK_CUDA(cudaMemcpyAsync(tmp, x, sizeof(cplx) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
-    tri_wavefront_kernel<<<nblk, 256, smem, stream>>>(LU, n, nblk, inv, x, flags, epoch, 0, tmp, perm);
-    tri_wavefront_kernel<<<nblk, 256, smem, stream>>>(LU, n, nblk, inv, x, flags, epoch, 1, nullptr, nullptr);
+    // L y = P b: b = x (gathered), y -> tmp;  U x = y: y = tmp, x -> x
+    tri_wavefront_kernel<<<nblk, 256, smem, stream>>>(LU, n, nblk, inv, tmp, flags, epoch, 0, x, perm);
+    tri_wavefront_kernel<<<nblk, 256, smem, stream>>>(LU, n, nblk, inv, x, flags, epoch, 1, tmp, nullptr);
     CARC_CHECK_CUDA(cudaGetLastError());
     return CARC_OK;
   }
