@@ -432,22 +432,39 @@ __global__ void __launch_bounds__(s3_max_threads(NRT), 1) stage3_kernel(const S3
   }
 }
 
-// out[i] = sum_slots partial[slot][i]  (fixed order -> deterministic)
-__global__ void __launch_bounds__(256) s3_reduce_kernel(const cplx* __restrict__ partial, cplx* __restrict__ out,
-                                                        int64_t n, int slots, int accumulate) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// out[i] = sum_slots partial[slot][i] in a fixed order (deterministic, the same on every rank).  32 elements per CTA,
+// 8 threads per element: thread (e, g) sums the slots g, g + 8, ... (independent loads, 512 contiguous bytes per warp),
+// the eight partial sums are combined in order 0..7.  (One thread per element walking all 150 - 600 slots was a
+// latency chain on 11 CTAs: 124 us per matvec at D = 6, chi = 8, a third of the fused kernel's own time.)
+// (no __restrict__: the multi-GPU path reduces in place, out == partial)
+__global__ void __launch_bounds__(256) s3_reduce_kernel(const cplx* partial, cplx* out, int64_t n, int slots, int accumulate) {
+  __shared__ double sre[8][32], sim[8][32];
+  const int e = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + e;
   double re = 0.0, im = 0.0;
-  for (int s = 0; s < slots; ++s) {
-    const cplx v = partial[(int64_t)s * n + i];
-    re += v.x;
-    im += v.y;
+  if (i < n) {
+#pragma unroll 4
+    for (int s = g; s < slots; s += 8) {
+      const cplx v = partial[(int64_t)s * n + i];
+      re += v.x;
+      im += v.y;
+    }
   }
-  if (accumulate) {
-    re += out[i].x;
-    im += out[i].y;
+  sre[g][e] = re;
+  sim[g][e] = im;
+  __syncthreads();
+  if (g == 0 && i < n) {
+#pragma unroll
+    for (int q = 1; q < 8; ++q) {
+      re += sre[q][e];
+      im += sim[q][e];
+    }
+    if (accumulate) {
+      re += out[i].x;
+      im += out[i].y;
+    }
+    out[i] = make_double2(re, im);
   }
-  out[i] = make_double2(re, im);
 }
 
 struct S3Config {
@@ -728,8 +745,14 @@ int stage3_apply(const Stage3Plan* plan, int P, int Q, int R, int S, int d, cons
     CARC_REQUIRE(workspace_elems >= (int64_t)kf.slots * n, CARC_ERR_VALUE, "stage3: workspace too small");
     int rc = stage3f_launch(plan, kf, P, Q, R, S, v, workspace, stream);
     if (rc) return rc;
-    if (comm) return comm_allreduce(comm, workspace, kf.slots, n, out, stream);
-    s3_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(workspace, out, n, kf.slots, 0);
+    if (comm) {
+      // slot sum in place (into slot 0: an element's eight readers and its one writer sit in the same CTA, behind a
+      // barrier), then the sum over ranks reads ONE slot per rank
+      s3_reduce_kernel<<<(unsigned)((n + 31) / 32), 256, 0, stream>>>(workspace, workspace, n, kf.slots, 0);
+      CARC_CHECK_CUDA(cudaGetLastError());
+      return comm_allreduce(comm, workspace, 1, n, out, stream);
+    }
+    s3_reduce_kernel<<<(unsigned)((n + 31) / 32), 256, 0, stream>>>(workspace, out, n, kf.slots, 0);
     CARC_CHECK_CUDA(cudaGetLastError());
     return CARC_OK;
   }
@@ -764,8 +787,12 @@ int stage3_apply(const Stage3Plan* plan, int P, int Q, int R, int S, int d, cons
   }
   if (rc) return rc;
   // multi-GPU: the slot sum and the sum over ranks are one kernel reading the peers' exchange buffers over NVLink
-  if (comm) return comm_allreduce(comm, workspace, k.slots, n, out, stream);
-  s3_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(workspace, out, n, k.slots, 0);
+  if (comm) {
+    s3_reduce_kernel<<<(unsigned)((n + 31) / 32), 256, 0, stream>>>(workspace, workspace, n, k.slots, 0);
+    CARC_CHECK_CUDA(cudaGetLastError());
+    return comm_allreduce(comm, workspace, 1, n, out, stream);
+  }
+  s3_reduce_kernel<<<(unsigned)((n + 31) / 32), 256, 0, stream>>>(workspace, out, n, k.slots, 0);
   CARC_CHECK_CUDA(cudaGetLastError());
   return CARC_OK;
 }
