@@ -798,8 +798,8 @@ def sweep_section(no_cpu):
             # first pass at a size builds its per-layout offset tables and grows the allocator pools (3x the steady-state
             # time at D = 3); a sweep runs hundreds of iterations at one size, so that pass is not timed
             sweep_bench.device_iterations(chi, D, False)
-        # two timed passes, the faster one reported: single passes show sporadic host-side stalls of 0.2 - 1.5 s (allocator
-        # / driver, not kernels) that land in a different phase each time
+        # two timed passes, the faster one reported and both listed (a host-driven loop of ~1 300 launches and ~100
+        # synchronisations per iteration at the small sizes is sensitive to whatever else the host is doing)
         passes = [sweep_bench.device_iterations(chi, D, False) for _ in range(2)]
         r = min(passes, key=lambda q: q["per_iteration"])
         rows.append({"D": D, "chi": chi, "gpu_s_per_iteration": r["per_iteration"], "minimize_s": r["minimize"] / 4,

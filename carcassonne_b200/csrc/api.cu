@@ -14,7 +14,8 @@ struct carc_operator {
   int P, Q, R, S, d;
   std::vector<carc::Stage3Term> terms;
   carc::Stage3Plan* plan = nullptr;
-  cplx* workspace = nullptr;
+  cplx* workspace = nullptr;    // partial sums: from the stream-ordered pool on the first apply (see stage3_plan_upload)
+  cudaStream_t workspace_stream = nullptr;
   int64_t workspace_elems = 0;
   int force_path = 0;
   bool finalized = false;
@@ -209,7 +210,6 @@ int carc_operator_finalize(carc_operator* op) {
   int prc = carc::stage3_plan_create(op->terms.data(), nt, &op->plan);
   if (prc) return prc;
   op->workspace_elems = carc::stage3_workspace_elems(nt, op->P, op->Q, op->R, op->S, op->d, Xmax);
-  CARC_CHECK_CUDA(cudaMalloc(&op->workspace, sizeof(cplx) * (op->workspace_elems > 0 ? op->workspace_elems : 1)));
   op->finalized = true;
   return CARC_OK;
 }
@@ -323,8 +323,19 @@ int carc_operator_apply(carc_operator* op, const void* v, void* out, void* strea
   if (op->kind == 1)
     return carc::dense_matvec(op->matrix, op->n, op->n, op->n, (const cplx*)v, (cplx*)out, make_double2(1.0, 0.0),
                               make_double2(0.0, 0.0), S(stream));
+  keep_pool_memory();
+  cudaStream_t st = S(stream);
+  int rc = carc::stage3_plan_upload(op->plan, st);
+  if (rc) return rc;
+  if (!op->workspace) {
+    CARC_CHECK_CUDA(cudaMallocAsync((void**)&op->workspace, sizeof(cplx) * (op->workspace_elems > 0 ? op->workspace_elems : 1), st));
+    op->workspace_stream = st;
+  } else if (op->workspace_stream != st) {
+    CARC_CHECK_CUDA(cudaStreamSynchronize(op->workspace_stream));
+    op->workspace_stream = st;
+  }
   return carc::stage3_apply(op->plan, op->P, op->Q, op->R, op->S, op->d, (const cplx*)v, (cplx*)out, op->workspace,
-                            op->workspace_elems, op->force_path, S(stream), op->comm);
+                            op->workspace_elems, op->force_path, st, op->comm);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -370,7 +381,7 @@ int carc_operator_set_comm(carc_operator* op, carc_comm* comm) {
 int carc_operator_destroy(carc_operator* op) {
   if (!op) return CARC_OK;
   carc::stage3_plan_destroy(op->plan);
-  if (op->workspace) cudaFree(op->workspace);
+  if (op->workspace) cudaFreeAsync(op->workspace, op->workspace_stream);
   delete op;
   return CARC_OK;
 }

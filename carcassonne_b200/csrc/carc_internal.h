@@ -76,10 +76,12 @@ struct Stage3Group {
 struct Stage3Plan {
   std::vector<Stage3Term> terms;     // sorted by group
   std::vector<Stage3Group> groups;
-  Stage3Term* terms_dev;
-  Stage3Group* groups_dev;
+  Stage3Term* terms_dev = nullptr;   // device copies: allocated from the stream-ordered pool and uploaded by
+  Stage3Group* groups_dev = nullptr; // stage3_plan_upload on the first apply, freed on the stream that used them last
+  cudaStream_t dev_stream = nullptr;
 };
 int stage3_plan_create(const Stage3Term* terms, int nterms, Stage3Plan** out);
+int stage3_plan_upload(Stage3Plan* plan, cudaStream_t stream);
 void stage3_plan_host(const Stage3Term* terms, int nterms, Stage3Plan* plan);
 void stage3_plan_destroy(Stage3Plan* plan);
 double stage3_executed_flops(const Stage3Plan* plan, int P, int Q, int R, int S, int d, int column_blocks = 1);

@@ -694,21 +694,38 @@ void stage3_plan_host(const Stage3Term* terms, int nterms, Stage3Plan* plan) {
 int stage3_plan_create(const Stage3Term* terms, int nterms, Stage3Plan** out) {
   Stage3Plan* plan = new Stage3Plan();
   stage3_plan_host(terms, nterms, plan);
-  if (nterms > 0) {
-    CARC_CHECK_CUDA(cudaMalloc(&plan->terms_dev, sizeof(Stage3Term) * nterms));
-    CARC_CHECK_CUDA(cudaMemcpy(plan->terms_dev, plan->terms.data(), sizeof(Stage3Term) * nterms, cudaMemcpyHostToDevice));
-    CARC_CHECK_CUDA(cudaMalloc(&plan->groups_dev, sizeof(Stage3Group) * plan->groups.size()));
-    CARC_CHECK_CUDA(cudaMemcpy(plan->groups_dev, plan->groups.data(), sizeof(Stage3Group) * plan->groups.size(),
-                               cudaMemcpyHostToDevice));
-  }
   *out = plan;
+  return CARC_OK;
+}
+
+// Device copies of the term / star tables, made on the stream of the first apply.  Stream-ordered allocation
+// (cudaMallocAsync / cudaFreeAsync from the default pool, whose release threshold the library raises): a sweep creates and
+// drops two operators per minimisation, and cudaMalloc / cudaFree -- which synchronise the device and, with tens of GB
+// mapped, took 0.06 - 0.8 s now and then (scripts/stall_probe.py) -- were the sporadic stalls of a sweep iteration.
+int stage3_plan_upload(Stage3Plan* plan, cudaStream_t stream) {
+  if (plan->terms.empty()) return CARC_OK;
+  if (plan->terms_dev) {
+    if (plan->dev_stream != stream) {
+      // used on another stream before: order this stream after everything queued there (rare)
+      CARC_CHECK_CUDA(cudaStreamSynchronize(plan->dev_stream));
+      plan->dev_stream = stream;
+    }
+    return CARC_OK;
+  }
+  CARC_CHECK_CUDA(cudaMallocAsync((void**)&plan->terms_dev, sizeof(Stage3Term) * plan->terms.size(), stream));
+  CARC_CHECK_CUDA(cudaMallocAsync((void**)&plan->groups_dev, sizeof(Stage3Group) * plan->groups.size(), stream));
+  CARC_CHECK_CUDA(cudaMemcpyAsync(plan->terms_dev, plan->terms.data(), sizeof(Stage3Term) * plan->terms.size(),
+                                  cudaMemcpyHostToDevice, stream));
+  CARC_CHECK_CUDA(cudaMemcpyAsync(plan->groups_dev, plan->groups.data(), sizeof(Stage3Group) * plan->groups.size(),
+                                  cudaMemcpyHostToDevice, stream));
+  plan->dev_stream = stream;
   return CARC_OK;
 }
 
 void stage3_plan_destroy(Stage3Plan* plan) {
   if (!plan) return;
-  if (plan->terms_dev) cudaFree(plan->terms_dev);
-  if (plan->groups_dev) cudaFree(plan->groups_dev);
+  if (plan->terms_dev) cudaFreeAsync(plan->terms_dev, plan->dev_stream);
+  if (plan->groups_dev) cudaFreeAsync(plan->groups_dev, plan->dev_stream);
   delete plan;
 }
 

@@ -9,6 +9,24 @@ from carcassonne_b200 import synthetic
 D, chi, reps = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 6
 records = []
 
+# every library call timed on the host: calls slower than 50 ms are reported by name (which C entry does a stall sit in?)
+from carcassonne_b200 import _lib
+slow_calls = []
+
+def _timed(name, fn):
+    def wrapper(*args):
+        t0 = time.perf_counter()
+        rc = fn(*args)
+        dt = time.perf_counter() - t0
+        if dt > 0.05:
+            slow_calls.append((name, round(dt, 3)))
+        return rc
+    return wrapper
+
+for _name in _lib.SIGNATURES:
+    setattr(_lib.lib, _name, _timed(_name, getattr(_lib.lib, _name)))
+_sync = torch.cuda.synchronize
+
 def snap():
     st = torch.cuda.memory_stats()
     free, total = torch.cuda.mem_get_info()
@@ -43,4 +61,5 @@ for key, rep, it, dt, a, b in records:
     m = med.get((key, it), dt)
     if rep > 0 and dt > 4 * m:
         print("STALL rep %d %s[%d]: %.3f s (median %.4f)  before %s  after %s" % (rep, key, it, dt, m, a, b))
+print("library calls slower than 50 ms:", slow_calls)
 print("total per rep:", [round(sum(r[3] for r in records if r[1] == rep), 3) for rep in range(reps)])
