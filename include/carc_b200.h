@@ -230,9 +230,11 @@ int carc_lu_factor(void* A, int n, void* piv_dev, int* singular_out, void* strea
  *   1  a pivot was <= 0 or not finite: A is garbage, factor a fresh copy with carc_lu_factor. */
 int carc_cholesky_factor_as_lu(void* A, int n, void* piv_dev, double hermitian_tolerance, int* status_out, void* stream);
 int carc_lu_solve(const void* LU, int n, const void* piv_dev, void* x, void* stream);
-/* The same solve for many right-hand sides in sequence (one per Arnoldi multiplication): invert the 128 x 128 diagonal
- * blocks of L and U once into inv_blocks (carc_lu_inverse_blocks_elems(n) complex numbers), after which every block
- * step of the substitution is a single launch. */
+/* The same solve for many right-hand sides in sequence (one per Arnoldi multiplication): invert the 64 x 64 diagonal
+ * blocks of L and U once into inv_blocks (carc_lu_inverse_blocks_elems(n) complex numbers: the inverted blocks, the
+ * hand-off flags of the wavefront substitutions, and the row interchanges of the factorisation as one gather
+ * permutation, built on the first solve).  Each substitution is then ONE launch; call carc_lu_invert_diagonal_blocks
+ * again whenever LU / piv_dev are overwritten by a new factorisation. */
 int64_t carc_lu_inverse_blocks_elems(int n);
 int carc_lu_invert_diagonal_blocks(const void* LU, int n, void* inv_blocks, void* stream);
 int carc_lu_solve_blocks(const void* LU, int n, const void* piv_dev, const void* inv_blocks, void* x, void* stream);
