@@ -314,6 +314,7 @@ int carc_stage3f_describe(int nterms, int P, int Q, int R, int S, int d, int64_t
     out[o++] = k.PB;
     out[o++] = k.RB;
   }
+  if (out_len >= o + 1) out[o++] = k.ws;   // consumer-warp slots of the warp-specialised kernel (0: symmetric kernel)
   return CARC_OK;
 }
 int carc_operator_num_groups(const carc_operator* op) { return (op && op->plan) ? (int)op->plan->groups.size() : -1; }

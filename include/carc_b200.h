@@ -150,6 +150,10 @@ int carc_stage3_path(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax
  * All output arrays hold nterms entries. */
 int carc_stage3_describe_stars(int nterms, const int32_t* a_id, const int32_t* b_id, const int64_t* X, int32_t* n_groups,
                                int32_t* group_kind, int32_t* group_first, int32_t* group_count, int32_t* sorted_term);
+/* Host-side launch plan of the folded fused kernel for one shape (no device call; tests/test_stage3f_plan.py reads it):
+ * out[0..15] = NPT, NRT, Q4, NSB, G, nstA, nstB, QS, BSTR, b_whole, consumer threads, ctas, slots, smem bytes, slotA, slotB;
+ * then sb_tile0[17], sb_cta0[17], cta_sb[160], cta_sl[160]; then, if out_len allows, PB, RB (output row / column blocks)
+ * and the consumer-warp slots of the warp-specialised kernel (8 or 12; 0 = symmetric kernel).  out_len >= 370. */
 int carc_stage3f_describe(int nterms, int P, int Q, int R, int S, int d, int64_t Xmax, int32_t* out, int out_len);
 int carc_operator_num_terms(const carc_operator* op);
 /* cmac count the reference's CostTracker assigns to one apply (data/cost_tracker.py:17-21) */

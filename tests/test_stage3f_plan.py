@@ -12,7 +12,7 @@ SMEM_LIMIT = 227 * 1024
 
 
 def describe(P, Q, R, S, X, nterms=9):
-    buf = np.full(16 + 17 + 17 + 160 + 160 + 2, -7, dtype=np.int32)
+    buf = np.full(16 + 17 + 17 + 160 + 160 + 3, -7, dtype=np.int32)
     rc = _lib.lib.carc_stage3f_describe(nterms, P, Q, R, S, 2, X, buf.ctypes.data, len(buf))
     if rc == _lib.ERR_UNSUPPORTED:
         return None
@@ -25,6 +25,7 @@ def describe(P, Q, R, S, X, nterms=9):
     k["cta_sb"] = buf[50:210]
     k["cta_sl"] = buf[210:370]
     k["PB"], k["RB"] = int(buf[370]), int(buf[371])
+    k["ws"] = int(buf[372])
     return k
 
 
@@ -35,6 +36,10 @@ def check_plan(P, Q, R, S, X):
     assert 1 <= k["ctas"] <= 148 and k["slots"] == k["ctas"] * k["G"]
     assert k["threads"] == 32 * k["G"] * k["NPT"] and k["threads"] <= (256 if k["NRT"] >= 7 else 384)
     assert k["smem"] <= SMEM_LIMIT
+    # warp-specialised launch: 8 consumer-warp slots (232 registers) where a warp accumulates 7 - 8 column tiles, 12 (152
+    # registers) otherwise, plus one producer warpgroup that serves at most four groups; the consumers fit their slots
+    assert k["ws"] == (8 if k["NRT"] >= 7 else 12) and k["G"] <= 4 and k["G"] * k["NPT"] <= k["ws"]
+    assert (k["ws"] + 4) * 32 <= 512 and 32 * (k["ws"] * (232 if k["ws"] == 8 else 152) + 4 * 40) <= 65536
     # the output in PB x RB blocks of at most NPT x NRT tiles (one block when P, R <= 64)
     assert k["NPT"] == -(-(-(-P // 8)) // k["PB"]) and k["NRT"] == -(-(-(-R // 8)) // k["RB"]) and k["Q4"] == -(-Q // 4)
     assert k["NRT"] <= 8 and (k["PB"], k["RB"]) == (1, 1) or P > 64 or R > 64 or k["PB"] >= 1
