@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcarc_b200.so")
+# CARC_B200_LIB: another build of the same library (A/B measurements of a kernel change); default: the in-tree build
+LIB_PATH = os.environ.get("CARC_B200_LIB") or os.path.join(_HERE, "libcarc_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

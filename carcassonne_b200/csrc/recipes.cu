@@ -170,30 +170,43 @@ __global__ void __launch_bounds__(256) diagonal_shift_kernel(cplx* G, int n, dou
 // blocked device LU spends ~0.4 ms per factorisation on grid barriers there (two cooperative panel launches), this kernel
 // a few dozen microseconds.  A is left untouched.
 constexpr int SMALL_LU_MAX = 118;
+// Two CTA-wide barriers per column: the pivot candidates of column k + 1 are tracked while column k's update runs (one
+// warp per row; lane 0 of a row's warp computes that row's new entry in column k + 1) and every warp reduces the 32
+// per-warp candidates itself; the column scaling is folded into the update (the row's warp computes its multiplier).
+// The back substitution runs on 128 threads only.  (The first version had five barriers per column and two per
+// substitution step: 153 us at n = 108, 16 such solves per sweep iteration at D = 3.)
 __global__ void __launch_bounds__(1024, 1) small_lu_solve_kernel(const cplx* __restrict__ A, int n, cplx* __restrict__ x) {
   extern __shared__ __align__(16) unsigned char small_lu_raw[];
   const int ld = n + 1;
   cplx* M = reinterpret_cast<cplx*>(small_lu_raw);
   cplx* rhs = M + (size_t)n * ld;
-  __shared__ double wval[32];
-  __shared__ int widx[32];
-  __shared__ int prow;
+  __shared__ double wval[2][32];
+  __shared__ int widx[2][32];
+  __shared__ cplx sol[128];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int e = tid; e < n * n; e += blockDim.x) M[(e / n) * ld + e % n] = A[e];
   for (int i = tid; i < n; i += blockDim.x) rhs[i] = x[i];
   __syncthreads();
-  for (int k = 0; k < n; ++k) {
-    // pivot search in column k
+  if (lane == 0) {   // candidates of column 0
     double best = -1.0;
     int arg = n;
-    for (int i = k + tid; i < n; i += blockDim.x) {
-      const cplx v = M[i * ld + k];
+    for (int i = warp; i < n; i += 32) {
+      const cplx v = M[i * ld];
       const double a = fabs(v.x) + fabs(v.y);
       if (a > best) {
         best = a;
         arg = i;
       }
     }
+    wval[0][warp] = best;
+    widx[0][warp] = arg;
+  }
+  __syncthreads();
+  for (int k = 0; k < n; ++k) {
+    const int par = k & 1;
+    // the pivot of column k: largest |re| + |im|, first on ties (every warp reduces the per-warp candidates)
+    double best = wval[par][lane];
+    int arg = widx[par][lane];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const double ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -203,27 +216,7 @@ __global__ void __launch_bounds__(1024, 1) small_lu_solve_kernel(const cplx* __r
         arg = oa;
       }
     }
-    if (lane == 0) {
-      wval[warp] = best;
-      widx[warp] = arg;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      best = lane < (int)(blockDim.x >> 5) ? wval[lane] : -1.0;
-      arg = lane < (int)(blockDim.x >> 5) ? widx[lane] : n;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
-        if (ob > best || (ob == best && oa < arg)) {
-          best = ob;
-          arg = oa;
-        }
-      }
-      if (lane == 0) prow = arg < n ? arg : k;
-    }
-    __syncthreads();
-    const int p = prow;
+    const int p = arg < n ? arg : k;
     if (p != k) {
       for (int j = tid; j < n; j += blockDim.x) {
         const cplx t = M[k * ld + j];
@@ -239,23 +232,28 @@ __global__ void __launch_bounds__(1024, 1) small_lu_solve_kernel(const cplx* __r
     }
     const cplx piv = M[k * ld + k];
     const double den = piv.x * piv.x + piv.y * piv.y;
-    if (den > 0.0) {
-      const cplx inv = make_double2(piv.x / den, -piv.y / den);
-      for (int i = k + 1 + tid; i < n; i += blockDim.x) {
-        const cplx v = M[i * ld + k];
-        M[i * ld + k] = make_double2(v.x * inv.x - v.y * inv.y, v.x * inv.y + v.y * inv.x);
-      }
-    }
-    __syncthreads();
-    // trailing update and the forward substitution of the right-hand side
-    for (int i = k + 1 + warp; i < n; i += (int)(blockDim.x >> 5)) {
-      const cplx l = M[i * ld + k];
+    const cplx inv = den > 0.0 ? make_double2(piv.x / den, -piv.y / den) : make_double2(1.0, 0.0);
+    // scale, trailing update, forward substitution of the right-hand side, candidates of column k + 1
+    double cbest = -1.0;
+    int carg = n;
+    for (int i = k + 1 + warp; i < n; i += 32) {
+      const cplx v = M[i * ld + k];
+      const cplx l = make_double2(v.x * inv.x - v.y * inv.y, v.x * inv.y + v.y * inv.x);
+      __syncwarp();
+      if (lane == 0) M[i * ld + k] = l;
       for (int j = k + 1 + lane; j < n; j += 32) {
         const cplx u = M[k * ld + j];
         cplx c = M[i * ld + j];
         c.x -= l.x * u.x - l.y * u.y;
         c.y -= l.x * u.y + l.y * u.x;
         M[i * ld + j] = c;
+        if (j == k + 1) {
+          const double a = fabs(c.x) + fabs(c.y);
+          if (a > cbest) {
+            cbest = a;
+            carg = i;
+          }
+        }
       }
       if (lane == 0) {
         const cplx u = rhs[k];
@@ -263,25 +261,27 @@ __global__ void __launch_bounds__(1024, 1) small_lu_solve_kernel(const cplx* __r
         rhs[i].y -= l.x * u.y + l.y * u.x;
       }
     }
+    if (lane == 0) {
+      wval[par ^ 1][warp] = cbest;
+      widx[par ^ 1][warp] = carg;
+    }
     __syncthreads();
   }
-  // back substitution with U
+  // back substitution with U on 128 threads (n <= 118): x_k is computed by every thread, thread i < k updates its entry
+  if (tid >= 128) return;
   for (int k = n - 1; k >= 0; --k) {
-    if (tid == 0) {
-      const cplx piv = M[k * ld + k], b = rhs[k];
-      const double den = piv.x * piv.x + piv.y * piv.y;
-      rhs[k] = make_double2((b.x * piv.x + b.y * piv.y) / den, (b.y * piv.x - b.x * piv.y) / den);
-    }
-    __syncthreads();
-    const cplx xk = rhs[k];
-    for (int i = tid; i < k; i += blockDim.x) {
-      const cplx u = M[i * ld + k];
-      rhs[i].x -= u.x * xk.x - u.y * xk.y;
-      rhs[i].y -= u.x * xk.y + u.y * xk.x;
+    const cplx piv = M[k * ld + k], b = rhs[k];
+    const double den = piv.x * piv.x + piv.y * piv.y;
+    const cplx xk = make_double2((b.x * piv.x + b.y * piv.y) / den, (b.y * piv.x - b.x * piv.y) / den);
+    if (tid == k) sol[k] = xk;
+    if (tid < k) {
+      const cplx u = M[tid * ld + k];
+      rhs[tid].x -= u.x * xk.x - u.y * xk.y;
+      rhs[tid].y -= u.x * xk.y + u.y * xk.x;
     }
     __syncthreads();
   }
-  for (int i = tid; i < n; i += blockDim.x) x[i] = rhs[i];
+  if (tid < n) x[tid] = sol[tid];
 }
 
 int small_lu_solve(const cplx* A, int n, cplx* x, cudaStream_t stream) {
@@ -290,7 +290,7 @@ int small_lu_solve(const cplx* A, int n, cplx* x, cudaStream_t stream) {
   int dev = 0;
   CARC_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev < 16 && !configured[dev]) {
-    CARC_CHECK_CUDA(cudaFuncSetAttribute(small_lu_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    CARC_CHECK_CUDA(cudaFuncSetAttribute(small_lu_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     configured[dev] = true;
   }
   small_lu_solve_kernel<<<1, 1024, smem, stream>>>(A, n, x);
