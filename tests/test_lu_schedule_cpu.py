@@ -84,3 +84,19 @@ def test_blocked_schedule_matches_scipy(n, OB):
     ref_lu, ref_piv = sla.lu_factor(a)
     assert np.array_equal(piv, ref_piv)
     assert np.abs(lu - ref_lu).max() <= 1e-10 * np.abs(ref_lu).max()
+
+
+def test_interchanges_as_one_gather():
+    """lu_perm_build_kernel: replaying "swap(b[j], b[piv[j]])" on an index array gives the gather permutation that
+    lu_solve_fast folds into the first substitution's right-hand-side read (csrc/solver.cu)."""
+    rng = np.random.default_rng(3)
+    for n in (1, 7, 64, 300):
+        piv = np.array([rng.integers(j, n) for j in range(n)])
+        b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        expect = b.copy()
+        for j in range(n):
+            expect[[j, piv[j]]] = expect[[piv[j], j]]
+        perm = np.arange(n)
+        for j in range(n):
+            perm[[j, piv[j]]] = perm[[piv[j], j]]
+        assert np.array_equal(b[perm], expect)
